@@ -1,0 +1,92 @@
+// 32-bit limb primitives with an explicit carry flag.
+//
+// Device build (sm_100a): one PTX instruction each (add.cc / madc.lo.cc ... -> IADD3.X / IMAD / IMAD.WIDE
+// carry chains in SASS).  Host build (RIPP_HOSTSIM, used only by tests/hostsim to unit-test the
+// *same* limb sequences on a CPU-only box): the carry flag is a thread-local variable.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RIPP_HD __host__ __device__ __forceinline__
+#define RIPP_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define RIPP_HD inline
+#define RIPP_HD_NOINLINE
+#endif
+
+#define RIPP_DEFCONST(name, n, ...)                \
+  RIPP_HD uint32_t name(int i) {                   \
+    const uint32_t a_[n] = {__VA_ARGS__};          \
+    return a_[i];                                  \
+  }
+
+namespace ripp {
+namespace limb {
+
+#if defined(__CUDA_ARCH__)
+
+RIPP_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+RIPP_HD uint32_t mul_hi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+
+#define RIPP_ASM3(fn, ins)                                                            \
+  RIPP_HD void fn(uint32_t& r, uint32_t a, uint32_t b) {                              \
+    asm volatile(ins " %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));                      \
+  }
+#define RIPP_ASM4(fn, ins)                                                            \
+  RIPP_HD void fn(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) {                  \
+    asm volatile(ins " %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));          \
+  }
+RIPP_ASM3(add_cc, "add.cc.u32")
+RIPP_ASM3(addc_cc, "addc.cc.u32")
+RIPP_ASM3(addc, "addc.u32")
+RIPP_ASM3(sub_cc, "sub.cc.u32")
+RIPP_ASM3(subc_cc, "subc.cc.u32")
+RIPP_ASM3(subc, "subc.u32")
+RIPP_ASM4(mad_lo_cc, "mad.lo.cc.u32")
+RIPP_ASM4(madc_lo_cc, "madc.lo.cc.u32")
+RIPP_ASM4(mad_hi_cc, "mad.hi.cc.u32")
+RIPP_ASM4(madc_hi_cc, "madc.hi.cc.u32")
+RIPP_ASM4(madc_lo, "madc.lo.u32")
+RIPP_ASM4(madc_hi, "madc.hi.u32")
+#undef RIPP_ASM3
+#undef RIPP_ASM4
+
+#else  // host emulation of the same primitives
+
+inline thread_local uint32_t cc_ = 0;
+
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline void add_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a + b;
+  r = (uint32_t)t;
+  cc_ = (uint32_t)(t >> 32);
+}
+inline void addc_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a + b + cc_;
+  r = (uint32_t)t;
+  cc_ = (uint32_t)(t >> 32);
+}
+inline void addc(uint32_t& r, uint32_t a, uint32_t b) { r = a + b + cc_; }
+inline void sub_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a - b;
+  r = (uint32_t)t;
+  cc_ = (uint32_t)(t >> 32) & 1u;
+}
+inline void subc_cc(uint32_t& r, uint32_t a, uint32_t b) {
+  uint64_t t = (uint64_t)a - b - cc_;
+  r = (uint32_t)t;
+  cc_ = (uint32_t)(t >> 32) & 1u;
+}
+inline void subc(uint32_t& r, uint32_t a, uint32_t b) { r = a - b - cc_; }
+inline void mad_lo_cc(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) { add_cc(r, mul_lo(a, b), c); }
+inline void madc_lo_cc(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) { addc_cc(r, mul_lo(a, b), c); }
+inline void mad_hi_cc(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) { add_cc(r, mul_hi(a, b), c); }
+inline void madc_hi_cc(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) { addc_cc(r, mul_hi(a, b), c); }
+inline void madc_lo(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) { addc(r, mul_lo(a, b), c); }
+inline void madc_hi(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) { addc(r, mul_hi(a, b), c); }
+
+#endif
+
+}  // namespace limb
+}  // namespace ripp
