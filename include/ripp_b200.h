@@ -1,0 +1,115 @@
+/* ripp_b200 -- C ABI of the B200-native backend for RIPP's inner-pairing-product hot path.
+ *
+ * This is the drop-in boundary: a thin Rust crate implements the reference's
+ * traits by calling these entry points (binding sketch in INTEGRATION.md).  Each function cites
+ * the reference interface it replaces (paths relative to the arkworks-rs/ripp checkout).
+ * There is no CPU fallback: every compute entry point launches CUDA kernels or fails.
+ *
+ * Data layout (all little-endian, packed, no padding):
+ *   Fr   : 8  x u32  Montgomery form, R = 2^256   (== ark-ff Fp256 limbs, [u64; 4])
+ *   Fq   : 12 x u32  Montgomery form, R = 2^384   (== ark-ff Fp384 limbs, [u64; 6])
+ *   Fq2  : c0, c1
+ *   G1 affine   : x, y            (96 B)   identity = all-zero bytes
+ *   G2 affine   : x, y over Fq2   (192 B)  identity = all-zero bytes
+ *   G1 Jacobian : X, Y, Z         (144 B)  == ark-ec short_weierstrass::Projective; identity Z = 0
+ *   G2 Jacobian : X, Y, Z         (288 B)
+ *   GT   : Fq12 = c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2 (each Fq2) (576 B) == ark PairingOutput.0
+ *
+ * Status: 0 = ok; negative = ripp_status.  ripp_last_error_string() describes the last failure
+ * on the calling thread.  Entry points taking `_dev` pointers expect device memory of the
+ * context's GPU and are asynchronous on the context's stream unless they return host data.
+ */
+#ifndef RIPP_B200_H
+#define RIPP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ripp_status {
+  RIPP_OK = 0,
+  RIPP_ERR_LEN_MISMATCH = -1, /* InnerProductError::MessageLengthInvalid, inner_products/src/lib.rs:18-38 */
+  RIPP_ERR_NOT_POW2 = -2,     /* gipa.rs:116-122,140-146 */
+  RIPP_ERR_CUDA = -3,
+  RIPP_ERR_ARG = -4,
+  RIPP_ERR_INNER_PRODUCT = -5, /* InnerProductArgumentError::InnerProductInvalid, ip_proofs/src/lib.rs:22-25 */
+  RIPP_ERR_NO_DEVICE = -6
+} ripp_status;
+
+typedef struct ripp_ctx ripp_ctx;
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* One context per GPU / per process rank.  `device` is the CUDA ordinal. */
+int ripp_ctx_create(int device, ripp_ctx** out);
+void ripp_ctx_destroy(ripp_ctx* ctx);
+const char* ripp_last_error_string(void);
+/* Blocks until all work queued on the context's stream has finished. */
+int ripp_ctx_sync(ripp_ctx* ctx);
+/* cudaStream_t of the context (as void*), for callers that time with CUDA events. */
+void* ripp_ctx_stream(ripp_ctx* ctx);
+/* Run on a caller-owned stream instead (e.g. torch's current stream, so that NCCL collectives and
+ * CUDA-event timing issued by the host framework are ordered with this library's kernels). */
+int ripp_ctx_set_stream(ripp_ctx* ctx, void* cuda_stream);
+/* Number of kernels launched by this context so far (bench.py's gpu_launches). */
+uint64_t ripp_ctx_launch_count(ripp_ctx* ctx);
+
+/* ---- device memory (residency; SURVEY.md §8b "residency") -------------------------------- */
+int ripp_dev_alloc(ripp_ctx* ctx, size_t bytes, void** dev_out);
+int ripp_dev_free(ripp_ctx* ctx, void* dev);
+int ripp_dev_upload(ripp_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+int ripp_dev_download(ripp_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
+
+/* ---- L1: inner products (inner_products/src/lib.rs) --------------------------------------- */
+/* PairingInnerProduct::inner_product (lib.rs:56-74) == cfg_multi_pairing (lib.rs:77-116):
+ * out = prod_i e(left[i], right[i]).  Host pointers, Jacobian inputs exactly as arkworks holds
+ * them; normalisation (lib.rs:80-81) happens on the GPU.  n_left != n_right -> LEN_MISMATCH. */
+int ripp_pairing_ip(ripp_ctx* ctx, const void* g1_jac, size_t n_left, const void* g2_jac, size_t n_right,
+                    void* gt_out);
+/* Same product over packed affine host inputs (sipp/src/lib.rs:221-224 product_of_pairings). */
+int ripp_pairing_ip_affine(ripp_ctx* ctx, const void* g1_aff, size_t n_left, const void* g2_aff, size_t n_right,
+                           void* gt_out);
+/* Device-resident variant: affine device vectors, result written to device memory (576 B). */
+int ripp_pairing_ip_dev(ripp_ctx* ctx, const void* g1_aff_dev, const void* g2_aff_dev, size_t n, void* gt_out_dev);
+/* Sharded variant for multi-GPU: product of Miller-loop values of this rank's
+ * slice WITHOUT the final exponentiation (one Fq12 partial, device memory) ... */
+int ripp_miller_partial_dev(ripp_ctx* ctx, const void* g1_aff_dev, const void* g2_aff_dev, size_t n,
+                            void* fq12_out_dev);
+/* ... and the combine: multiply `count` partials (gathered from all ranks, device memory) and
+ * apply the single shared final exponentiation (lib.rs:115). */
+int ripp_gt_combine_dev(ripp_ctx* ctx, const void* fq12_partials_dev, size_t count, void* gt_out_dev);
+
+/* ---- element-wise scalar multiplication (kernel K8) ------------------------------------------ */
+/* out[i] = scalars[i] * points[i] with distinct scalars: the `a[i] * r^i` / `ck[i] * r^-i` maps of
+ * groth16_aggregation.rs:118-131 and `a[i] * r[i]` of sipp/src/lib.rs:61-65,189-193.
+ * points == NULL means the standard generator for every i (tipa/mod.rs:153-160 SRS powers and the
+ * synthetic inputs of SURVEY.md §8d).  Scalars are Fr in Montgomery form; inputs/outputs affine,
+ * device memory. */
+int ripp_g1_scale_dev(ripp_ctx* ctx, const void* g1_aff_dev, const void* fr_dev, size_t n, void* g1_aff_out_dev);
+int ripp_g2_scale_dev(ripp_ctx* ctx, const void* g2_aff_dev, const void* fr_dev, size_t n, void* g2_aff_out_dev);
+
+/* ---- diagnostics --------------------------------------------------------------------------- */
+/* Element-wise primitive ops on device, used by the GPU parity tests to pin the PTX limb layer:
+ * op in ripp_test_op; a, b, r are HOST arrays of n elements of the op's operand size. */
+typedef enum ripp_test_op {
+  RIPP_OP_FQ_MUL = 0, RIPP_OP_FQ_ADD, RIPP_OP_FQ_SUB, RIPP_OP_FQ_INV, RIPP_OP_FQ_HALF,
+  RIPP_OP_FR_MUL, RIPP_OP_FR_ADD, RIPP_OP_FR_SUB, RIPP_OP_FR_INV,
+  RIPP_OP_FQ2_MUL, RIPP_OP_FQ2_SQR, RIPP_OP_FQ2_INV,
+  RIPP_OP_FQ12_MUL, RIPP_OP_FQ12_SQR, RIPP_OP_FQ12_INV, RIPP_OP_FQ12_CYC_SQR, RIPP_OP_FQ12_FROB1,
+  RIPP_OP_FINAL_EXP, RIPP_OP_MILLER,       /* MILLER: a = G1 affine, b = G2 affine, r = Fq12 */
+  RIPP_OP_G1_ADD, RIPP_OP_G1_DBL, RIPP_OP_G2_ADD, RIPP_OP_G2_DBL /* affine in, affine out */
+} ripp_test_op;
+int ripp_test_elementwise(ripp_ctx* ctx, int op, const void* a, const void* b, void* r, size_t n);
+
+/* Integer-pipe microbenchmark that defines the roofline denominator:
+ * kind 0 = independent IMAD.WIDE.U32 chains (one MAC32 each), 1 = 32-bit IMAD chains,
+ * 2 = carry-chained mad.lo.cc/madc.hi.cc pairs.  Returns multiply-accumulates per second
+ * and the average kernel time in ms. */
+int ripp_bench_imad(ripp_ctx* ctx, int kind, int iters, double* macs_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIPP_B200_H */

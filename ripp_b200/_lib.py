@@ -1,0 +1,186 @@
+"""ctypes binding of libripp_b200.so (include/ripp_b200.h).  No CPU fallback: importing works
+without a GPU (so the symbol table can be checked), but creating a context without one raises."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libripp_b200.so")
+
+RIPP_OK = 0
+RIPP_ERR_LEN_MISMATCH = -1
+RIPP_ERR_NOT_POW2 = -2
+RIPP_ERR_CUDA = -3
+RIPP_ERR_ARG = -4
+RIPP_ERR_INNER_PRODUCT = -5
+RIPP_ERR_NO_DEVICE = -6
+
+TEST_OPS = [
+    "FQ_MUL", "FQ_ADD", "FQ_SUB", "FQ_INV", "FQ_HALF",
+    "FR_MUL", "FR_ADD", "FR_SUB", "FR_INV",
+    "FQ2_MUL", "FQ2_SQR", "FQ2_INV",
+    "FQ12_MUL", "FQ12_SQR", "FQ12_INV", "FQ12_CYC_SQR", "FQ12_FROB1",
+    "FINAL_EXP", "MILLER",
+    "G1_ADD", "G1_DBL", "G2_ADD", "G2_DBL",
+]
+TEST_OP_ID = {n: i for i, n in enumerate(TEST_OPS)}
+
+
+class RippError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("ripp_b200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+class LengthMismatch(RippError):
+    """InnerProductError::MessageLengthInvalid (inner_products/src/lib.rs:18-38)."""
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libripp_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                "ripp_b200 has no CPU fallback"
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        L.ripp_last_error_string.restype = ctypes.c_char_p
+        L.ripp_ctx_stream.restype = ctypes.c_void_p
+        L.ripp_ctx_launch_count.restype = ctypes.c_uint64
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != RIPP_OK:
+        msg = lib().ripp_last_error_string().decode()
+        if status == RIPP_ERR_LEN_MISMATCH:
+            raise LengthMismatch(status, msg)
+        raise RippError(status, msg)
+
+
+def _p(a):
+    """void* of a host numpy array / device pointer int / None."""
+    if a is None:
+        return ctypes.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return ctypes.c_void_p(a.ctypes.data)
+    if isinstance(a, DeviceBuffer):
+        return ctypes.c_void_p(a.ptr)
+    return ctypes.c_void_p(int(a))
+
+
+class DeviceBuffer:
+    """RAII handle on device memory owned by a Context (`ripp_vec_*` of SURVEY.md §8b)."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.nbytes = ctx, nbytes
+        p = ctypes.c_void_p()
+        check(lib().ripp_dev_alloc(ctx.handle, ctypes.c_size_t(nbytes), ctypes.byref(p)))
+        self.ptr = p.value
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host)
+        assert host.nbytes <= self.nbytes
+        check(lib().ripp_dev_upload(self.ctx.handle, _p(self.ptr), _p(host), ctypes.c_size_t(host.nbytes)))
+        return self
+
+    def download(self, shape, dtype=np.uint32, offset=0):
+        out = np.empty(shape, dtype=dtype)
+        assert offset + out.nbytes <= self.nbytes
+        check(lib().ripp_dev_download(self.ctx.handle, _p(out), _p(self.ptr + offset), ctypes.c_size_t(out.nbytes)))
+        return out
+
+    def free(self):
+        if self.ptr:
+            check(lib().ripp_dev_free(self.ctx.handle, _p(self.ptr)))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, device=0):
+        h = ctypes.c_void_p()
+        check(lib().ripp_ctx_create(int(device), ctypes.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            lib().ripp_ctx_destroy(self.handle)
+            self.handle = None
+
+    def sync(self):
+        check(lib().ripp_ctx_sync(self.handle))
+
+    @property
+    def stream(self):
+        return lib().ripp_ctx_stream(self.handle)
+
+    def set_stream(self, cuda_stream):
+        check(lib().ripp_ctx_set_stream(self.handle, ctypes.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    @property
+    def launches(self):
+        return int(lib().ripp_ctx_launch_count(self.handle))
+
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, host):
+        host = np.ascontiguousarray(host)
+        return DeviceBuffer(self, host.nbytes).upload(host)
+
+    # ---- L1 -------------------------------------------------------------------------------
+    def pairing_ip(self, g1_jac, g2_jac):
+        """Host Jacobian arrays (n, 36) / (n, 72) uint32 -> GT (144,) uint32."""
+        out = np.empty(144, dtype=np.uint32)
+        check(lib().ripp_pairing_ip(self.handle, _p(g1_jac), ctypes.c_size_t(len(g1_jac)), _p(g2_jac),
+                                    ctypes.c_size_t(len(g2_jac)), _p(out)))
+        return out
+
+    def pairing_ip_affine(self, g1, g2):
+        out = np.empty(144, dtype=np.uint32)
+        check(lib().ripp_pairing_ip_affine(self.handle, _p(g1), ctypes.c_size_t(len(g1)), _p(g2),
+                                           ctypes.c_size_t(len(g2)), _p(out)))
+        return out
+
+    def pairing_ip_dev(self, g1_dev, g2_dev, n, out_dev):
+        check(lib().ripp_pairing_ip_dev(self.handle, _p(g1_dev), _p(g2_dev), ctypes.c_size_t(n), _p(out_dev)))
+
+    def miller_partial_dev(self, g1_dev, g2_dev, n, out_dev):
+        check(lib().ripp_miller_partial_dev(self.handle, _p(g1_dev), _p(g2_dev), ctypes.c_size_t(n), _p(out_dev)))
+
+    def gt_combine_dev(self, partials_dev, count, out_dev):
+        check(lib().ripp_gt_combine_dev(self.handle, _p(partials_dev), ctypes.c_size_t(count), _p(out_dev)))
+
+    def g1_scale_dev(self, pts_dev, fr_dev, n, out_dev):
+        check(lib().ripp_g1_scale_dev(self.handle, _p(pts_dev), _p(fr_dev), ctypes.c_size_t(n), _p(out_dev)))
+
+    def g2_scale_dev(self, pts_dev, fr_dev, n, out_dev):
+        check(lib().ripp_g2_scale_dev(self.handle, _p(pts_dev), _p(fr_dev), ctypes.c_size_t(n), _p(out_dev)))
+
+    # ---- diagnostics ----------------------------------------------------------------------
+    def test_elementwise(self, op, a, b, out_words):
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        n = a.shape[0]
+        b = None if b is None else np.ascontiguousarray(b, dtype=np.uint32)
+        r = np.empty((n, out_words), dtype=np.uint32)
+        check(lib().ripp_test_elementwise(self.handle, TEST_OP_ID[op], _p(a), _p(b), _p(r), ctypes.c_size_t(n)))
+        return r
+
+    def bench_imad(self, kind, iters=2048):
+        macs, ms = ctypes.c_double(), ctypes.c_double()
+        check(lib().ripp_bench_imad(self.handle, int(kind), int(iters), ctypes.byref(macs), ctypes.byref(ms)))
+        return macs.value, ms.value

@@ -27,7 +27,7 @@ struct Jac {
   RIPP_HD Jac neg() const { return {x, -y, z}; }
 
   // dbl-2009-l (a = 0): 2M + 5S
-  RIPP_HD Jac dbl() const {
+  RIPP_FN Jac dbl() const {
     F A = x.sqr(), B = y.sqr(), C = B.sqr();
     F D = ((x + B).sqr() - A - C).dbl();
     F E = A.dbl() + A;
@@ -39,7 +39,7 @@ struct Jac {
     return r;
   }
   // madd-2007-bl: 7M + 4S
-  RIPP_HD Jac add_mixed(const Aff<F>& q) const {
+  RIPP_FN Jac add_mixed(const Aff<F>& q) const {
     if (q.is_inf()) return *this;
     if (is_inf()) return {q.x, q.y, F::one()};
     F Z1Z1 = z.sqr();
@@ -63,7 +63,7 @@ struct Jac {
     return r;
   }
   // add-2007-bl: 11M + 5S
-  RIPP_HD Jac add(const Jac& q) const {
+  RIPP_FN Jac add(const Jac& q) const {
     if (q.is_inf()) return *this;
     if (is_inf()) return q;
     F Z1Z1 = z.sqr(), Z2Z2 = q.z.sqr();
@@ -99,7 +99,7 @@ struct Jac {
 // MSB-first double-and-add; `bits` little-endian 32-bit words of the canonical scalar, nbits significant.
 // Control flow depends only on the scalar => uniform across a warp when the scalar is shared.
 template <class F>
-RIPP_HD Jac<F> scalar_mul(const Aff<F>& p, const uint32_t* bits, int nbits) {
+RIPP_FN Jac<F> scalar_mul(const Aff<F>& p, const uint32_t* bits, int nbits) {
   Jac<F> acc = Jac<F>::inf();
   for (int i = nbits - 1; i >= 0; i--) {
     acc = acc.dbl();

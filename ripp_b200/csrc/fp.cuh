@@ -93,9 +93,16 @@ RIPP_HD void mont_redc(uint32_t* X, uint32_t* Y) {
   addc(Y[N - 1], Y[N - 1], 0);
 }
 
+#if defined(RIPP_HOSTSIM)
+inline thread_local uint64_t mul_count_[2] = {0, 0};  // [Fr, Fq] products, tests only (op-count model)
+#endif
+
 template <class P>
 RIPP_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   constexpr int N = P::N;
+#if defined(RIPP_HOSTSIM)
+  mul_count_[N == 12]++;
+#endif
   static_assert(N % 2 == 0, "even limb count");
   uint32_t ev[N], od[N];
 #pragma unroll
@@ -220,7 +227,7 @@ struct alignas(16) Fp {
     return *this * o;
   }
   // a^(p-2); returns 0 for a = 0
-  RIPP_HD Fp inv() const {
+  RIPP_FN Fp inv() const {
     Fp r = one();
     for (int i = P::BITS - 1; i >= 0; i--) {
       r = r.sqr();

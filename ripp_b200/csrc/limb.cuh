@@ -8,10 +8,12 @@
 
 #if defined(__CUDACC__)
 #define RIPP_HD __host__ __device__ __forceinline__
-#define RIPP_HD_NOINLINE __host__ __device__ __noinline__
+// Functions at and above the Fq2-product level are real calls on the device: fully inlining a
+// Miller loop (~10^5 instructions) makes ptxas run for hours and thrashes the instruction cache.
+#define RIPP_FN __host__ __device__ __noinline__
 #else
 #define RIPP_HD inline
-#define RIPP_HD_NOINLINE
+#define RIPP_FN inline
 #endif
 
 #define RIPP_DEFCONST(name, n, ...)                \

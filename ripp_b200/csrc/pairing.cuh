@@ -19,7 +19,7 @@ struct Line {
 };
 
 // T <- 2T, returns the tangent line at T.  3 M2 + 6 S2.
-RIPP_HD Line dbl_step(G2Proj& r) {
+RIPP_FN Line dbl_step(G2Proj& r) {
   Fq2 a = (r.x * r.y).half();
   Fq2 b = r.y.sqr();
   Fq2 c = r.z.sqr();
@@ -38,7 +38,7 @@ RIPP_HD Line dbl_step(G2Proj& r) {
 }
 
 // T <- T + Q, returns the chord through T and Q.  11 M2 + 2 S2.
-RIPP_HD Line add_step(G2Proj& r, const G2Aff& q) {
+RIPP_FN Line add_step(G2Proj& r, const G2Aff& q) {
   Fq2 theta = r.y - q.y * r.z;
   Fq2 lambda = r.x - q.x * r.z;
   Fq2 c = theta.sqr();
@@ -59,7 +59,7 @@ RIPP_HD void ell(Fq12& f, const Line& l, const G1Aff& p) {
 }
 
 // f_{|x|,Q}(P), conjugated because x < 0; 1 if either point is the identity.
-RIPP_HD Fq12 miller_loop(const G1Aff& p, const G2Aff& q) {
+RIPP_FN Fq12 miller_loop(const G1Aff& p, const G2Aff& q) {
   Fq12 f = Fq12::one();
   if (p.is_inf() || q.is_inf()) return f;
   G2Proj t = {q.x, q.y, Fq2::one()};
@@ -76,7 +76,7 @@ RIPP_HD Fq12 miller_loop(const G1Aff& p, const G2Aff& q) {
 }
 
 // a^x for a in the cyclotomic subgroup (x = -|x|)
-RIPP_HD Fq12 exp_by_x(const Fq12& a) {
+RIPP_FN Fq12 exp_by_x(const Fq12& a) {
   Fq12 r = a;
   for (int i = 62; i >= 0; i--) {
     r = r.cyclotomic_sqr();
@@ -85,7 +85,7 @@ RIPP_HD Fq12 exp_by_x(const Fq12& a) {
   return r.conj();
 }
 
-RIPP_HD Fq12 final_exponentiation(const Fq12& f) {
+RIPP_FN Fq12 final_exponentiation(const Fq12& f) {
   // easy part: f^((p^6 - 1)(p^2 + 1))
   Fq12 r = f.conj() * f.inv();
   r = r.frob<2>() * r;

@@ -1,0 +1,523 @@
+// ripp_b200: CUDA kernels (sm_100a) + C ABI (include/ripp_b200.h).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ripp_b200.h"
+#include "pairing.cuh"
+
+using namespace ripp;
+
+// ------------------------------------------------------------------------------------------------
+// context / errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+struct ripp_ctx {
+  int device;
+  cudaStream_t stream;
+  cudaStream_t own_stream;
+  uint64_t launches;
+  // scratch (grown on demand)
+  void* scratch[4];
+  size_t scratch_bytes[4];
+};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(RIPP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + \
+                                     std::to_string(__LINE__));                                          \
+  } while (0)
+#define OK(call)              \
+  do {                        \
+    int s_ = (call);          \
+    if (s_ != RIPP_OK) return s_; \
+  } while (0)
+#define LAUNCHED(ctx)        \
+  do {                       \
+    (ctx)->launches++;       \
+    CU(cudaGetLastError());  \
+  } while (0)
+
+static int scratch(ripp_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (ctx->scratch_bytes[slot] < bytes) {
+    if (ctx->scratch[slot]) CU(cudaFree(ctx->scratch[slot]));
+    ctx->scratch[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
+    CU(cudaMalloc(&ctx->scratch[slot], bytes));
+    ctx->scratch_bytes[slot] = bytes;
+  }
+  *out = ctx->scratch[slot];
+  return RIPP_OK;
+}
+
+extern "C" const char* ripp_last_error_string(void) { return g_err.c_str(); }
+
+extern "C" int ripp_ctx_create(int device, ripp_ctx** out) {
+  if (!out) return fail(RIPP_ERR_ARG, "null out");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(RIPP_ERR_NO_DEVICE, std::string("no CUDA device (ripp_b200 has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(RIPP_ERR_ARG, "bad device ordinal");
+  CU(cudaSetDevice(device));
+  ripp_ctx* c = new ripp_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  *out = c;
+  return RIPP_OK;
+}
+
+extern "C" void ripp_ctx_destroy(ripp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 4; i++)
+    if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" int ripp_ctx_sync(ripp_ctx* ctx) {
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RIPP_OK;
+}
+extern "C" void* ripp_ctx_stream(ripp_ctx* ctx) { return (void*)ctx->stream; }
+extern "C" int ripp_ctx_set_stream(ripp_ctx* ctx, void* s) {
+  if (!ctx) return fail(RIPP_ERR_ARG, "null ctx");
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+  return RIPP_OK;
+}
+extern "C" uint64_t ripp_ctx_launch_count(ripp_ctx* ctx) { return ctx->launches; }
+
+extern "C" int ripp_dev_alloc(ripp_ctx* ctx, size_t bytes, void** dev_out) {
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMalloc(dev_out, bytes ? bytes : 16));
+  return RIPP_OK;
+}
+extern "C" int ripp_dev_free(ripp_ctx* ctx, void* dev) {
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaFree(dev));
+  return RIPP_OK;
+}
+extern "C" int ripp_dev_upload(ripp_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes) {
+  CU(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RIPP_OK;
+}
+extern "C" int ripp_dev_download(ripp_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+  CU(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RIPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: normalisation (inner_products/src/lib.rs:80-81 normalize_batch)
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void k_normalize(const Jac<F>* __restrict__ in, Aff<F>* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Jac<F> p = in[i];
+  Aff<F> a;
+  if (p.is_inf())
+    a = Aff<F>::inf();
+  else if (p.z == F::one())
+    a = {p.x, p.y};
+  else
+    a = p.to_affine();
+  out[i] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: multi-Miller loop.  One (G1, G2) pair per thread; the 32 Miller values of a warp are
+// multiplied with a shuffle butterfly and lane 0 writes one Fq12 partial per warp.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fq12 shfl_xor_fq12(const Fq12& a, int m) {
+  Fq12 r;
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
+  uint32_t* pr = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < 144; i++) pr[i] = __shfl_xor_sync(0xffffffffu, pa[i], m);
+  return r;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_miller(const G1Aff* __restrict__ ps, const G2Aff* __restrict__ qs, size_t n,
+                                                 Fq12* __restrict__ partials) {
+  size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+  Fq12 f = Fq12::one();
+  if (i < n) f = miller_loop(ps[i], qs[i]);
+#pragma unroll 1
+  for (int m = 16; m >= 1; m >>= 1) f = f * shfl_xor_fq12(f, m);
+  if ((threadIdx.x & 31) == 0) partials[i >> 5] = f;
+}
+
+// out[t] = prod in[t*R .. min(m, t*R+R))
+__global__ void k_fq12_reduce(const Fq12* __restrict__ in, size_t m, int R, Fq12* __restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * R;
+  if (lo >= m) return;
+  size_t hi = lo + R < m ? lo + R : m;
+  Fq12 f = in[lo];
+  for (size_t j = lo + 1; j < hi; j++) f = f * in[j];
+  out[t] = f;
+}
+
+__global__ void k_final_exp(const Fq12* __restrict__ in, Fq12* __restrict__ out, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = final_exponentiation(in[t]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: element-wise scalar multiplication with distinct scalars (K8)
+// ------------------------------------------------------------------------------------------------
+template <class F, bool GEN>
+__global__ void __launch_bounds__(64) k_scale(const Aff<F>* __restrict__ pts, const Fr* __restrict__ sc, size_t n,
+                                              Aff<F>* __restrict__ out, Aff<F> gen) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = sc[i].from_mont();
+  Aff<F> p = GEN ? gen : pts[i];
+  out[i] = scalar_mul(p, s.v, 255).to_affine();
+}
+
+template <class F>
+static int scale_dev(ripp_ctx* ctx, const void* pts, const void* sc, size_t n, void* out, const Aff<F>& gen) {
+  if (!ctx || (n && (!sc || !out))) return fail(RIPP_ERR_ARG, "null argument");
+  if (n == 0) return RIPP_OK;
+  CU(cudaSetDevice(ctx->device));
+  unsigned blocks = (unsigned)((n + 63) / 64);
+  if (pts)
+    k_scale<F, false><<<blocks, 64, 0, ctx->stream>>>((const Aff<F>*)pts, (const Fr*)sc, n, (Aff<F>*)out, gen);
+  else
+    k_scale<F, true><<<blocks, 64, 0, ctx->stream>>>(nullptr, (const Fr*)sc, n, (Aff<F>*)out, gen);
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}
+extern "C" int ripp_g1_scale_dev(ripp_ctx* ctx, const void* pts, const void* sc, size_t n, void* out) {
+  return scale_dev<Fq>(ctx, pts, sc, n, out, g1_generator());
+}
+extern "C" int ripp_g2_scale_dev(ripp_ctx* ctx, const void* pts, const void* sc, size_t n, void* out) {
+  return scale_dev<Fq2>(ctx, pts, sc, n, out, g2_generator());
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics
+// ------------------------------------------------------------------------------------------------
+template <class TA, class TB, class TR, class Fn>
+__global__ void k_elementwise(const TA* a, const TB* b, TR* r, size_t n, Fn fn) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) r[i] = fn(a[i], b[i]);
+}
+
+template <class TA, class TB, class TR, class Fn>
+static int run_elementwise(ripp_ctx* ctx, const void* a, const void* b, void* r, size_t n, Fn fn) {
+  void *da, *db, *dr;
+  OK(scratch(ctx, 0, n * sizeof(TA), &da));
+  OK(scratch(ctx, 1, n * sizeof(TB), &db));
+  OK(scratch(ctx, 2, n * sizeof(TR), &dr));
+  CU(cudaMemcpyAsync(da, a, n * sizeof(TA), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(db, b ? b : a, n * (b ? sizeof(TB) : (sizeof(TA) < sizeof(TB) ? sizeof(TA) : sizeof(TB))),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  int block = 64;
+  k_elementwise<TA, TB, TR, Fn><<<(unsigned)((n + block - 1) / block), block, 0, ctx->stream>>>(
+      (const TA*)da, (const TB*)db, (TR*)dr, n, fn);
+  LAUNCHED(ctx);
+  CU(cudaMemcpyAsync(r, dr, n * sizeof(TR), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RIPP_OK;
+}
+
+struct OpFqMul { __device__ Fq operator()(const Fq& a, const Fq& b) const { return a * b; } };
+struct OpFqAdd { __device__ Fq operator()(const Fq& a, const Fq& b) const { return a + b; } };
+struct OpFqSub { __device__ Fq operator()(const Fq& a, const Fq& b) const { return a - b; } };
+struct OpFqInv { __device__ Fq operator()(const Fq& a, const Fq&) const { return a.inv(); } };
+struct OpFqHalf { __device__ Fq operator()(const Fq& a, const Fq&) const { return a.half(); } };
+struct OpFrMul { __device__ Fr operator()(const Fr& a, const Fr& b) const { return a * b; } };
+struct OpFrAdd { __device__ Fr operator()(const Fr& a, const Fr& b) const { return a + b; } };
+struct OpFrSub { __device__ Fr operator()(const Fr& a, const Fr& b) const { return a - b; } };
+struct OpFrInv { __device__ Fr operator()(const Fr& a, const Fr&) const { return a.inv(); } };
+struct OpFq2Mul { __device__ Fq2 operator()(const Fq2& a, const Fq2& b) const { return a * b; } };
+struct OpFq2Sqr { __device__ Fq2 operator()(const Fq2& a, const Fq2&) const { return a.sqr(); } };
+struct OpFq2Inv { __device__ Fq2 operator()(const Fq2& a, const Fq2&) const { return a.inv(); } };
+struct OpFq12Mul { __device__ Fq12 operator()(const Fq12& a, const Fq12& b) const { return a * b; } };
+struct OpFq12Sqr { __device__ Fq12 operator()(const Fq12& a, const Fq12&) const { return a.sqr(); } };
+struct OpFq12Inv { __device__ Fq12 operator()(const Fq12& a, const Fq12&) const { return a.inv(); } };
+struct OpFq12Cyc { __device__ Fq12 operator()(const Fq12& a, const Fq12&) const { return a.cyclotomic_sqr(); } };
+struct OpFq12Frob1 { __device__ Fq12 operator()(const Fq12& a, const Fq12&) const { return a.frob<1>(); } };
+struct OpFinalExp { __device__ Fq12 operator()(const Fq12& a, const Fq12&) const { return final_exponentiation(a); } };
+struct OpMiller { __device__ Fq12 operator()(const G1Aff& a, const G2Aff& b) const { return miller_loop(a, b); } };
+template <class F>
+struct OpAdd {
+  __device__ Aff<F> operator()(const Aff<F>& a, const Aff<F>& b) const {
+    return Jac<F>::from_affine(a).add(Jac<F>::from_affine(b)).to_affine();
+  }
+};
+template <class F>
+struct OpDbl {
+  __device__ Aff<F> operator()(const Aff<F>& a, const Aff<F>&) const { return Jac<F>::from_affine(a).dbl().to_affine(); }
+};
+
+extern "C" int ripp_test_elementwise(ripp_ctx* ctx, int op, const void* a, const void* b, void* r, size_t n) {
+  if (!ctx || !a || !r) return fail(RIPP_ERR_ARG, "null argument");
+  if (n == 0) return RIPP_OK;
+  CU(cudaSetDevice(ctx->device));
+  switch (op) {
+    case RIPP_OP_FQ_MUL: return run_elementwise<Fq, Fq, Fq>(ctx, a, b, r, n, OpFqMul());
+    case RIPP_OP_FQ_ADD: return run_elementwise<Fq, Fq, Fq>(ctx, a, b, r, n, OpFqAdd());
+    case RIPP_OP_FQ_SUB: return run_elementwise<Fq, Fq, Fq>(ctx, a, b, r, n, OpFqSub());
+    case RIPP_OP_FQ_INV: return run_elementwise<Fq, Fq, Fq>(ctx, a, b, r, n, OpFqInv());
+    case RIPP_OP_FQ_HALF: return run_elementwise<Fq, Fq, Fq>(ctx, a, b, r, n, OpFqHalf());
+    case RIPP_OP_FR_MUL: return run_elementwise<Fr, Fr, Fr>(ctx, a, b, r, n, OpFrMul());
+    case RIPP_OP_FR_ADD: return run_elementwise<Fr, Fr, Fr>(ctx, a, b, r, n, OpFrAdd());
+    case RIPP_OP_FR_SUB: return run_elementwise<Fr, Fr, Fr>(ctx, a, b, r, n, OpFrSub());
+    case RIPP_OP_FR_INV: return run_elementwise<Fr, Fr, Fr>(ctx, a, b, r, n, OpFrInv());
+    case RIPP_OP_FQ2_MUL: return run_elementwise<Fq2, Fq2, Fq2>(ctx, a, b, r, n, OpFq2Mul());
+    case RIPP_OP_FQ2_SQR: return run_elementwise<Fq2, Fq2, Fq2>(ctx, a, b, r, n, OpFq2Sqr());
+    case RIPP_OP_FQ2_INV: return run_elementwise<Fq2, Fq2, Fq2>(ctx, a, b, r, n, OpFq2Inv());
+    case RIPP_OP_FQ12_MUL: return run_elementwise<Fq12, Fq12, Fq12>(ctx, a, b, r, n, OpFq12Mul());
+    case RIPP_OP_FQ12_SQR: return run_elementwise<Fq12, Fq12, Fq12>(ctx, a, b, r, n, OpFq12Sqr());
+    case RIPP_OP_FQ12_INV: return run_elementwise<Fq12, Fq12, Fq12>(ctx, a, b, r, n, OpFq12Inv());
+    case RIPP_OP_FQ12_CYC_SQR: return run_elementwise<Fq12, Fq12, Fq12>(ctx, a, b, r, n, OpFq12Cyc());
+    case RIPP_OP_FQ12_FROB1: return run_elementwise<Fq12, Fq12, Fq12>(ctx, a, b, r, n, OpFq12Frob1());
+    case RIPP_OP_FINAL_EXP: return run_elementwise<Fq12, Fq12, Fq12>(ctx, a, b, r, n, OpFinalExp());
+    case RIPP_OP_MILLER: return run_elementwise<G1Aff, G2Aff, Fq12>(ctx, a, b, r, n, OpMiller());
+    case RIPP_OP_G1_ADD: return run_elementwise<G1Aff, G1Aff, G1Aff>(ctx, a, b, r, n, OpAdd<Fq>());
+    case RIPP_OP_G1_DBL: return run_elementwise<G1Aff, G1Aff, G1Aff>(ctx, a, b, r, n, OpDbl<Fq>());
+    case RIPP_OP_G2_ADD: return run_elementwise<G2Aff, G2Aff, G2Aff>(ctx, a, b, r, n, OpAdd<Fq2>());
+    case RIPP_OP_G2_DBL: return run_elementwise<G2Aff, G2Aff, G2Aff>(ctx, a, b, r, n, OpDbl<Fq2>());
+  }
+  return fail(RIPP_ERR_ARG, "unknown test op");
+}
+
+// Integer-pipe peak microbenchmark.  8 independent accumulators per thread, register-only.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_imad(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  if (KIND == 0) {
+    uint64_t acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = a + j;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a + u), "r"(b));
+      }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= acc[j];
+    if (s == 0x1234567) out[0] = (uint32_t)s;
+  } else if (KIND == 1) {
+    uint32_t acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = a + j;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[j]) : "r"(a + u), "r"(b));
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= acc[j];
+    if (s == 0x1234567) out[0] = s;
+  } else {
+    // carry-chained pairs exactly as mont_row issues them: 2 independent chains of 8 limbs
+    uint32_t x[8], y[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      x[j] = a + j;
+      y[j] = b + j;
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        limb::mad_lo_cc(x[0], a + u, b, x[0]);
+        limb::madc_hi_cc(x[1], a + u, b, x[1]);
+        limb::madc_lo_cc(x[2], a + u, y[2], x[2]);
+        limb::madc_hi_cc(x[3], a + u, y[2], x[3]);
+        limb::madc_lo_cc(x[4], a + u, y[4], x[4]);
+        limb::madc_hi_cc(x[5], a + u, y[4], x[5]);
+        limb::madc_lo_cc(x[6], a + u, y[6], x[6]);
+        limb::madc_hi(x[7], a + u, y[6], x[7]);
+        limb::mad_lo_cc(y[0], b + u, a, y[0]);
+        limb::madc_hi_cc(y[1], b + u, a, y[1]);
+        limb::madc_lo_cc(y[2], b + u, x[2], y[2]);
+        limb::madc_hi_cc(y[3], b + u, x[2], y[3]);
+        limb::madc_lo_cc(y[4], b + u, x[4], y[4]);
+        limb::madc_hi_cc(y[5], b + u, x[4], y[5]);
+        limb::madc_lo_cc(y[6], b + u, x[6], y[6]);
+        limb::madc_hi(y[7], b + u, x[6], y[7]);
+      }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= x[j] ^ y[j];
+    if (s == 0x1234567) out[0] = s;
+  }
+}
+
+extern "C" int ripp_bench_imad(ripp_ctx* ctx, int kind, int iters, double* macs_per_s, double* ms_out) {
+  if (!ctx || !macs_per_s) return fail(RIPP_ERR_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, ctx->device));
+  void* out;
+  OK(scratch(ctx, 3, 256, &out));
+  int blocks = prop.multiProcessorCount * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(cudaEventRecord(e0, ctx->stream));
+    if (kind == 0)
+      k_imad<0><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, 12345u + rep);
+    else if (kind == 1)
+      k_imad<1><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, 12345u + rep);
+    else
+      k_imad<2><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, 12345u + rep);
+    LAUNCHED(ctx);
+    CU(cudaEventRecord(e1, ctx->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  // MACs per thread per iteration: kind 0/1: 64; kind 2: 8 pairs x 2 chains x 8 = 64 pairs = 64 32x32 products
+  double macs = (double)blocks * threads * (double)iters * 64.0;
+  *macs_per_s = macs / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  return RIPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// L1: pairing inner product
+// ------------------------------------------------------------------------------------------------
+static const int MILLER_BLOCK = 64;
+
+static int miller_partial(ripp_ctx* ctx, const G1Aff* p, const G2Aff* q, size_t n, Fq12* out_dev) {
+  if (n == 0) {
+    Fq12 one = Fq12::one();
+    CU(cudaMemcpyAsync(out_dev, &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RIPP_OK;
+  }
+  size_t nblocks = (n + MILLER_BLOCK - 1) / MILLER_BLOCK;
+  size_t nwarps = nblocks * (MILLER_BLOCK / 32);
+  const int R = 8;
+  void *bufA, *bufB;
+  OK(scratch(ctx, 2, nwarps * sizeof(Fq12), &bufA));
+  OK(scratch(ctx, 3, ((nwarps + R - 1) / R) * sizeof(Fq12) + 256, &bufB));
+  k_miller<MILLER_BLOCK><<<(unsigned)nblocks, MILLER_BLOCK, 0, ctx->stream>>>(p, q, n, (Fq12*)bufA);
+  LAUNCHED(ctx);
+  size_t m = nwarps;
+  Fq12 *src = (Fq12*)bufA, *dst = (Fq12*)bufB;
+  while (m > 1) {
+    size_t mo = (m + R - 1) / R;
+    Fq12* o = (mo == 1) ? out_dev : dst;
+    k_fq12_reduce<<<(unsigned)((mo + 63) / 64), 64, 0, ctx->stream>>>(src, m, R, o);
+    LAUNCHED(ctx);
+    Fq12* t = src;
+    src = dst;
+    dst = t;
+    m = mo;
+  }
+  if (nwarps == 1) CU(cudaMemcpyAsync(out_dev, bufA, sizeof(Fq12), cudaMemcpyDeviceToDevice, ctx->stream));
+  return RIPP_OK;
+}
+
+extern "C" int ripp_miller_partial_dev(ripp_ctx* ctx, const void* g1, const void* g2, size_t n, void* out) {
+  if (!ctx || !out || (n && (!g1 || !g2))) return fail(RIPP_ERR_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  return miller_partial(ctx, (const G1Aff*)g1, (const G2Aff*)g2, n, (Fq12*)out);
+}
+
+extern "C" int ripp_gt_combine_dev(ripp_ctx* ctx, const void* partials, size_t count, void* out) {
+  if (!ctx || !out || !partials || count == 0) return fail(RIPP_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->device));
+  void* tmp;
+  OK(scratch(ctx, 3, sizeof(Fq12) + 256, &tmp));
+  k_fq12_reduce<<<1, 32, 0, ctx->stream>>>((const Fq12*)partials, count, (int)count, (Fq12*)tmp);
+  LAUNCHED(ctx);
+  k_final_exp<<<1, 32, 0, ctx->stream>>>((const Fq12*)tmp, (Fq12*)out, 1);
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}
+
+extern "C" int ripp_pairing_ip_dev(ripp_ctx* ctx, const void* g1, const void* g2, size_t n, void* out) {
+  if (!ctx || !out || (n && (!g1 || !g2))) return fail(RIPP_ERR_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  void* part;
+  OK(scratch(ctx, 1, sizeof(Fq12) + 256, &part));
+  OK(miller_partial(ctx, (const G1Aff*)g1, (const G2Aff*)g2, n, (Fq12*)part));
+  k_final_exp<<<1, 32, 0, ctx->stream>>>((const Fq12*)part, (Fq12*)out, 1);
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}
+
+static int pairing_ip_host(ripp_ctx* ctx, const void* g1, size_t nl, const void* g2, size_t nr, void* gt_out, bool jac) {
+  if (!ctx || !gt_out) return fail(RIPP_ERR_ARG, "null argument");
+  if (nl != nr)
+    return fail(RIPP_ERR_LEN_MISMATCH,
+                "left length, right length: " + std::to_string(nl) + ", " + std::to_string(nr));
+  size_t n = nl;
+  if (n && (!g1 || !g2)) return fail(RIPP_ERR_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  void* dbuf;
+  size_t s1 = jac ? sizeof(G1Jac) : sizeof(G1Aff), s2 = jac ? sizeof(G2Jac) : sizeof(G2Aff);
+  size_t off_g2 = (n * s1 + 255) & ~(size_t)255;
+  size_t off_a1 = off_g2 + ((n * s2 + 255) & ~(size_t)255);
+  size_t off_a2 = off_a1 + ((n * sizeof(G1Aff) + 255) & ~(size_t)255);
+  size_t off_out = off_a2 + ((n * sizeof(G2Aff) + 255) & ~(size_t)255);
+  OK(scratch(ctx, 0, off_out + 1024, &dbuf));
+  char* d = (char*)dbuf;
+  const G1Aff* pa;
+  const G2Aff* qa;
+  if (n) {
+    CU(cudaMemcpyAsync(d, g1, n * s1, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d + off_g2, g2, n * s2, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (jac && n) {
+    k_normalize<Fq><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const G1Jac*)d, (G1Aff*)(d + off_a1), n);
+    LAUNCHED(ctx);
+    k_normalize<Fq2><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const G2Jac*)(d + off_g2), (G2Aff*)(d + off_a2), n);
+    LAUNCHED(ctx);
+    pa = (const G1Aff*)(d + off_a1);
+    qa = (const G2Aff*)(d + off_a2);
+  } else {
+    pa = (const G1Aff*)d;
+    qa = (const G2Aff*)(d + off_g2);
+  }
+  OK(ripp_pairing_ip_dev(ctx, pa, qa, n, d + off_out));
+  CU(cudaMemcpyAsync(gt_out, d + off_out, sizeof(Fq12), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RIPP_OK;
+}
+
+extern "C" int ripp_pairing_ip(ripp_ctx* ctx, const void* g1_jac, size_t nl, const void* g2_jac, size_t nr, void* gt_out) {
+  return pairing_ip_host(ctx, g1_jac, nl, g2_jac, nr, gt_out, true);
+}
+extern "C" int ripp_pairing_ip_affine(ripp_ctx* ctx, const void* g1, size_t nl, const void* g2, size_t nr, void* gt_out) {
+  return pairing_ip_host(ctx, g1, nl, g2, nr, gt_out, false);
+}

@@ -23,14 +23,14 @@ struct Fq2 {
   RIPP_HD Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
   RIPP_HD Fq2 conj() const { return {c0, -c1}; }
   // Karatsuba: 3 Fq products
-  RIPP_HD Fq2 operator*(const Fq2& b) const {
+  RIPP_FN Fq2 operator*(const Fq2& b) const {
     Fq t0 = c0 * b.c0;
     Fq t1 = c1 * b.c1;
     Fq t2 = (c0 + c1) * (b.c0 + b.c1);
     return {t0 - t1, t2 - t0 - t1};
   }
   // complex squaring: 2 Fq products
-  RIPP_HD Fq2 sqr() const {
+  RIPP_FN Fq2 sqr() const {
     Fq t = c0 * c1;
     return {(c0 + c1) * (c0 - c1), t.dbl()};
   }
@@ -100,7 +100,7 @@ struct Fq6 {
   // sparse: times (b1 v): 3 Fq2 products
   RIPP_HD Fq6 mul_by_1(const Fq2& b1) const { return {(c2 * b1).mul_xi(), c0 * b1, c1 * b1}; }
   RIPP_HD Fq6 mul_fq2(const Fq2& s) const { return {c0 * s, c1 * s, c2 * s}; }
-  RIPP_HD Fq6 inv() const {
+  RIPP_FN Fq6 inv() const {
     Fq2 t0 = c0.sqr() - (c1 * c2).mul_xi();
     Fq2 t1 = c2.sqr().mul_xi() - c0 * c1;
     Fq2 t2 = c1.sqr() - c0 * c2;
@@ -113,12 +113,12 @@ struct Fq12 {
   Fq6 c0, c1;
   RIPP_HD static Fq12 one() { return {Fq6::one(), Fq6::zero()}; }
   RIPP_HD bool operator==(const Fq12& b) const { return c0 == b.c0 && c1 == b.c1; }
-  RIPP_HD Fq12 operator*(const Fq12& b) const {
+  RIPP_FN Fq12 operator*(const Fq12& b) const {
     Fq6 aa = c0 * b.c0, bb = c1 * b.c1;
     Fq6 m = (c0 + c1) * (b.c0 + b.c1) - aa - bb;
     return {aa + bb.mul_v(), m};
   }
-  RIPP_HD Fq12 sqr() const {
+  RIPP_FN Fq12 sqr() const {
     // complex squaring over Fq6: 2 Fq6 products
     Fq6 ab = c0 * c1;
     Fq6 t = (c0 + c1) * (c0 + c1.mul_v()) - ab - ab.mul_v();
@@ -126,12 +126,12 @@ struct Fq12 {
   }
   // w -> -w (= p^6 Frobenius; the inverse on the cyclotomic subgroup)
   RIPP_HD Fq12 conj() const { return {c0, -c1}; }
-  RIPP_HD Fq12 inv() const {
+  RIPP_FN Fq12 inv() const {
     Fq6 d = (c0.sqr() - c1.sqr().mul_v()).inv();
     return {c0 * d, -(c1 * d)};
   }
   // times the sparse element (d0 + d1 v) + (d4 v) w   [M-twist line, ark-ec `mul_by_014`]: 13 Fq2 products
-  RIPP_HD Fq12 mul_by_014(const Fq2& d0, const Fq2& d1, const Fq2& d4) const {
+  RIPP_FN Fq12 mul_by_014(const Fq2& d0, const Fq2& d1, const Fq2& d4) const {
     Fq6 aa = c0.mul_by_01(d0, d1);
     Fq6 bb = c1.mul_by_1(d4);
     Fq6 m = (c0 + c1).mul_by_01(d0, d1 + d4) - aa - bb;
@@ -145,7 +145,7 @@ struct Fq12 {
   }
   // p^n Frobenius for n = 1, 2, 3
   template <int NPOW>
-  RIPP_HD Fq12 frob() const {
+  RIPP_FN Fq12 frob() const {
     Fq12 r = *this;
 #pragma unroll
     for (int kk = 0; kk < 6; kk++) {
@@ -159,7 +159,7 @@ struct Fq12 {
     return r;
   }
   // Granger-Scott squaring, valid only in the cyclotomic subgroup: 9 Fq2 squarings-equivalents (6 products)
-  RIPP_HD Fq12 cyclotomic_sqr() const {
+  RIPP_FN Fq12 cyclotomic_sqr() const {
     const Fq2 &r0 = c0.c0, &r4 = c0.c1, &r3 = c0.c2, &r2 = c1.c0, &r1 = c1.c1, &r5 = c1.c2;
     Fq2 tmp = r0 * r1;
     Fq2 t0 = (r0 + r1) * (r1.mul_xi() + r0) - tmp - tmp.mul_xi();

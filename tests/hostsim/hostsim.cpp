@@ -52,6 +52,8 @@ void hs_g2_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { st(r, G2Jac:
 void hs_g2_add_mixed(const uint32_t* a, const uint32_t* b, uint32_t* r) { st(r, G2Jac::from_affine(ld<G2Aff>(a)).add_mixed(ld<G2Aff>(b)).to_affine()); }
 void hs_g2_dbl(const uint32_t* a, const uint32_t*, uint32_t* r) { st(r, G2Jac::from_affine(ld<G2Aff>(a)).dbl().to_affine()); }
 void hs_g2_mul(const uint32_t* a, const uint32_t* bits, int nbits, uint32_t* r) { st(r, scalar_mul(ld<G2Aff>(a), bits, nbits).to_affine()); }
+uint64_t hs_mul_count(int which) { return detail::mul_count_[which]; }
+void hs_mul_count_reset() { detail::mul_count_[0] = detail::mul_count_[1] = 0; }
 void hs_g1_gen(uint32_t* r) { st(r, g1_generator()); }
 void hs_g2_gen(uint32_t* r) { st(r, g2_generator()); }
 void hs_miller(const uint32_t* p, const uint32_t* q, uint32_t* r) { st(r, miller_loop(ld<G1Aff>(p), ld<G2Aff>(q))); }

@@ -1,0 +1,127 @@
+"""The device arithmetic headers (ripp_b200/csrc/*.cuh), compiled for the host with an emulated
+carry flag, against the independent Python big-int oracle.  Pins the limb sequences, tower,
+group law, Miller loop and final exponentiation without a GPU; tests/test_gpu_*.py repeat the
+comparison on the real PTX path."""
+import random
+
+import pytest
+
+from oracle import bls12_381 as E
+from ripp_b200 import codec as C
+
+rnd = random.Random(2024)
+rf = lambda: rnd.randrange(E.P)
+rf2 = lambda: (rf(), rf())
+rf12 = lambda: tuple(rf2() for _ in range(6))
+
+
+@pytest.mark.parametrize("pre,p,n,radix", [("fq", E.P, 12, 1 << 384), ("fr", E.R, 8, 1 << 256)])
+def test_prime_field(hostsim, pre, p, n, radix):
+    rinv = pow(radix, -1, p)
+    w = lambda v: C._words(v, n)
+    cases = [(0, 0), (p - 1, p - 1), (1, p - 1), (0, 5)] + [(rnd.randrange(p), rnd.randrange(p)) for _ in range(500)]
+    for a, b in cases:
+        assert C._int(hostsim.call("hs_%s_mul" % pre, w(a), w(b), out=n)) == a * b * rinv % p
+        assert C._int(hostsim.call("hs_%s_add" % pre, w(a), w(b), out=n)) == (a + b) % p
+        assert C._int(hostsim.call("hs_%s_sub" % pre, w(a), w(b), out=n)) == (a - b) % p
+        assert C._int(hostsim.call("hs_%s_half" % pre, w(a), w(b), out=n)) == a * pow(2, -1, p) % p
+    for _ in range(10):
+        a = rnd.randrange(1, p)
+        assert C._int(hostsim.call("hs_%s_inv" % pre, w(a * radix % p), w(0), out=n)) == pow(a, -1, p) * radix % p
+
+
+def test_fq2(hostsim):
+    for _ in range(50):
+        a, b = rf2(), rf2()
+        assert C.fq2_dec(hostsim.call("hs_fq2_mul", C.fq2_enc(a), C.fq2_enc(b), out=24)) == E.f2_mul(a, b)
+        assert C.fq2_dec(hostsim.call("hs_fq2_sqr", C.fq2_enc(a), C.fq2_enc(b), out=24)) == E.f2_sqr(a)
+        assert C.fq2_dec(hostsim.call("hs_fq2_inv", C.fq2_enc(a), C.fq2_enc(b), out=24)) == E.f2_inv(a)
+
+
+def _f6(a):  # oracle has no Fq6 type: embed (c0, c1, c2) as c0 + c1 w^2 + c2 w^4
+    return (a[0], (0, 0), a[1], (0, 0), a[2], (0, 0))
+
+
+def test_fq6(hostsim):
+    import numpy as np
+
+    enc = lambda a: np.concatenate([C.fq2_enc(c) for c in a])
+    dec = lambda w: tuple(C.fq2_dec(w[24 * i : 24 * i + 24]) for i in range(3))
+    for _ in range(20):
+        a, b = (rf2(), rf2(), rf2()), (rf2(), rf2(), rf2())
+        got = dec(hostsim.call("hs_fq6_mul", enc(a), enc(b), out=72))
+        assert _f6(got) == E.f12_mul(_f6(a), _f6(b))
+        got = dec(hostsim.call("hs_fq6_sqr", enc(a), enc(b), out=72))
+        assert _f6(got) == E.f12_sqr(_f6(a))
+        got = dec(hostsim.call("hs_fq6_inv", enc(a), enc(b), out=72))
+        assert _f6(got) == E.f12_inv(_f6(a))
+
+
+def test_fq12(hostsim):
+    for _ in range(10):
+        a, b = rf12(), rf12()
+        ea, eb = C.gt_enc(a), C.gt_enc(b)
+        assert C.gt_dec(hostsim.call("hs_fq12_mul", ea, eb, out=144)) == E.f12_mul(a, b)
+        assert C.gt_dec(hostsim.call("hs_fq12_sqr", ea, eb, out=144)) == E.f12_sqr(a)
+        assert C.gt_dec(hostsim.call("hs_fq12_inv", ea, eb, out=144)) == E.f12_inv(a)
+        for n in (1, 2, 3):
+            assert C.gt_dec(hostsim.call("hs_fq12_frob%d" % n, ea, eb, out=144)) == E.f12_frob(a, n)
+        d0, d1, d4 = rf2(), rf2(), rf2()
+        sparse = (d0, (0, 0), d1, d4, (0, 0), (0, 0))  # d0 + d1 v + d4 v w = d0 + d1 w^2 + d4 w^3
+        got = hostsim.call("hs_fq12_mul_by_014", ea, C.fq2_enc(d0), C.fq2_enc(d1), C.fq2_enc(d4), out=144)
+        assert C.gt_dec(got) == E.f12_mul(a, sparse)
+
+
+def test_cyclotomic(hostsim):
+    a = rf12()
+    c = E.f12_mul(E.f12_conj(a), E.f12_inv(a))
+    c = E.f12_mul(E.f12_frob(c, 2), c)  # in the cyclotomic subgroup
+    ec = C.gt_enc(c)
+    assert C.gt_dec(hostsim.call("hs_fq12_cyc_sqr", ec, ec, out=144)) == E.f12_sqr(c)
+    assert C.gt_dec(hostsim.call("hs_fq12_exp_by_x", ec, ec, out=144)) == E.f12_cyc_pow(c, E.X)
+
+
+@pytest.mark.parametrize("grp", ["g1", "g2"])
+def test_group_law(hostsim, grp):
+    if grp == "g1":
+        enc, dec, n, gen, add, mul, neg = C.g1_enc, C.g1_dec, 24, E.G1_GEN, E.g1_add, E.g1_mul, E.g1_neg
+    else:
+        enc, dec, n, gen, add, mul, neg = C.g2_enc, C.g2_dec, 48, E.G2_GEN, E.g2_add, E.g2_mul, E.g2_neg
+    assert dec(hostsim.call("hs_%s_gen" % grp, out=n)) == gen
+    for _ in range(5):
+        a, b = mul(gen, rnd.randrange(E.R)), mul(gen, rnd.randrange(E.R))
+        for x, y in ((a, b), (a, a), (a, neg(a)), (a, None), (None, b), (None, None)):
+            assert dec(hostsim.call("hs_%s_add" % grp, enc(x), enc(y), out=n)) == add(x, y)
+            assert dec(hostsim.call("hs_%s_add_mixed" % grp, enc(x), enc(y), out=n)) == add(x, y)
+        assert dec(hostsim.call("hs_%s_dbl" % grp, enc(a), enc(a), out=n)) == add(a, a)
+        for k in (0, 1, E.R - 1, rnd.randrange(E.R)):
+            assert dec(hostsim.call("hs_%s_mul" % grp, enc(a), C.scalar_words(k), 255, out=n)) == mul(a, k)
+
+
+def test_pairing(hostsim):
+    p, q = E.g1_mul(E.G1_GEN, 123), E.g2_mul(E.G2_GEN, 456)
+    f = E.miller_loop(p, q)
+    ef = C.gt_enc(f)
+    assert C.gt_dec(hostsim.call("hs_final_exp", ef, ef, out=144)) == E.final_exponentiation(f)
+    # Miller values differ by subfield factors between formulas; they agree after the final exponentiation
+    m = hostsim.call("hs_miller", C.g1_enc(p), C.g2_enc(q), out=144)
+    assert C.gt_dec(hostsim.call("hs_final_exp", m, m, out=144)) == E.pairing(p, q)
+    ps = [E.g1_mul(E.G1_GEN, i + 2) for i in range(4)] + [None, E.G1_GEN]
+    qs = [E.g2_mul(E.G2_GEN, 3 * i + 1) for i in range(4)] + [E.G2_GEN, None]
+    got = hostsim.call("hs_pairing_product", len(ps), C.g1_vec_enc(ps), C.g2_vec_enc(qs), out=144)
+    assert C.gt_dec(got) == E.multi_pairing(ps, qs)
+
+
+def test_op_counts(hostsim):
+    """Algorithmic Fq-product counts behind the roofline model (bench.py)."""
+    p, q = E.g1_mul(E.G1_GEN, 7), E.g2_mul(E.G2_GEN, 9)
+    hostsim.lib.hs_mul_count_reset()
+    m = hostsim.call("hs_miller", C.g1_enc(p), C.g2_enc(q), out=144)
+    miller = hostsim.lib.hs_mul_count(1)
+    hostsim.lib.hs_mul_count_reset()
+    hostsim.call("hs_final_exp", m, m, out=144)
+    fexp = hostsim.lib.hs_mul_count(1)
+    import bench
+
+    assert miller == bench.FQ_MUL_PER_MILLER_PAIR
+    assert fexp == bench.FQ_MUL_PER_FINAL_EXP
