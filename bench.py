@@ -120,7 +120,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # one non-default stream shared by torch (events, NCCL ordering) and the library's kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     n = 1 << args.logn
 
