@@ -81,6 +81,29 @@ int ripp_miller_partial_dev(ripp_ctx* ctx, const void* g1_aff_dev, const void* g
  * apply the single shared final exponentiation (lib.rs:115). */
 int ripp_gt_combine_dev(ripp_ctx* ctx, const void* fq12_partials_dev, size_t count, void* gt_out_dev);
 
+/* MultiexponentiationInnerProduct::inner_product (lib.rs:123-142) == G::msm(normalize_batch(left), right),
+ * also PedersenCommitment::commit (dh_commitments/src/pedersen/mod.rs:24-26).  Host pointers:
+ * bases Jacobian, scalars Fr (Montgomery), result Jacobian (Z = 1, or Z = 0 for the identity). */
+int ripp_msm_g1(ripp_ctx* ctx, const void* g1_jac, size_t n_left, const void* fr, size_t n_right, void* g1_jac_out);
+int ripp_msm_g2(ripp_ctx* ctx, const void* g2_jac, size_t n_left, const void* fr, size_t n_right, void* g2_jac_out);
+/* Device-resident variants: affine bases, result one affine point in device memory.  Also the
+ * KZG opening MSM of tipa/mod.rs:333-334. */
+int ripp_msm_g1_dev(ripp_ctx* ctx, const void* g1_aff_dev, const void* fr_dev, size_t n, void* g1_aff_out_dev);
+int ripp_msm_g2_dev(ripp_ctx* ctx, const void* g2_aff_dev, const void* fr_dev, size_t n, void* g2_aff_out_dev);
+/* ScalarInnerProduct::inner_product (lib.rs:149-166): sum_i a[i] * b[i] in Fr. */
+int ripp_scalar_ip(ripp_ctx* ctx, const void* fr_a, size_t n_left, const void* fr_b, size_t n_right, void* fr_out);
+int ripp_scalar_ip_dev(ripp_ctx* ctx, const void* fr_a_dev, const void* fr_b_dev, size_t n, void* fr_out_dev);
+
+/* ---- folds with one shared scalar (kernel K7) ------------------------------------------------ */
+/* out[i] = hi[i] * c + lo[i]: the four "rescale" maps of a GIPA round (gipa.rs:261-291, scalar-mul
+ * primitive mul_helper, ip_proofs/src/lib.rs:15-19) and of SIPP (sipp/src/lib.rs:87-100).
+ * c is ONE Fr in Montgomery form in HOST memory (32 B); vectors are device-resident (affine points
+ * or Fr); out may alias lo.  Only the significant bits of c are walked, so the 128-bit challenges
+ * cost half of a full-width scalar. */
+int ripp_g1_fold_dev(ripp_ctx* ctx, const void* hi_dev, const void* lo_dev, const void* c_host, size_t n, void* out_dev);
+int ripp_g2_fold_dev(ripp_ctx* ctx, const void* hi_dev, const void* lo_dev, const void* c_host, size_t n, void* out_dev);
+int ripp_fr_fold_dev(ripp_ctx* ctx, const void* hi_dev, const void* lo_dev, const void* c_host, size_t n, void* out_dev);
+
 /* ---- element-wise scalar multiplication (kernel K8) ------------------------------------------ */
 /* out[i] = scalars[i] * points[i] with distinct scalars: the `a[i] * r^i` / `ck[i] * r^-i` maps of
  * groth16_aggregation.rs:118-131 and `a[i] * r[i]` of sipp/src/lib.rs:61-65,189-193.

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libripp_b200.so")
+LIB_PATH = os.environ.get("RIPP_B200_LIB") or os.path.join(HERE, "libripp_b200.so")
 
 RIPP_OK = 0
 RIPP_ERR_LEN_MISMATCH = -1
@@ -170,6 +170,36 @@ class Context:
 
     def g2_scale_dev(self, pts_dev, fr_dev, n, out_dev):
         check(lib().ripp_g2_scale_dev(self.handle, _p(pts_dev), _p(fr_dev), ctypes.c_size_t(n), _p(out_dev)))
+
+    def msm_g1(self, g1_jac, fr):
+        out = np.empty(36, dtype=np.uint32)
+        check(lib().ripp_msm_g1(self.handle, _p(g1_jac), ctypes.c_size_t(len(g1_jac)), _p(fr), ctypes.c_size_t(len(fr)), _p(out)))
+        return out
+
+    def msm_g2(self, g2_jac, fr):
+        out = np.empty(72, dtype=np.uint32)
+        check(lib().ripp_msm_g2(self.handle, _p(g2_jac), ctypes.c_size_t(len(g2_jac)), _p(fr), ctypes.c_size_t(len(fr)), _p(out)))
+        return out
+
+    def msm_g1_dev(self, bases_dev, fr_dev, n, out_dev):
+        check(lib().ripp_msm_g1_dev(self.handle, _p(bases_dev), _p(fr_dev), ctypes.c_size_t(n), _p(out_dev)))
+
+    def msm_g2_dev(self, bases_dev, fr_dev, n, out_dev):
+        check(lib().ripp_msm_g2_dev(self.handle, _p(bases_dev), _p(fr_dev), ctypes.c_size_t(n), _p(out_dev)))
+
+    def scalar_ip(self, a, b):
+        out = np.empty(8, dtype=np.uint32)
+        check(lib().ripp_scalar_ip(self.handle, _p(a), ctypes.c_size_t(len(a)), _p(b), ctypes.c_size_t(len(b)), _p(out)))
+        return out
+
+    def g1_fold_dev(self, hi, lo, c_host, n, out):
+        check(lib().ripp_g1_fold_dev(self.handle, _p(hi), _p(lo), _p(c_host), ctypes.c_size_t(n), _p(out)))
+
+    def g2_fold_dev(self, hi, lo, c_host, n, out):
+        check(lib().ripp_g2_fold_dev(self.handle, _p(hi), _p(lo), _p(c_host), ctypes.c_size_t(n), _p(out)))
+
+    def fr_fold_dev(self, hi, lo, c_host, n, out):
+        check(lib().ripp_fr_fold_dev(self.handle, _p(hi), _p(lo), _p(c_host), ctypes.c_size_t(n), _p(out)))
 
     # ---- diagnostics ----------------------------------------------------------------------
     def test_elementwise(self, op, a, b, out_words):

@@ -117,6 +117,31 @@ def g1_jac_enc(pt, z=1):
     return np.concatenate([fq_enc(pt[0] * z * z), fq_enc(pt[1] * z * z * z), fq_enc(z)])
 
 
+def g1_jac_dec(a):
+    a = np.asarray(a)
+    z = fq_dec(a[24:36])
+    if z == 0:
+        return None
+    zi = pow(z, -1, P)
+    return (fq_dec(a[:12]) * zi * zi % P, fq_dec(a[12:24]) * zi * zi * zi % P)
+
+
+def g2_jac_enc(pt):
+    if pt is None:
+        return np.concatenate([fq2_enc((1, 0)), fq2_enc((1, 0)), fq2_enc((0, 0))])
+    return np.concatenate([fq2_enc(pt[0]), fq2_enc(pt[1]), fq2_enc((1, 0))])
+
+
+def g2_jac_dec(a):
+    """Only Z in {0, 1} (what the library returns)."""
+    a = np.asarray(a)
+    z = fq2_dec(a[48:72])
+    if z == (0, 0):
+        return None
+    assert z == (1, 0)
+    return (fq2_dec(a[:24]), fq2_dec(a[24:48]))
+
+
 def gt_enc(f):
     return np.concatenate([fq2_enc(f[k]) for k in _TOWER_ORDER])
 

@@ -1,0 +1,64 @@
+// Shared host-side plumbing of the library: context, error reporting, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ripp_b200.h"
+#include "pairing.cuh"
+
+using namespace ripp;
+
+// ------------------------------------------------------------------------------------------------
+// context / errors
+// ------------------------------------------------------------------------------------------------
+std::string& ripp_err_slot();
+
+#define RIPP_SCRATCH_SLOTS 12
+struct ripp_ctx {
+  int device;
+  cudaStream_t stream;
+  cudaStream_t own_stream;
+  uint64_t launches;
+  // scratch (grown on demand)
+  void* scratch[RIPP_SCRATCH_SLOTS];
+  size_t scratch_bytes[RIPP_SCRATCH_SLOTS];
+};
+
+static inline int fail(int code, const std::string& msg) {
+  ripp_err_slot() = msg;
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(RIPP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + \
+                                     std::to_string(__LINE__));                                          \
+  } while (0)
+#define OK(call)              \
+  do {                        \
+    int s_ = (call);          \
+    if (s_ != RIPP_OK) return s_; \
+  } while (0)
+#define LAUNCHED(ctx)        \
+  do {                       \
+    (ctx)->launches++;       \
+    CU(cudaGetLastError());  \
+  } while (0)
+
+static inline int scratch(ripp_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (ctx->scratch_bytes[slot] < bytes) {
+    if (ctx->scratch[slot]) CU(cudaFree(ctx->scratch[slot]));
+    ctx->scratch[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
+    CU(cudaMalloc(&ctx->scratch[slot], bytes));
+    ctx->scratch_bytes[slot] = bytes;
+  }
+  *out = ctx->scratch[slot];
+  return RIPP_OK;
+}
+

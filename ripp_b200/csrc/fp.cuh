@@ -48,49 +48,33 @@ RIPP_HD void final_sub(uint32_t* r) {
   for (int i = 0; i < N; i++) r[i] = borrow ? r[i] : t[i];
 }
 
-// One row of the interleaved product after the first: X is the aligned accumulator, Y the one that
-// is offset by a limb (see DESIGN.md "Montgomery multiplication").
+// One row of the interleaved product after the first.  X is the aligned accumulator, Y the one
+// offset by a limb; both are held as N/2 aligned (lo, hi) register pairs (DESIGN.md "Montgomery").
 template <class P>
-RIPP_HD void mont_row(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
-  constexpr int N = P::N;
-  add_cc(X[0], X[0], Y[1]);
+RIPP_HD void mont_row(uint64_t* X, uint64_t* Y, const uint32_t* a, uint32_t bi) {
+  constexpr int H = P::N / 2;
+  add_lo_hi_cc(X[0], Y[0]);
 #pragma unroll
-  for (int j = 0; j < N - 2; j += 2) {
-    madc_lo_cc(Y[j], a[j + 1], bi, Y[j + 2]);
-    madc_hi_cc(Y[j + 1], a[j + 1], bi, Y[j + 3]);
-  }
-  madc_lo_cc(Y[N - 2], a[N - 1], bi, 0);
-  madc_hi(Y[N - 1], a[N - 1], bi, 0);
-  mad_lo_cc(X[0], a[0], bi, X[0]);
-  madc_hi_cc(X[1], a[0], bi, X[1]);
+  for (int k = 0; k < H - 1; k++) mwc_cc(Y[k], a[2 * k + 1], bi, Y[k + 1]);
+  mwc(Y[H - 1], a[2 * H - 1], bi, 0);
+  mw_cc(X[0], a[0], bi, X[0]);
 #pragma unroll
-  for (int j = 2; j < N; j += 2) {
-    madc_lo_cc(X[j], a[j], bi, X[j]);
-    madc_hi_cc(X[j + 1], a[j], bi, X[j + 1]);
-  }
-  addc(Y[N - 1], Y[N - 1], 0);
+  for (int k = 1; k < H; k++) mwc_cc(X[k], a[2 * k], bi, X[k]);
+  addc_hi(Y[H - 1]);
 }
 
 // Add m*p with m chosen so the lowest limb of X cancels.
 template <class P>
-RIPP_HD void mont_redc(uint32_t* X, uint32_t* Y) {
-  constexpr int N = P::N;
-  uint32_t m = mul_lo(X[0], P::M0);
-  mad_lo_cc(Y[0], P::p(1), m, Y[0]);
-  madc_hi_cc(Y[1], P::p(1), m, Y[1]);
+RIPP_HD void mont_redc(uint64_t* X, uint64_t* Y) {
+  constexpr int H = P::N / 2;
+  uint32_t m = mul_lo((uint32_t)X[0], P::M0);
+  mw_cc(Y[0], P::p(1), m, Y[0]);
 #pragma unroll
-  for (int j = 2; j < N; j += 2) {
-    madc_lo_cc(Y[j], P::p(j + 1), m, Y[j]);
-    madc_hi_cc(Y[j + 1], P::p(j + 1), m, Y[j + 1]);
-  }
-  mad_lo_cc(X[0], P::p(0), m, X[0]);
-  madc_hi_cc(X[1], P::p(0), m, X[1]);
+  for (int k = 1; k < H; k++) mwc_cc(Y[k], P::p(2 * k + 1), m, Y[k]);
+  mw_cc(X[0], P::p(0), m, X[0]);
 #pragma unroll
-  for (int j = 2; j < N; j += 2) {
-    madc_lo_cc(X[j], P::p(j), m, X[j]);
-    madc_hi_cc(X[j + 1], P::p(j), m, X[j + 1]);
-  }
-  addc(Y[N - 1], Y[N - 1], 0);
+  for (int k = 1; k < H; k++) mwc_cc(X[k], P::p(2 * k), m, X[k]);
+  addc_hi(Y[H - 1]);
 }
 
 #if defined(RIPP_HOSTSIM)
@@ -100,17 +84,16 @@ inline thread_local uint64_t mul_count_[2] = {0, 0};  // [Fr, Fq] products, test
 template <class P>
 RIPP_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   constexpr int N = P::N;
+  constexpr int H = N / 2;
+  static_assert(N % 2 == 0, "even limb count");
 #if defined(RIPP_HOSTSIM)
   mul_count_[N == 12]++;
 #endif
-  static_assert(N % 2 == 0, "even limb count");
-  uint32_t ev[N], od[N];
+  uint64_t ev[H], od[H];
 #pragma unroll
-  for (int j = 0; j < N; j += 2) {
-    ev[j] = mul_lo(a[j], b[0]);
-    ev[j + 1] = mul_hi(a[j], b[0]);
-    od[j] = mul_lo(a[j + 1], b[0]);
-    od[j + 1] = mul_hi(a[j + 1], b[0]);
+  for (int k = 0; k < H; k++) {
+    ev[k] = mul_wide(a[2 * k], b[0]);
+    od[k] = mul_wide(a[2 * k + 1], b[0]);
   }
   mont_redc<P>(ev, od);
 #pragma unroll
@@ -122,11 +105,19 @@ RIPP_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
       mont_redc<P>(ev, od);
     }
   }
-  // od[0] == 0 now; value / 2^32 = ev[k] + od[k+1] at limb k
-  add_cc(r[0], ev[0], od[1]);
+  // od's lowest limb is 0 now; value / 2^32 = ev[k] + od[k+1] at limb k
+  uint32_t e[N], o[N];
 #pragma unroll
-  for (int k = 1; k < N - 1; k++) addc_cc(r[k], ev[k], od[k + 1]);
-  addc(r[N - 1], ev[N - 1], 0);
+  for (int k = 0; k < H; k++) {
+    e[2 * k] = (uint32_t)ev[k];
+    e[2 * k + 1] = (uint32_t)(ev[k] >> 32);
+    o[2 * k] = (uint32_t)od[k];
+    o[2 * k + 1] = (uint32_t)(od[k] >> 32);
+  }
+  add_cc(r[0], e[0], o[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) addc_cc(r[k], e[k], o[k + 1]);
+  addc(r[N - 1], e[N - 1], 0);
   final_sub<P>(r);
 }
 
@@ -204,7 +195,7 @@ struct alignas(16) Fp {
     r.v[N - 1] >>= 1;
     return r;
   }
-  RIPP_HD Fp operator*(const Fp& b) const {
+  RIPP_FN Fp operator*(const Fp& b) const {
     Fp r;
     detail::mont_mul<P>(r.v, v, b.v);
     return r;

@@ -10,7 +10,7 @@
 #define RIPP_HD __host__ __device__ __forceinline__
 // Functions at and above the Fq2-product level are real calls on the device: fully inlining a
 // Miller loop (~10^5 instructions) makes ptxas run for hours and thrashes the instruction cache.
-#define RIPP_FN __host__ __device__ __noinline__
+#define RIPP_FN __host__ __device__ __noinline__ inline
 #else
 #define RIPP_HD inline
 #define RIPP_FN inline
@@ -53,6 +53,34 @@ RIPP_ASM4(madc_hi, "madc.hi.u32")
 #undef RIPP_ASM3
 #undef RIPP_ASM4
 
+// 32x32+64 -> 64 multiply-accumulate on an aligned register pair, with carry in/out.  Keeping the
+// (lo, hi) halves in one 64-bit variable is what lets ptxas emit a single IMAD.WIDE.U32[.X]
+// instead of IMAD + IMAD.HI + 2 IADD3.X when several products are in flight.
+#define RIPP_MW(fn, ilo, ihi)                                                                         \
+  RIPP_HD void fn(uint64_t& r, uint32_t a, uint32_t b, uint64_t c) {                                  \
+    asm volatile("{\n\t.reg .u32 l, h;\n\tmov.b64 {l, h}, %3;\n\t" ilo " l, %1, %2, l;\n\t" ihi         \
+                 " h, %1, %2, h;\n\tmov.b64 %0, {l, h};\n\t}"                                          \
+                 : "=l"(r)                                                                            \
+                 : "r"(a), "r"(b), "l"(c));                                                           \
+  }
+RIPP_MW(mw_cc, "mad.lo.cc.u32", "madc.hi.cc.u32")
+RIPP_MW(mwc_cc, "madc.lo.cc.u32", "madc.hi.cc.u32")
+RIPP_MW(mwc, "madc.lo.cc.u32", "madc.hi.u32")
+#undef RIPP_MW
+RIPP_HD uint64_t mul_wide(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
+// lo(x) += hi(y), carry out
+RIPP_HD void add_lo_hi_cc(uint64_t& x, uint64_t y) {
+  asm volatile("{\n\t.reg .u32 xl, xh, yl, yh;\n\tmov.b64 {xl, xh}, %0;\n\tmov.b64 {yl, yh}, %1;\n\t"
+               "add.cc.u32 xl, xl, yh;\n\tmov.b64 %0, {xl, xh};\n\t}"
+               : "+l"(x)
+               : "l"(y));
+}
+// hi(x) += carry
+RIPP_HD void addc_hi(uint64_t& x) {
+  asm volatile("{\n\t.reg .u32 xl, xh;\n\tmov.b64 {xl, xh}, %0;\n\taddc.u32 xh, xh, 0;\n\tmov.b64 %0, {xl, xh};\n\t}"
+               : "+l"(x));
+}
+
 #else  // host emulation of the same primitives
 
 inline thread_local uint32_t cc_ = 0;
@@ -87,6 +115,36 @@ inline void mad_hi_cc(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) { add_cc(
 inline void madc_hi_cc(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) { addc_cc(r, mul_hi(a, b), c); }
 inline void madc_lo(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) { addc(r, mul_lo(a, b), c); }
 inline void madc_hi(uint32_t& r, uint32_t a, uint32_t b, uint32_t c) { addc(r, mul_hi(a, b), c); }
+
+inline uint64_t mul_wide(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
+inline void mw_cc(uint64_t& r, uint32_t a, uint32_t b, uint64_t c) {
+  uint32_t l = (uint32_t)c, h = (uint32_t)(c >> 32);
+  mad_lo_cc(l, a, b, l);
+  madc_hi_cc(h, a, b, h);
+  r = ((uint64_t)h << 32) | l;
+}
+inline void mwc_cc(uint64_t& r, uint32_t a, uint32_t b, uint64_t c) {
+  uint32_t l = (uint32_t)c, h = (uint32_t)(c >> 32);
+  madc_lo_cc(l, a, b, l);
+  madc_hi_cc(h, a, b, h);
+  r = ((uint64_t)h << 32) | l;
+}
+inline void mwc(uint64_t& r, uint32_t a, uint32_t b, uint64_t c) {
+  uint32_t l = (uint32_t)c, h = (uint32_t)(c >> 32);
+  madc_lo_cc(l, a, b, l);
+  madc_hi(h, a, b, h);
+  r = ((uint64_t)h << 32) | l;
+}
+inline void add_lo_hi_cc(uint64_t& x, uint64_t y) {
+  uint32_t l = (uint32_t)x;
+  add_cc(l, l, (uint32_t)(y >> 32));
+  x = (x & 0xffffffff00000000ull) | l;
+}
+inline void addc_hi(uint64_t& x) {
+  uint32_t h = (uint32_t)(x >> 32);
+  addc(h, h, 0);
+  x = (x & 0xffffffffull) | ((uint64_t)h << 32);
+}
 
 #endif
 

@@ -1,0 +1,389 @@
+// Variable-base MSM (Pippenger) over G1/G2, uniform-scalar folds and Fr vector ops.
+//
+// Replaces: `G::msm(normalize_batch(L), R)` of MultiexponentiationInnerProduct
+// (inner_products/src/lib.rs:123-142), PedersenCommitment::commit (pedersen/mod.rs:24-26), the KZG
+// opening MSMs (tipa/mod.rs:333-334), and the "rescale" maps of GIPA/SIPP (gipa.rs:261-291,
+// sipp/src/lib.rs:87-100; scalar-mul primitive `mul_helper`, ip_proofs/src/lib.rs:15-19).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// MSM
+// ------------------------------------------------------------------------------------------------
+struct MsmPlan {
+  int c;       // window bits
+  int nw;      // windows
+  uint32_t B;  // buckets per window (2^c, bucket 0 unused)
+  uint32_t L;  // buckets per reduction chunk
+  uint32_t T;  // chunks per window
+};
+
+static MsmPlan msm_plan(size_t n) {
+  int lg = 0;
+  while (((size_t)2 << lg) <= n) lg++;
+  MsmPlan p;
+  p.c = lg - 2;
+  if (p.c < 4) p.c = 4;
+  if (p.c > 16) p.c = 16;
+  p.nw = (255 + p.c - 1) / p.c;
+  p.B = 1u << p.c;
+  p.L = p.B / 256;
+  if (p.L < 2) p.L = 2;
+  if (p.L > 32) p.L = 32;
+  p.T = p.B / p.L;
+  return p;
+}
+
+__device__ __forceinline__ uint32_t msm_digit(const uint32_t* s, int w, int c) {
+  int o = w * c;
+  int wi = o >> 5, sh = o & 31;
+  uint64_t v = s[wi];
+  if (wi + 1 < 8) v |= (uint64_t)s[wi + 1] << 32;
+  return (uint32_t)(v >> sh) & ((1u << c) - 1);
+}
+
+// canonical scalars + per-(window, bucket) histogram
+__global__ void k_msm_prepare(const Fr* __restrict__ sc, size_t n, Fr* __restrict__ canon, uint32_t* __restrict__ counts,
+                              int c, int nw) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = sc[i].from_mont();
+  canon[i] = s;
+  uint32_t B = 1u << c;
+  for (int w = 0; w < nw; w++) {
+    uint32_t d = msm_digit(s.v, w, c);
+    if (d) atomicAdd(&counts[(size_t)w * B + d], 1u);
+  }
+}
+
+// exclusive scan of counts within each window (one block per window) -> offsets into idx[w*n ..]
+__global__ void k_msm_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                           uint32_t* __restrict__ cursor, uint32_t B, size_t n) {
+  __shared__ uint32_t part[256];
+  int w = blockIdx.x;
+  uint32_t per = (B + 255) / 256;
+  uint32_t lo = threadIdx.x * per, hi = lo + per < B ? lo + per : B;
+  uint32_t s = 0;
+  for (uint32_t j = lo; j < hi; j++) s += counts[(size_t)w * B + j];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int t = 0; t < 256; t++) {
+      uint32_t v = part[t];
+      part[t] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  uint32_t run = part[threadIdx.x] + (uint32_t)((size_t)w * n);
+  for (uint32_t j = lo; j < hi; j++) {
+    offsets[(size_t)w * B + j] = run;
+    cursor[(size_t)w * B + j] = run;
+    run += counts[(size_t)w * B + j];
+  }
+}
+
+__global__ void k_msm_scatter(const Fr* __restrict__ canon, size_t n, uint32_t* __restrict__ cursor,
+                              uint32_t* __restrict__ idx, int c, int nw) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = canon[i];
+  uint32_t B = 1u << c;
+  for (int w = 0; w < nw; w++) {
+    uint32_t d = msm_digit(s.v, w, c);
+    if (d) idx[atomicAdd(&cursor[(size_t)w * B + d], 1u)] = (uint32_t)i;
+  }
+}
+
+// one thread per (window, bucket): sum of the bucket's points
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate(const Aff<F>* __restrict__ bases, const uint32_t* __restrict__ idx,
+                                                        const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ counts, Jac<F>* __restrict__ buckets,
+                                                        size_t total) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t start = offsets[t], cnt = counts[t];
+  Jac<F> acc = Jac<F>::inf();
+  for (uint32_t j = 0; j < cnt; j++) acc = acc.add_mixed(bases[idx[start + j]]);
+  buckets[t] = acc;
+}
+
+// one thread per (window, chunk of L buckets): sum_b b * bucket[b] restricted to the chunk
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_bucket_reduce(const Jac<F>* __restrict__ buckets, uint32_t B, uint32_t L,
+                                                           uint32_t T, Jac<F>* __restrict__ partials, size_t total) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t w = (uint32_t)(t / T), ch = (uint32_t)(t % T);
+  uint32_t j0 = ch * L;  // chunk covers buckets j0 .. j0+L-1 (bucket 0 is empty)
+  Jac<F> run = Jac<F>::inf(), acc = Jac<F>::inf();
+  for (uint32_t b = L; b-- > 0;) {
+    run = run.add(buckets[(size_t)w * B + j0 + b]);
+    if (b > 0) acc = acc.add(run);
+  }
+  // acc = sum_b b_local * bucket, run = sum bucket; add j0 * run
+  if (j0 && !run.is_inf()) {
+    Jac<F> m = Jac<F>::inf();
+    for (int bit = 31 - __clz(j0); bit >= 0; bit--) {
+      m = m.dbl();
+      if ((j0 >> bit) & 1) m = m.add(run);
+    }
+    acc = acc.add(m);
+  }
+  partials[t] = acc;
+}
+
+// segmented sum: out[w][t] = sum in[w][t*R .. min(T, t*R+R))
+template <class F>
+__global__ void __launch_bounds__(128) k_jac_reduce(const Jac<F>* __restrict__ in, uint32_t T, uint32_t R, uint32_t To,
+                                                    Jac<F>* __restrict__ out, size_t total) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t w = (uint32_t)(t / To), k = (uint32_t)(t % To);
+  uint32_t lo = k * R, hi = lo + R < T ? lo + R : T;
+  Jac<F> acc = in[(size_t)w * T + lo];
+  for (uint32_t j = lo + 1; j < hi; j++) acc = acc.add(in[(size_t)w * T + j]);
+  out[t] = acc;
+}
+
+template <class F>
+__global__ void k_msm_horner(const Jac<F>* __restrict__ sums, int nw, int c, Aff<F>* __restrict__ out) {
+  if (threadIdx.x || blockIdx.x) return;
+  Jac<F> acc = sums[nw - 1];
+  for (int w = nw - 2; w >= 0; w--) {
+    for (int j = 0; j < c; j++) acc = acc.dbl();
+    acc = acc.add(sums[w]);
+  }
+  *out = acc.to_affine();
+}
+
+template <class F>
+static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, Aff<F>* out) {
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) {
+    CU(cudaMemsetAsync(out, 0, sizeof(Aff<F>), ctx->stream));
+    return RIPP_OK;
+  }
+  MsmPlan p = msm_plan(n);
+  size_t WB = (size_t)p.nw * p.B;
+  void *canon, *cnt, *idx, *bkt, *parts;
+  OK(scratch(ctx, 4, n * sizeof(Fr), &canon));
+  OK(scratch(ctx, 5, 3 * WB * sizeof(uint32_t), &cnt));
+  OK(scratch(ctx, 6, (size_t)p.nw * n * sizeof(uint32_t), &idx));
+  OK(scratch(ctx, 7, WB * sizeof(Jac<F>), &bkt));
+  OK(scratch(ctx, 8, 2 * (size_t)p.nw * p.T * sizeof(Jac<F>), &parts));
+  uint32_t* counts = (uint32_t*)cnt;
+  uint32_t* offsets = counts + WB;
+  uint32_t* cursor = offsets + WB;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemsetAsync(counts, 0, WB * sizeof(uint32_t), st));
+  k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, n, (Fr*)canon, counts, p.c, p.nw);
+  LAUNCHED(ctx);
+  k_msm_scan<<<p.nw, 256, 0, st>>>(counts, offsets, cursor, p.B, n);
+  LAUNCHED(ctx);
+  k_msm_scatter<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const Fr*)canon, n, cursor, (uint32_t*)idx, p.c, p.nw);
+  LAUNCHED(ctx);
+  k_msm_accumulate<F><<<(unsigned)((WB + 127) / 128), 128, 0, st>>>(bases, (const uint32_t*)idx, offsets, counts,
+                                                                   (Jac<F>*)bkt, WB);
+  LAUNCHED(ctx);
+  size_t WT = (size_t)p.nw * p.T;
+  Jac<F>* pa = (Jac<F>*)parts;
+  Jac<F>* pb = pa + WT;
+  k_msm_bucket_reduce<F><<<(unsigned)((WT + 127) / 128), 128, 0, st>>>((const Jac<F>*)bkt, p.B, p.L, p.T, pa, WT);
+  LAUNCHED(ctx);
+  uint32_t T = p.T;
+  const uint32_t R = 8;
+  while (T > 1) {
+    uint32_t To = (T + R - 1) / R;
+    size_t tot = (size_t)p.nw * To;
+    k_jac_reduce<F><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(pa, T, R, To, pb, tot);
+    LAUNCHED(ctx);
+    Jac<F>* t = pa;
+    pa = pb;
+    pb = t;
+    T = To;
+  }
+  k_msm_horner<F><<<1, 32, 0, st>>>(pa, p.nw, p.c, out);
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}
+
+extern "C" int ripp_msm_g1_dev(ripp_ctx* ctx, const void* bases, const void* sc, size_t n, void* out) {
+  if (!ctx || !out || (n && (!bases || !sc))) return fail(RIPP_ERR_ARG, "null argument");
+  return msm_dev<Fq>(ctx, (const G1Aff*)bases, (const Fr*)sc, n, (G1Aff*)out);
+}
+extern "C" int ripp_msm_g2_dev(ripp_ctx* ctx, const void* bases, const void* sc, size_t n, void* out) {
+  if (!ctx || !out || (n && (!bases || !sc))) return fail(RIPP_ERR_ARG, "null argument");
+  return msm_dev<Fq2>(ctx, (const G2Aff*)bases, (const Fr*)sc, n, (G2Aff*)out);
+}
+
+template <class F>
+__global__ void k_normalize_any(const Jac<F>* __restrict__ in, Aff<F>* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Jac<F> p = in[i];
+  out[i] = p.is_inf() ? Aff<F>::inf() : (p.z == F::one() ? Aff<F>{p.x, p.y} : p.to_affine());
+}
+template <class F>
+__global__ void k_aff_to_jac(const Aff<F>* __restrict__ in, Jac<F>* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = Jac<F>::from_affine(in[i]);
+}
+
+// MultiexponentiationInnerProduct::inner_product (inner_products/src/lib.rs:123-142), host pointers
+template <class F>
+static int msm_host(ripp_ctx* ctx, const void* bases_jac, size_t nl, const void* sc, size_t nr, void* out_jac) {
+  if (!ctx || !out_jac) return fail(RIPP_ERR_ARG, "null argument");
+  if (nl != nr)
+    return fail(RIPP_ERR_LEN_MISMATCH, "left length, right length: " + std::to_string(nl) + ", " + std::to_string(nr));
+  size_t n = nl;
+  if (n && (!bases_jac || !sc)) return fail(RIPP_ERR_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  size_t o_sc = (n * sizeof(Jac<F>) + 255) & ~(size_t)255;
+  size_t o_aff = o_sc + ((n * sizeof(Fr) + 255) & ~(size_t)255);
+  size_t o_out = o_aff + ((n * sizeof(Aff<F>) + 255) & ~(size_t)255);
+  void* buf;
+  OK(scratch(ctx, 0, o_out + 1024, &buf));
+  char* d = (char*)buf;
+  if (n) {
+    CU(cudaMemcpyAsync(d, bases_jac, n * sizeof(Jac<F>), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d + o_sc, sc, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    k_normalize_any<F><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const Jac<F>*)d, (Aff<F>*)(d + o_aff), n);
+    LAUNCHED(ctx);
+  }
+  OK(msm_dev<F>(ctx, (const Aff<F>*)(d + o_aff), (const Fr*)(d + o_sc), n, (Aff<F>*)(d + o_out)));
+  k_aff_to_jac<F><<<1, 32, 0, ctx->stream>>>((const Aff<F>*)(d + o_out), (Jac<F>*)(d + o_out + 512), 1);
+  LAUNCHED(ctx);
+  CU(cudaMemcpyAsync(out_jac, d + o_out + 512, sizeof(Jac<F>), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RIPP_OK;
+}
+extern "C" int ripp_msm_g1(ripp_ctx* ctx, const void* b, size_t nl, const void* s, size_t nr, void* out) {
+  return msm_host<Fq>(ctx, b, nl, s, nr, out);
+}
+extern "C" int ripp_msm_g2(ripp_ctx* ctx, const void* b, size_t nl, const void* s, size_t nr, void* out) {
+  return msm_host<Fq2>(ctx, b, nl, s, nr, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// folds with one scalar shared by all elements: out[i] = hi[i] * c + lo[i]
+// ------------------------------------------------------------------------------------------------
+struct ScalarBits {
+  uint32_t w[8];
+  int nbits;
+};
+
+static ScalarBits scalar_bits(const void* fr_mont_host) {
+  Fr s;
+  memcpy(s.v, fr_mont_host, sizeof(Fr));
+  s = s.from_mont();
+  ScalarBits b;
+  b.nbits = 0;
+  for (int i = 0; i < 8; i++) {
+    b.w[i] = s.v[i];
+    if (s.v[i]) b.nbits = 32 * i + (32 - __builtin_clz(s.v[i]));
+  }
+  return b;
+}
+
+template <class F>
+__global__ void __launch_bounds__(64, 8) k_fold(const Aff<F>* __restrict__ hi, const Aff<F>* __restrict__ lo, ScalarBits c,
+                                                size_t n, Aff<F>* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Jac<F> acc = scalar_mul(hi[i], c.w, c.nbits);
+  acc = acc.add_mixed(lo[i]);
+  out[i] = acc.to_affine();
+}
+
+template <class F>
+static int fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c, size_t n, void* out) {
+  if (!ctx || !c || (n && (!hi || !lo || !out))) return fail(RIPP_ERR_ARG, "null argument");
+  if (n == 0) return RIPP_OK;
+  CU(cudaSetDevice(ctx->device));
+  k_fold<F><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const Aff<F>*)hi, (const Aff<F>*)lo, scalar_bits(c), n,
+                                                            (Aff<F>*)out);
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}
+extern "C" int ripp_g1_fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c, size_t n, void* out) {
+  return fold_dev<Fq>(ctx, hi, lo, c, n, out);
+}
+extern "C" int ripp_g2_fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c, size_t n, void* out) {
+  return fold_dev<Fq2>(ctx, hi, lo, c, n, out);
+}
+
+__global__ void k_fr_fold(const Fr* __restrict__ hi, const Fr* __restrict__ lo, Fr c, size_t n, Fr* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = hi[i] * c + lo[i];
+}
+extern "C" int ripp_fr_fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c, size_t n, void* out) {
+  if (!ctx || !c || (n && (!hi || !lo || !out))) return fail(RIPP_ERR_ARG, "null argument");
+  if (n == 0) return RIPP_OK;
+  CU(cudaSetDevice(ctx->device));
+  Fr cc;
+  memcpy(cc.v, c, sizeof(Fr));
+  k_fr_fold<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const Fr*)hi, (const Fr*)lo, cc, n, (Fr*)out);
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ScalarInnerProduct (inner_products/src/lib.rs:149-166): sum a_i b_i in Fr
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fr_dot(const Fr* __restrict__ a, const Fr* __restrict__ b, size_t n, uint32_t R, Fr* __restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * R;
+  if (lo >= n) return;
+  size_t hi = lo + R < n ? lo + R : n;
+  Fr acc = Fr::zero();
+  for (size_t j = lo; j < hi; j++) acc = acc + (b ? a[j] * b[j] : a[j]);
+  out[t] = acc;
+}
+
+extern "C" int ripp_scalar_ip_dev(ripp_ctx* ctx, const void* a, const void* b, size_t n, void* out) {
+  if (!ctx || !out || (n && (!a || !b))) return fail(RIPP_ERR_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) {
+    CU(cudaMemsetAsync(out, 0, sizeof(Fr), ctx->stream));
+    return RIPP_OK;
+  }
+  const uint32_t R = 16;
+  size_t m = (n + R - 1) / R;
+  void* buf;
+  OK(scratch(ctx, 9, 2 * m * sizeof(Fr) + 64, &buf));
+  Fr* pa = (Fr*)buf;
+  Fr* pb = pa + m;
+  k_fr_dot<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>((const Fr*)a, (const Fr*)b, n, R, m == 1 ? (Fr*)out : pa);
+  LAUNCHED(ctx);
+  while (m > 1) {
+    size_t mo = (m + R - 1) / R;
+    k_fr_dot<<<(unsigned)((mo + 127) / 128), 128, 0, ctx->stream>>>(pa, nullptr, m, R, mo == 1 ? (Fr*)out : pb);
+    LAUNCHED(ctx);
+    Fr* t = pa;
+    pa = pb;
+    pb = t;
+    m = mo;
+  }
+  return RIPP_OK;
+}
+
+extern "C" int ripp_scalar_ip(ripp_ctx* ctx, const void* a, size_t nl, const void* b, size_t nr, void* out) {
+  if (!ctx || !out) return fail(RIPP_ERR_ARG, "null argument");
+  if (nl != nr)
+    return fail(RIPP_ERR_LEN_MISMATCH, "left length, right length: " + std::to_string(nl) + ", " + std::to_string(nr));
+  size_t n = nl;
+  CU(cudaSetDevice(ctx->device));
+  void* buf;
+  OK(scratch(ctx, 0, 2 * n * sizeof(Fr) + 256, &buf));
+  Fr* d = (Fr*)buf;
+  if (n) {
+    CU(cudaMemcpyAsync(d, a, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d + n, b, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  OK(ripp_scalar_ip_dev(ctx, d, d + n, n, d + 2 * n));
+  CU(cudaMemcpyAsync(out, d + 2 * n, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RIPP_OK;
+}

@@ -1,64 +1,8 @@
 // ripp_b200: CUDA kernels (sm_100a) + C ABI (include/ripp_b200.h).
-#include <cuda_runtime.h>
-#include <stdio.h>
-#include <string.h>
+#include "common.cuh"
 
-#include <string>
-#include <vector>
-
-#include "../../include/ripp_b200.h"
-#include "pairing.cuh"
-
-using namespace ripp;
-
-// ------------------------------------------------------------------------------------------------
-// context / errors
-// ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-
-struct ripp_ctx {
-  int device;
-  cudaStream_t stream;
-  cudaStream_t own_stream;
-  uint64_t launches;
-  // scratch (grown on demand)
-  void* scratch[4];
-  size_t scratch_bytes[4];
-};
-
-static int fail(int code, const std::string& msg) {
-  g_err = msg;
-  return code;
-}
-#define CU(call)                                                                                         \
-  do {                                                                                                   \
-    cudaError_t e_ = (call);                                                                             \
-    if (e_ != cudaSuccess)                                                                               \
-      return fail(RIPP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + \
-                                     std::to_string(__LINE__));                                          \
-  } while (0)
-#define OK(call)              \
-  do {                        \
-    int s_ = (call);          \
-    if (s_ != RIPP_OK) return s_; \
-  } while (0)
-#define LAUNCHED(ctx)        \
-  do {                       \
-    (ctx)->launches++;       \
-    CU(cudaGetLastError());  \
-  } while (0)
-
-static int scratch(ripp_ctx* ctx, int slot, size_t bytes, void** out) {
-  if (ctx->scratch_bytes[slot] < bytes) {
-    if (ctx->scratch[slot]) CU(cudaFree(ctx->scratch[slot]));
-    ctx->scratch[slot] = nullptr;
-    ctx->scratch_bytes[slot] = 0;
-    CU(cudaMalloc(&ctx->scratch[slot], bytes));
-    ctx->scratch_bytes[slot] = bytes;
-  }
-  *out = ctx->scratch[slot];
-  return RIPP_OK;
-}
+std::string& ripp_err_slot() { return g_err; }
 
 extern "C" const char* ripp_last_error_string(void) { return g_err.c_str(); }
 
@@ -83,7 +27,7 @@ extern "C" void ripp_ctx_destroy(ripp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < RIPP_SCRATCH_SLOTS; i++)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -155,8 +99,11 @@ __device__ __forceinline__ Fq12 shfl_xor_fq12(const Fq12& a, int m) {
   return r;
 }
 
+#ifndef RIPP_MILLER_THREADS_PER_SM
+#define RIPP_MILLER_THREADS_PER_SM 256
+#endif
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_miller(const G1Aff* __restrict__ ps, const G2Aff* __restrict__ qs, size_t n,
+__global__ void __launch_bounds__(BLOCK, RIPP_MILLER_THREADS_PER_SM / BLOCK) k_miller(const G1Aff* __restrict__ ps, const G2Aff* __restrict__ qs, size_t n,
                                                  Fq12* __restrict__ partials) {
   size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x;
   Fq12 f = Fq12::one();
@@ -186,7 +133,7 @@ __global__ void k_final_exp(const Fq12* __restrict__ in, Fq12* __restrict__ out,
 // kernels: element-wise scalar multiplication with distinct scalars (K8)
 // ------------------------------------------------------------------------------------------------
 template <class F, bool GEN>
-__global__ void __launch_bounds__(64) k_scale(const Aff<F>* __restrict__ pts, const Fr* __restrict__ sc, size_t n,
+__global__ void __launch_bounds__(64, 8) k_scale(const Aff<F>* __restrict__ pts, const Fr* __restrict__ sc, size_t n,
                                               Aff<F>* __restrict__ out, Aff<F> gen) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

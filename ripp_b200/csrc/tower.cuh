@@ -17,10 +17,10 @@ struct Fq2 {
   RIPP_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
   RIPP_HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
   RIPP_HD bool operator!=(const Fq2& b) const { return !(*this == b); }
-  RIPP_HD Fq2 operator+(const Fq2& b) const { return {c0 + b.c0, c1 + b.c1}; }
-  RIPP_HD Fq2 operator-(const Fq2& b) const { return {c0 - b.c0, c1 - b.c1}; }
-  RIPP_HD Fq2 operator-() const { return {-c0, -c1}; }
-  RIPP_HD Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+  RIPP_FN Fq2 operator+(const Fq2& b) const { return {c0 + b.c0, c1 + b.c1}; }
+  RIPP_FN Fq2 operator-(const Fq2& b) const { return {c0 - b.c0, c1 - b.c1}; }
+  RIPP_FN Fq2 operator-() const { return {-c0, -c1}; }
+  RIPP_FN Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
   RIPP_HD Fq2 conj() const { return {c0, -c1}; }
   // Karatsuba: 3 Fq products
   RIPP_FN Fq2 operator*(const Fq2& b) const {
@@ -34,10 +34,10 @@ struct Fq2 {
     Fq t = c0 * c1;
     return {(c0 + c1) * (c0 - c1), t.dbl()};
   }
-  RIPP_HD Fq2 mul_fq(const Fq& s) const { return {c0 * s, c1 * s}; }
-  RIPP_HD Fq2 half() const { return {c0.half(), c1.half()}; }
+  RIPP_FN Fq2 mul_fq(const Fq& s) const { return {c0 * s, c1 * s}; }
+  RIPP_FN Fq2 half() const { return {c0.half(), c1.half()}; }
   // times xi = 1 + u
-  RIPP_HD Fq2 mul_xi() const { return {c0 - c1, c0 + c1}; }
+  RIPP_FN Fq2 mul_xi() const { return {c0 - c1, c0 + c1}; }
   RIPP_HD Fq2 inv() const {
     Fq d = (c0.sqr() + c1.sqr()).inv();
     return {c0 * d, -(c1 * d)};
@@ -71,14 +71,14 @@ struct Fq6 {
   // times v
   RIPP_HD Fq6 mul_v() const { return {c2.mul_xi(), c0, c1}; }
   // Karatsuba / Toom-style: 6 Fq2 products
-  RIPP_HD Fq6 operator*(const Fq6& b) const {
+  RIPP_FN Fq6 operator*(const Fq6& b) const {
     Fq2 a0 = c0 * b.c0, a1 = c1 * b.c1, a2 = c2 * b.c2;
     Fq2 t0 = ((c1 + c2) * (b.c1 + b.c2) - a1 - a2).mul_xi() + a0;
     Fq2 t1 = (c0 + c1) * (b.c0 + b.c1) - a0 - a1 + a2.mul_xi();
     Fq2 t2 = (c0 + c2) * (b.c0 + b.c2) - a0 - a2 + a1;
     return {t0, t1, t2};
   }
-  RIPP_HD Fq6 sqr() const {
+  RIPP_FN Fq6 sqr() const {
     // CH-SQR2: 2 Fq2 products + 3 squarings
     Fq2 s0 = c0.sqr();
     Fq2 ab = c0 * c1;
@@ -90,7 +90,7 @@ struct Fq6 {
     return {s0 + s3.mul_xi(), s1 + s4.mul_xi(), s1 + s2 + s3 - s0 - s4};
   }
   // sparse: times (b0 + b1 v): 5 Fq2 products
-  RIPP_HD Fq6 mul_by_01(const Fq2& b0, const Fq2& b1) const {
+  RIPP_FN Fq6 mul_by_01(const Fq2& b0, const Fq2& b1) const {
     Fq2 a0 = c0 * b0, a1 = c1 * b1;
     Fq2 t0 = ((c1 + c2) * b1 - a1).mul_xi() + a0;
     Fq2 t1 = (c0 + c1) * (b0 + b1) - a0 - a1;
@@ -98,7 +98,7 @@ struct Fq6 {
     return {t0, t1, t2};
   }
   // sparse: times (b1 v): 3 Fq2 products
-  RIPP_HD Fq6 mul_by_1(const Fq2& b1) const { return {(c2 * b1).mul_xi(), c0 * b1, c1 * b1}; }
+  RIPP_FN Fq6 mul_by_1(const Fq2& b1) const { return {(c2 * b1).mul_xi(), c0 * b1, c1 * b1}; }
   RIPP_HD Fq6 mul_fq2(const Fq2& s) const { return {c0 * s, c1 * s, c2 * s}; }
   RIPP_FN Fq6 inv() const {
     Fq2 t0 = c0.sqr() - (c1 * c2).mul_xi();

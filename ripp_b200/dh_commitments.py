@@ -1,5 +1,9 @@
 """Host-side mirror of `dh_commitments/src` (trait DoublyHomomorphicCommitment, lib.rs:20-55)."""
-from .inner_products import PairingInnerProduct
+from .inner_products import (
+    MultiexponentiationInnerProductG1,
+    MultiexponentiationInnerProductG2,
+    PairingInnerProduct,
+)
 
 
 class _Commitment:
@@ -23,3 +27,17 @@ class AFGHOCommitmentG2(_Commitment):
     @staticmethod
     def commit(k, m, ctx=None):
         return PairingInnerProduct.inner_product(k, m, ctx)
+
+
+class PedersenCommitmentG1(_Commitment):
+    """pedersen/mod.rs:14-27 with G = G1: commit = MSM(keys, msgs)."""
+
+    @staticmethod
+    def commit(k, m, ctx=None):
+        return MultiexponentiationInnerProductG1.inner_product(k, m, ctx)
+
+
+class PedersenCommitmentG2(_Commitment):
+    @staticmethod
+    def commit(k, m, ctx=None):
+        return MultiexponentiationInnerProductG2.inner_product(k, m, ctx)

@@ -1,0 +1,106 @@
+"""MultiexponentiationInnerProduct / Pedersen / ScalarInnerProduct and the fold kernels on the GPU
+against the oracle.  Mirrors dh_commitments/src/pedersen/mod.rs:40-54 (correct verifies, wrong does
+not, wrong length errors)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bls12_381 as E
+from oracle import synth as OS
+from ripp_b200 import _lib, codec as C, synth
+
+pytestmark = pytest.mark.gpu
+rnd = random.Random(99)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 5, 33, 100, 300])
+def test_msm_g1_matches_oracle(ctx, n):
+    from ripp_b200.inner_products import MultiexponentiationInnerProductG1 as IP
+
+    pts = OS.g1_points("m-a", n, seed=n)
+    sc = [rnd.randrange(E.R) for _ in range(n)]
+    if n >= 5:
+        sc[0], sc[1], sc[2] = 0, 1, E.R - 1
+        pts[3] = None
+    if n >= 33:  # repeated points and P, -P in the same MSM
+        pts[10] = pts[11]
+        pts[12] = E.g1_neg(pts[13])
+        sc[12] = sc[13]
+    assert IP.inner_product(pts, sc, ctx) == E.msm(pts, sc, E.g1_add, E.g1_mul)
+
+
+@pytest.mark.parametrize("n", [1, 7, 64, 130])
+def test_msm_g2_matches_oracle(ctx, n):
+    from ripp_b200.inner_products import MultiexponentiationInnerProductG2 as IP
+
+    pts = OS.g2_points("m-b", n, seed=n)
+    sc = [rnd.randrange(E.R) for _ in range(n)]
+    assert IP.inner_product(pts, sc, ctx) == E.msm(pts, sc, E.g2_add, E.g2_mul)
+
+
+def test_msm_linearity_at_scale(ctx):
+    """sum s_i (t_i G) = (sum s_i t_i) G at 2^14 points; oracle does one scalar multiplication."""
+    n = 1 << 14
+    t = synth.scalars("lin-t", n)
+    s = synth.scalars("lin-s", n)
+    bases = synth.g1_points_dev(ctx, "lin-t", n)
+    sc = ctx.to_device(C.fr_vec_enc(s))
+    out = ctx.alloc(96)
+    ctx.msm_g1_dev(bases, sc, n, out)
+    e = sum(a * b for a, b in zip(s, t)) % E.R
+    assert C.g1_dec(out.download(24)) == E.g1_mul(E.G1_GEN, e)
+    bases2 = synth.g2_points_dev(ctx, "lin-t", n)
+    out2 = ctx.alloc(192)
+    ctx.msm_g2_dev(bases2, sc, n, out2)
+    assert C.g2_dec(out2.download(48)) == E.g2_mul(E.G2_GEN, e)
+
+
+def test_pedersen_commitment(ctx):
+    from ripp_b200.dh_commitments import PedersenCommitmentG1 as Ped
+
+    n = 8
+    ck = OS.g1_points("ped-ck", n)
+    msg = [rnd.randrange(E.R) for _ in range(n)]
+    wrong = [rnd.randrange(E.R) for _ in range(n)]
+    com = Ped.commit(ck, msg, ctx)
+    assert com == E.msm(ck, msg, E.g1_add, E.g1_mul)
+    assert Ped.verify(ck, msg, com, ctx)
+    assert not Ped.verify(ck, wrong, com, ctx)
+    with pytest.raises(_lib.LengthMismatch):
+        Ped.verify(ck[:-1], msg, com, ctx)
+
+
+def test_scalar_inner_product(ctx):
+    from ripp_b200.inner_products import ScalarInnerProduct as IP
+
+    for n in (0, 1, 17, 1000):
+        a = [rnd.randrange(E.R) for _ in range(n)]
+        b = [rnd.randrange(E.R) for _ in range(n)]
+        assert IP.inner_product(a, b, ctx) == sum(x * y for x, y in zip(a, b)) % E.R
+    with pytest.raises(_lib.LengthMismatch):
+        IP.inner_product([1, 2], [3], ctx)
+
+
+@pytest.mark.parametrize("cbits", [255, 128, 1])
+def test_folds(ctx, cbits):
+    """out[i] = hi[i] * c + lo[i] (gipa.rs:261-291) for G1, G2 and Fr."""
+    n = 37
+    c = rnd.randrange(1 << (cbits - 1), min(E.R, 1 << cbits)) if cbits > 1 else 1
+    ch = C.fr_enc(c).copy()
+    hi1, lo1 = OS.g1_points("f-hi", n), OS.g1_points("f-lo", n)
+    hi2, lo2 = OS.g2_points("f-hi", n), OS.g2_points("f-lo", n)
+    lo1[0], hi1[1] = None, None
+    lo1[2] = E.g1_neg(E.g1_mul(hi1[2], c))  # result is the identity
+    d_hi, d_lo = ctx.to_device(C.g1_vec_enc(hi1)), ctx.to_device(C.g1_vec_enc(lo1))
+    ctx.g1_fold_dev(d_hi, d_lo, ch, n, d_lo)  # in place over lo
+    assert C.g1_vec_dec(d_lo.download((n, 24))) == [E.g1_add(E.g1_mul(h, c), l) for h, l in zip(hi1, lo1)]
+    d_hi, d_lo = ctx.to_device(C.g2_vec_enc(hi2)), ctx.to_device(C.g2_vec_enc(lo2))
+    out = ctx.alloc(n * 192)
+    ctx.g2_fold_dev(d_hi, d_lo, ch, n, out)
+    assert C.g2_vec_dec(out.download((n, 48))) == [E.g2_add(E.g2_mul(h, c), l) for h, l in zip(hi2, lo2)]
+    a = [rnd.randrange(E.R) for _ in range(n)]
+    b = [rnd.randrange(E.R) for _ in range(n)]
+    d_a, d_b = ctx.to_device(C.fr_vec_enc(a)), ctx.to_device(C.fr_vec_enc(b))
+    ctx.fr_fold_dev(d_a, d_b, ch, n, d_b)
+    assert C.fr_vec_dec(d_b.download((n, 8))) == [(x * c + y) % E.R for x, y in zip(a, b)]
