@@ -73,6 +73,10 @@ int ripp_pairing_ip_affine(ripp_ctx* ctx, const void* g1_aff, size_t n_left, con
                            void* gt_out);
 /* Device-resident variant: affine device vectors, result written to device memory (576 B). */
 int ripp_pairing_ip_dev(ripp_ctx* ctx, const void* g1_aff_dev, const void* g2_aff_dev, size_t n, void* gt_out_dev);
+/* Several equal-length products in ONE launch (the six commitments of a GIPA round, gipa.rs:220-231):
+ * g1_aff_dev / g2_aff_dev are HOST arrays of nseg (<= 8) device pointers; out gets nseg GT values. */
+int ripp_pairing_ip_batch_dev(ripp_ctx* ctx, int nseg, const void* const* g1_aff_dev, const void* const* g2_aff_dev,
+                              size_t n, void* gt_out_dev);
 /* Sharded variant for multi-GPU: product of Miller-loop values of this rank's
  * slice WITHOUT the final exponentiation (one Fq12 partial, device memory) ... */
 int ripp_miller_partial_dev(ripp_ctx* ctx, const void* g1_aff_dev, const void* g2_aff_dev, size_t n,
@@ -112,6 +116,54 @@ int ripp_fr_fold_dev(ripp_ctx* ctx, const void* hi_dev, const void* lo_dev, cons
  * device memory. */
 int ripp_g1_scale_dev(ripp_ctx* ctx, const void* g1_aff_dev, const void* fr_dev, size_t n, void* g1_aff_out_dev);
 int ripp_g2_scale_dev(ripp_ctx* ctx, const void* g2_aff_dev, const void* fr_dev, size_t n, void* g2_aff_out_dev);
+
+/* ---- L3: device-resident provers ------------------------------------------------------------ */
+/* Instantiations of GIPA<IP, LMC, RMC, IPC, Blake2b> (ip_proofs/src/gipa.rs:16-22); element types of
+ * (left message A, right message B, left key v, right key w): */
+typedef enum ripp_gipa_kind {
+  RIPP_GIPA_PAIRING = 0,               /* Pairing, AFGHO-G1, AFGHO-G2, Identity<GT>: (G1, G2, G2, G1)   gipa.rs:472-475 */
+  RIPP_GIPA_MULTIEXP_PEDERSEN = 1,     /* Multiexp<G1>, AFGHO-G1, Pedersen<G1>, Identity<G1>: (G1, Fr, G2, G1)  gipa.rs:500-503 */
+  RIPP_GIPA_MULTIEXP_SSM = 2,          /* Multiexp<G1>, AFGHO-G1, SSMPlaceholder, Identity<G1>: (G1, Fr, G2, -)
+                                          structured_scalar_message.rs:130-136, groth16_aggregation.rs:42-48 */
+  RIPP_GIPA_SCALAR_PEDERSEN_G2_G2 = 3, /* Scalar, Pedersen<G2>, Pedersen<G2>, Identity<Fr>: (Fr, Fr, G2, G2)  gipa.rs:531-536 */
+  RIPP_GIPA_SCALAR_PEDERSEN_G2_G1 = 4, /* Scalar, Pedersen<G2>, Pedersen<G1>, Identity<Fr>: (Fr, Fr, G2, G1)  tipa/mod.rs:501-506 */
+  RIPP_GIPA_SCALAR_SSM = 5             /* Scalar, Pedersen<G2>, SSMPlaceholder, Identity<Fr>: (Fr, Fr, G2, -)
+                                          structured_scalar_message.rs:392-423 */
+} ripp_gipa_kind;
+
+/* GIPA::prove_with_aux (gipa.rs:162-178 -> _prove :181-312).  Vectors are device resident (affine
+ * points / Fr), n a power of two; they are not modified.  Runs all log2(n) rounds on the device.
+ *   proof_out      GIPAProof in arkworks serialize_uncompressed bytes (steps reversed as gipa.rs:298-299,
+ *                  then r_base); *proof_len receives the length (also when proof_cap is too small)
+ *   transcript_out log2(n) Fr (Montgomery): GIPAAux::r_transcript, may be NULL
+ *   ck_base_out    GIPAAux::ck_base = (v0, w0) serialised */
+int ripp_gipa_prove_dev(ripp_ctx* ctx, int kind, const void* a_dev, const void* b_dev, const void* v_dev,
+                        const void* w_dev, size_t n, uint8_t* proof_out, size_t proof_cap, size_t* proof_len,
+                        void* transcript_out, uint8_t* ck_base_out, size_t ck_cap, size_t* ck_len);
+
+/* prove_commitment_key_kzg_opening (tipa/mod.rs:304-337): opening of the product-form polynomial
+ * f(X) = prod_j (1 + x_j r^(2^j) X^(2^(j+1))) at z over n_srs = 2*2^k - 1 SRS powers (device).
+ * transcript (k Fr), r_shift, z: host, Montgomery.  Result: one affine point (host). */
+int ripp_kzg_open_g1_dev(ripp_ctx* ctx, const void* srs_g1_dev, size_t n_srs, const void* transcript, size_t k,
+                         const void* r_shift, const void* z, void* g1_aff_out);
+int ripp_kzg_open_g2_dev(ripp_ctx* ctx, const void* srs_g2_dev, size_t n_srs, const void* transcript, size_t k,
+                         const void* r_shift, const void* z, void* g2_aff_out);
+
+/* TIPA::prove_with_srs_shift (tipa/mod.rs:176-231) for kinds with a G1 right key, and
+ * TIPAWithSSM::prove_with_structured_scalar_message (structured_scalar_message.rs:211-268) for the
+ * *_SSM kinds (w_dev NULL, r_shift ignored).  srs_g1 = g^(alpha^i), srs_g2 = h^(beta^i), i < 2n-1.
+ * r_shift: one Fr (host, Montgomery) or NULL for 1.  Output: TIPAProof / TIPAWithSSMProof bytes. */
+int ripp_tipa_prove_dev(ripp_ctx* ctx, int kind, const void* srs_g1_dev, const void* srs_g2_dev, const void* a_dev,
+                        const void* b_dev, const void* v_dev, const void* w_dev, size_t n, const void* r_shift,
+                        uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
+/* ---- L4: aggregate_proofs (applications/groth16_aggregation.rs:77-160) ------------------------ */
+/* a, c: n G1 affine; b: n G2 affine (the Groth16 proofs' A, B, C); SRS as above.  Output bytes:
+ * com_a, com_b, com_c, ip_ab (GT), agg_c (G1), TIPAProof(ab), TIPAWithSSMProof(c) -- the field order
+ * of AggregateProof (:58-66).  Fails with RIPP_ERR_INNER_PRODUCT if the :133-136 assertion fails. */
+int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, const void* srs_g2_dev, const void* a_dev,
+                            const void* b_dev, const void* c_dev, size_t n, uint8_t* proof_out, size_t proof_cap,
+                            size_t* proof_len);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* Element-wise primitive ops on device, used by the GPU parity tests to pin the PTX limb layer:

@@ -33,6 +33,10 @@ class RippError(RuntimeError):
         self.status = status
 
 
+GIPA_PAIRING, GIPA_MULTIEXP_PEDERSEN, GIPA_MULTIEXP_SSM = 0, 1, 2
+GIPA_SCALAR_PEDERSEN_G2_G2, GIPA_SCALAR_PEDERSEN_G2_G1, GIPA_SCALAR_SSM = 3, 4, 5
+
+
 class LengthMismatch(RippError):
     """InnerProductError::MessageLengthInvalid (inner_products/src/lib.rs:18-38)."""
 
@@ -200,6 +204,46 @@ class Context:
 
     def fr_fold_dev(self, hi, lo, c_host, n, out):
         check(lib().ripp_fr_fold_dev(self.handle, _p(hi), _p(lo), _p(c_host), ctypes.c_size_t(n), _p(out)))
+
+    # ---- L3 / L4 ------------------------------------------------------------------------------
+    def gipa_prove_dev(self, kind, a, b, v, w, n):
+        """-> (GIPAProof bytes, r_transcript (k, 8) uint32, ck_base bytes)."""
+        k = max(n.bit_length() - 1, 0)
+        cap = 64 + k * 6 * 600 + 2 * 600
+        proof = np.empty(cap, dtype=np.uint8)
+        plen, cklen = ctypes.c_size_t(), ctypes.c_size_t()
+        tr = np.zeros((k, 8), dtype=np.uint32)
+        ck = np.empty(1024, dtype=np.uint8)
+        check(lib().ripp_gipa_prove_dev(self.handle, int(kind), _p(a), _p(b), _p(v), _p(w), ctypes.c_size_t(n), _p(proof),
+                                        ctypes.c_size_t(cap), ctypes.byref(plen), _p(tr), _p(ck), ctypes.c_size_t(1024),
+                                        ctypes.byref(cklen)))
+        return proof[: plen.value].tobytes(), tr, ck[: cklen.value].tobytes()
+
+    def tipa_prove_dev(self, kind, srs_g1, srs_g2, a, b, v, w, n, r_shift=None):
+        k = max(n.bit_length() - 1, 0)
+        cap = 64 + k * 6 * 600 + 8 * 600
+        proof = np.empty(cap, dtype=np.uint8)
+        plen = ctypes.c_size_t()
+        check(lib().ripp_tipa_prove_dev(self.handle, int(kind), _p(srs_g1), _p(srs_g2), _p(a), _p(b), _p(v), _p(w),
+                                        ctypes.c_size_t(n), _p(r_shift), _p(proof), ctypes.c_size_t(cap), ctypes.byref(plen)))
+        return proof[: plen.value].tobytes()
+
+    def kzg_open_dev(self, group, srs, n_srs, transcript, r_shift, z):
+        k = len(transcript)
+        out = np.zeros(24 if group == 1 else 48, dtype=np.uint32)
+        fn = lib().ripp_kzg_open_g1_dev if group == 1 else lib().ripp_kzg_open_g2_dev
+        check(fn(self.handle, _p(srs), ctypes.c_size_t(n_srs), _p(np.ascontiguousarray(transcript)), ctypes.c_size_t(k),
+                 _p(r_shift), _p(z), _p(out)))
+        return out
+
+    def tipp_aggregate_dev(self, srs_g1, srs_g2, a, b, c, n):
+        k = max(n.bit_length() - 1, 0)
+        cap = 8 * 600 + 2 * (64 + k * 6 * 600 + 8 * 600)
+        proof = np.empty(cap, dtype=np.uint8)
+        plen = ctypes.c_size_t()
+        check(lib().ripp_tipp_aggregate_dev(self.handle, _p(srs_g1), _p(srs_g2), _p(a), _p(b), _p(c), ctypes.c_size_t(n),
+                                            _p(proof), ctypes.c_size_t(cap), ctypes.byref(plen)))
+        return proof[: plen.value].tobytes()
 
     # ---- diagnostics ----------------------------------------------------------------------
     def test_elementwise(self, op, a, b, out_words):

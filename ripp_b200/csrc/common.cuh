@@ -17,7 +17,8 @@ using namespace ripp;
 // ------------------------------------------------------------------------------------------------
 std::string& ripp_err_slot();
 
-#define RIPP_SCRATCH_SLOTS 12
+#define RIPP_SCRATCH_SLOTS 16
+#define RIPP_MAX_BATCH 8
 struct ripp_ctx {
   int device;
   cudaStream_t stream;
@@ -62,3 +63,6 @@ static inline int scratch(ripp_ctx* ctx, int slot, size_t bytes, void** out) {
   return RIPP_OK;
 }
 
+
+// cross-file internals
+int ripp_pairing_batch_internal(ripp_ctx* ctx, int nseg, const void* const* g1, const void* const* g2, size_t n, void* out);

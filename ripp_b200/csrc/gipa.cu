@@ -1,0 +1,523 @@
+// Device-resident GIPA / TIPA / TIPA-with-structured-scalar-message provers and the TIPP Groth16
+// aggregation prover.  The four state vectors of a GIPA instance stay in HBM across the log n
+// halving rounds; per round only the six commitment values (<= 6 x 576 B) come back to the host
+// for the Fiat-Shamir hash, and one 32-byte challenge goes down with the fold launches.
+//
+// Restates (paths relative to the arkworks-rs/ripp checkout):
+//   ip_proofs/src/gipa.rs:162-312                      GIPA::prove_with_aux / _prove
+//   ip_proofs/src/tipa/mod.rs:176-231,304-337,393-422  TIPA::prove_with_srs_shift + KZG openings
+//   ip_proofs/src/tipa/structured_scalar_message.rs:211-268
+//   ip_proofs/src/applications/groth16_aggregation.rs:77-160  aggregate_proofs
+// Outputs are arkworks `serialize_uncompressed` bytes (what derive(CanonicalSerialize) emits for
+// GIPAProof / TIPAProof / TIPAWithSSMProof), so the Rust shim deserialises them directly.
+#include "common.cuh"
+#include "hash.h"
+
+typedef std::vector<uint8_t> Bytes;
+
+// ------------------------------------------------------------------------------------------------
+// host-side serialisation (ark-serialize 0.4 uncompressed)
+// ------------------------------------------------------------------------------------------------
+static void put_fr(Bytes& o, const Fr& m) {
+  Fr c = m.from_mont();
+  const uint8_t* p = (const uint8_t*)c.v;
+  o.insert(o.end(), p, p + 32);
+}
+static void put_fq_le(Bytes& o, const Fq& m) {
+  Fq c = m.from_mont();
+  const uint8_t* p = (const uint8_t*)c.v;
+  o.insert(o.end(), p, p + 48);
+}
+static void put_fq_be(Bytes& o, const Fq& m, uint8_t flags = 0) {
+  Fq c = m.from_mont();
+  const uint8_t* p = (const uint8_t*)c.v;
+  size_t at = o.size();
+  for (int i = 47; i >= 0; i--) o.push_back(p[i]);
+  o[at] |= flags;
+}
+static void put_gt(Bytes& o, const Fq12& f) {
+  const Fq* c = reinterpret_cast<const Fq*>(&f);
+  for (int i = 0; i < 12; i++) put_fq_le(o, c[i]);
+}
+// ark-bls12-381 0.4: big-endian x || y, infinity = 0x40 then zeros
+static void put_g1(Bytes& o, const G1Aff& p) {
+  if (p.is_inf()) {
+    o.push_back(0x40);
+    o.insert(o.end(), 95, 0);
+    return;
+  }
+  put_fq_be(o, p.x);
+  put_fq_be(o, p.y);
+}
+static void put_g2(Bytes& o, const G2Aff& p) {
+  if (p.is_inf()) {
+    o.push_back(0x40);
+    o.insert(o.end(), 191, 0);
+    return;
+  }
+  put_fq_be(o, p.x.c1);
+  put_fq_be(o, p.x.c0);
+  put_fq_be(o, p.y.c1);
+  put_fq_be(o, p.y.c0);
+}
+static void put_u64_le(Bytes& o, uint64_t v) {
+  for (int i = 0; i < 8; i++) o.push_back((uint8_t)(v >> (8 * i)));
+}
+static void put_u64_be(Bytes& o, uint64_t v) {
+  for (int i = 7; i >= 0; i--) o.push_back((uint8_t)(v >> (8 * i)));
+}
+
+static Fr fr_from_u128_be(const uint8_t* d) {
+  // gipa.rs:248-251: Fr::from(u128::from_be_bytes(digest[0..16]))
+  Fr c = Fr::zero();
+  for (int i = 0; i < 16; i++) c.v[(15 - i) / 4] |= (uint32_t)d[i] << (8 * ((15 - i) % 4));
+  return c.to_mont();
+}
+// ark-ff 0.4 Fp::from_random_bytes: first 32 bytes little-endian, top bit cleared, None if >= r
+static bool fr_from_random_bytes(const uint8_t* d, Fr* out) {
+  Fr c;
+  memcpy(c.v, d, 32);
+  c.v[7] &= 0x7fffffffu;
+  for (int i = 7; i >= 0; i--) {
+    uint32_t m = FrParams::p(i);
+    if (c.v[i] < m) break;
+    if (c.v[i] > m) return false;
+    if (i == 0) return false;  // equal to r
+  }
+  *out = c.to_mont();
+  return true;
+}
+// tipa/mod.rs:195-209 and friends: hash(nonce_be || parts) until from_random_bytes accepts
+static Fr challenge_from_random_bytes(const Bytes& parts) {
+  for (uint64_t nonce = 0;; nonce++) {
+    Bytes h;
+    put_u64_be(h, nonce);
+    h.insert(h.end(), parts.begin(), parts.end());
+    uint8_t d[64];
+    ripp_hash::blake2b512(h.data(), h.size(), d);
+    Fr c;
+    if (fr_from_random_bytes(d, &c)) return c;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// typed device vectors
+// ------------------------------------------------------------------------------------------------
+enum VT { VT_NONE = 0, VT_G1 = 1, VT_G2 = 2, VT_FR = 3, VT_GT = 4 };
+static size_t vt_size(int t) { return t == VT_G1 ? 96 : t == VT_G2 ? 192 : t == VT_FR ? 32 : t == VT_GT ? 576 : 0; }
+
+struct Slice {
+  int t;
+  const char* p;
+};
+static Slice at(int t, const void* base, size_t off) { return Slice{t, base ? (const char*)base + off * vt_size(t) : nullptr}; }
+
+// result of one inner product / commitment, host copy
+struct Val {
+  int t;  // VT_GT / VT_G1 / VT_G2 / VT_FR
+  alignas(16) uint8_t raw[576];
+};
+static void put_val(Bytes& o, const Val& v) {
+  switch (v.t) {
+    case VT_GT: put_gt(o, *reinterpret_cast<const Fq12*>(v.raw)); break;
+    case VT_G1: put_g1(o, *reinterpret_cast<const G1Aff*>(v.raw)); break;
+    case VT_G2: put_g2(o, *reinterpret_cast<const G2Aff*>(v.raw)); break;
+    case VT_FR: put_fr(o, *reinterpret_cast<const Fr*>(v.raw)); break;
+  }
+}
+
+static int ip_out_type(int a, int b) {
+  if ((a == VT_G1 && b == VT_G2) || (a == VT_G2 && b == VT_G1)) return VT_GT;
+  if (a == VT_NONE || b == VT_NONE) return VT_FR;  // SSMPlaceholderCommitment: Fr::zero()
+  if (a == VT_FR && b == VT_FR) return VT_FR;
+  return a == VT_FR ? b : a;  // MSM
+}
+
+// Up to 8 inner products of equal length evaluated together; pairing-type ones share one launch.
+static int eval_products(ripp_ctx* ctx, int k, const Slice* xs, const Slice* ys, size_t n, Val* out) {
+  void* res;
+  OK(scratch(ctx, 10, 8 * 576 + 8 * 576, &res));
+  char* r = (char*)res;
+  const void *g1[8], *g2[8];
+  int pair_slot[8], np = 0;
+  for (int i = 0; i < k; i++) {
+    out[i].t = ip_out_type(xs[i].t, ys[i].t);
+    memset(out[i].raw, 0, sizeof(out[i].raw));
+    if (out[i].t == VT_GT) {
+      bool xg1 = xs[i].t == VT_G1;
+      g1[np] = xg1 ? xs[i].p : ys[i].p;
+      g2[np] = xg1 ? ys[i].p : xs[i].p;
+      pair_slot[np++] = i;
+    }
+  }
+  if (np) OK(ripp_pairing_batch_internal(ctx, np, g1, g2, n, r));
+  for (int j = 0; j < np; j++)
+    CU(cudaMemcpyAsync(out[pair_slot[j]].raw, r + 576 * j, 576, cudaMemcpyDeviceToHost, ctx->stream));
+  for (int i = 0; i < k; i++) {
+    int a = xs[i].t, b = ys[i].t;
+    if (out[i].t == VT_GT || a == VT_NONE || b == VT_NONE) continue;
+    char* dst = r + 8 * 576 + 576 * i;
+    if (a == VT_FR && b == VT_FR) {
+      OK(ripp_scalar_ip_dev(ctx, xs[i].p, ys[i].p, n, dst));
+    } else {
+      const char* pts = a == VT_FR ? ys[i].p : xs[i].p;
+      const char* sc = a == VT_FR ? xs[i].p : ys[i].p;
+      if (out[i].t == VT_G1)
+        OK(ripp_msm_g1_dev(ctx, pts, sc, n, dst));
+      else
+        OK(ripp_msm_g2_dev(ctx, pts, sc, n, dst));
+    }
+    CU(cudaMemcpyAsync(out[i].raw, dst, vt_size(out[i].t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RIPP_OK;
+}
+
+static int fold_typed(ripp_ctx* ctx, int t, char* base, size_t split, const Fr& c) {
+  if (t == VT_NONE || !base) return RIPP_OK;  // HomomorphicPlaceholderValue: no-op (identity/mod.rs:18-30)
+  char* hi = base + split * vt_size(t);
+  if (t == VT_G1) return ripp_g1_fold_dev(ctx, hi, base, c.v, split, base);
+  if (t == VT_G2) return ripp_g2_fold_dev(ctx, hi, base, c.v, split, base);
+  return ripp_fr_fold_dev(ctx, hi, base, c.v, split, base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GIPA (gipa.rs:162-312)
+// ------------------------------------------------------------------------------------------------
+struct GipaSpec {
+  int a, b, v, w;  // element types of the left message, right message, left key, right key
+};
+static bool gipa_spec(int kind, GipaSpec* s) {
+  switch (kind) {
+    case RIPP_GIPA_PAIRING: *s = {VT_G1, VT_G2, VT_G2, VT_G1}; return true;
+    case RIPP_GIPA_MULTIEXP_PEDERSEN: *s = {VT_G1, VT_FR, VT_G2, VT_G1}; return true;
+    case RIPP_GIPA_MULTIEXP_SSM: *s = {VT_G1, VT_FR, VT_G2, VT_NONE}; return true;
+    case RIPP_GIPA_SCALAR_PEDERSEN_G2_G2: *s = {VT_FR, VT_FR, VT_G2, VT_G2}; return true;
+    case RIPP_GIPA_SCALAR_PEDERSEN_G2_G1: *s = {VT_FR, VT_FR, VT_G2, VT_G1}; return true;
+    case RIPP_GIPA_SCALAR_SSM: *s = {VT_FR, VT_FR, VT_G2, VT_NONE}; return true;
+  }
+  return false;
+}
+
+struct GipaOut {
+  Bytes proof;                 // GIPAProof, serialize_uncompressed
+  std::vector<Fr> transcript;  // r_transcript (reversed: element 0 = last round's c)
+  Val a0, b0, v0, w0;          // r_base and ck_base
+};
+
+static int gipa_prove(ripp_ctx* ctx, const GipaSpec& sp, const void* a_in, const void* b_in, const void* v_in,
+                      const void* w_in, size_t n, GipaOut* out) {
+  if (n == 0 || (n & (n - 1)))
+    return fail(RIPP_ERR_NOT_POW2, "left length, right length: " + std::to_string(n) + ", " + std::to_string(n));
+  CU(cudaSetDevice(ctx->device));
+  // working copies (gipa.rs:175-176 clones all four vectors)
+  size_t sa = n * vt_size(sp.a), sb = n * vt_size(sp.b), sv = n * vt_size(sp.v), sw = n * vt_size(sp.w);
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  void* work;
+  OK(scratch(ctx, 11, up(sa) + up(sb) + up(sv) + up(sw) + 1024, &work));
+  char* A = (char*)work;
+  char* B = A + up(sa);
+  char* V = B + up(sb);
+  char* W = sp.w == VT_NONE ? nullptr : V + up(sv);
+  CU(cudaMemcpyAsync(A, a_in, sa, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(B, b_in, sb, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(V, v_in, sv, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (W) CU(cudaMemcpyAsync(W, w_in, sw, cudaMemcpyDeviceToDevice, ctx->stream));
+
+  std::vector<std::vector<Val>> steps;  // per round: com_1 (3) then com_2 (3)
+  std::vector<Fr> transcript;
+  size_t len = n;
+  while (len > 1) {
+    size_t split = len / 2;
+    // gipa.rs:209-231 -- com_1 = (IP(A_R, v_L), IP(w_R, B_L), IP(A_R, B_L)); com_2 = (IP(A_L, v_R), IP(w_L, B_R), IP(A_L, B_R))
+    Slice xs[6] = {at(sp.a, A, split), at(sp.w, W, split), at(sp.a, A, split), at(sp.a, A, 0), at(sp.w, W, 0), at(sp.a, A, 0)};
+    Slice ys[6] = {at(sp.v, V, 0), at(sp.b, B, 0), at(sp.b, B, 0), at(sp.v, V, split), at(sp.b, B, split), at(sp.b, B, split)};
+    if (sp.w == VT_NONE) xs[1].t = xs[4].t = VT_NONE;
+    std::vector<Val> com(6);
+    OK(eval_products(ctx, 6, xs, ys, split, com.data()));
+    // gipa.rs:235-258 -- Fiat-Shamir challenge
+    Fr c, c_inv;
+    for (uint64_t nonce = 0;; nonce++) {
+      Bytes h;
+      put_u64_be(h, nonce);
+      put_fr(h, transcript.empty() ? Fr::zero() : transcript.back());
+      for (int i = 0; i < 6; i++) {
+        if (i % 3 == 2) put_u64_le(h, 1);  // IdentityOutput<T>(Vec<T>) of length 1
+        put_val(h, com[i]);
+      }
+      uint8_t d[64];
+      ripp_hash::blake2b512(h.data(), h.size(), d);
+      c_inv = fr_from_u128_be(d);
+      if (!c_inv.is_zero()) {
+        c = c_inv.inv();  // (c, c_inv) swapped as in gipa.rs:253-255
+        break;
+      }
+    }
+    // gipa.rs:261-291 -- rescale
+    OK(fold_typed(ctx, sp.a, A, split, c));
+    OK(fold_typed(ctx, sp.b, B, split, c_inv));
+    OK(fold_typed(ctx, sp.v, V, split, c_inv));
+    OK(fold_typed(ctx, sp.w, W, split, c));
+    steps.push_back(com);
+    transcript.push_back(c);
+    len = split;
+  }
+  // base values
+  out->a0.t = sp.a;
+  out->b0.t = sp.b;
+  out->v0.t = sp.v;
+  out->w0.t = sp.w;
+  memset(out->a0.raw, 0, 576);
+  memset(out->b0.raw, 0, 576);
+  memset(out->v0.raw, 0, 576);
+  memset(out->w0.raw, 0, 576);
+  CU(cudaMemcpyAsync(out->a0.raw, A, vt_size(sp.a), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out->b0.raw, B, vt_size(sp.b), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out->v0.raw, V, vt_size(sp.v), cudaMemcpyDeviceToHost, ctx->stream));
+  if (W) CU(cudaMemcpyAsync(out->w0.raw, W, vt_size(sp.w), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  // gipa.rs:298-299 -- reversed
+  out->transcript.assign(transcript.rbegin(), transcript.rend());
+  out->proof.clear();
+  put_u64_le(out->proof, steps.size());
+  for (size_t r = steps.size(); r-- > 0;) {
+    for (int i = 0; i < 6; i++) {
+      if (i % 3 == 2) put_u64_le(out->proof, 1);
+      put_val(out->proof, steps[r][i]);
+    }
+  }
+  put_val(out->proof, out->a0);
+  put_val(out->proof, out->b0);
+  return RIPP_OK;
+}
+
+static int copy_out(const Bytes& b, uint8_t* dst, size_t cap, size_t* len) {
+  if (len) *len = b.size();
+  if (!dst || cap < b.size()) return fail(RIPP_ERR_ARG, "output buffer too small: need " + std::to_string(b.size()));
+  memcpy(dst, b.data(), b.size());
+  return RIPP_OK;
+}
+
+extern "C" int ripp_gipa_prove_dev(ripp_ctx* ctx, int kind, const void* a_dev, const void* b_dev, const void* v_dev,
+                                   const void* w_dev, size_t n, uint8_t* proof_out, size_t proof_cap, size_t* proof_len,
+                                   void* transcript_out, uint8_t* ck_base_out, size_t ck_cap, size_t* ck_len) {
+  GipaSpec sp;
+  if (!ctx || !gipa_spec(kind, &sp)) return fail(RIPP_ERR_ARG, "bad context or GIPA kind");
+  if (!a_dev || !b_dev || !v_dev || (sp.w != VT_NONE && !w_dev)) return fail(RIPP_ERR_ARG, "null vector");
+  GipaOut g;
+  OK(gipa_prove(ctx, sp, a_dev, b_dev, v_dev, w_dev, n, &g));
+  OK(copy_out(g.proof, proof_out, proof_cap, proof_len));
+  if (transcript_out) memcpy(transcript_out, g.transcript.data(), g.transcript.size() * sizeof(Fr));
+  Bytes ck;
+  put_val(ck, g.v0);
+  if (sp.w != VT_NONE) put_val(ck, g.w0);
+  return copy_out(ck, ck_base_out, ck_cap, ck_len);
+}
+
+// ------------------------------------------------------------------------------------------------
+// KZG opening of a structured final commitment key (tipa/mod.rs:304-337, 407-422)
+// ------------------------------------------------------------------------------------------------
+// coefficients of f(X) = prod_j (1 + x_j r^(2^j) X^(2^(j+1))) interleaved with zeros (length 2n-1),
+// then q = (f - f(z)) / (X - z) by synthetic division; returns q zero-padded to n_srs (Montgomery).
+static std::vector<Fr> kzg_quotient(const std::vector<Fr>& transcript, const Fr& r_shift, const Fr& z, size_t n_srs) {
+  std::vector<Fr> coeffs(1, Fr::one());
+  Fr power_2_r = r_shift;
+  for (size_t i = 0; i < transcript.size(); i++) {
+    Fr m = transcript[i] * power_2_r;
+    size_t cur = coeffs.size();
+    coeffs.reserve(2 * cur);
+    for (size_t j = 0; j < cur; j++) coeffs.push_back(coeffs[j] * m);
+    power_2_r = power_2_r * power_2_r;
+  }
+  // f has degree 2(len-1): f[2i] = coeffs[i], odd coefficients are zero
+  size_t deg = 2 * (coeffs.size() - 1);
+  std::vector<Fr> q(n_srs, Fr::zero());
+  Fr carry = Fr::zero();
+  for (size_t i = deg; i >= 1; i--) {
+    Fr fi = (i % 2 == 0) ? coeffs[i / 2] : Fr::zero();
+    carry = fi + z * carry;
+    q[i - 1] = carry;
+  }
+  return q;
+}
+
+template <class F>
+static int kzg_open(ripp_ctx* ctx, const void* srs_dev, size_t n_srs, const std::vector<Fr>& transcript, const Fr& r_shift,
+                    const Fr& z, Aff<F>* out_host) {
+  std::vector<Fr> q = kzg_quotient(transcript, r_shift, z, n_srs);
+  void* d;
+  OK(scratch(ctx, 12, n_srs * sizeof(Fr) + 1024, &d));
+  CU(cudaMemcpyAsync(d, q.data(), n_srs * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  char* res = (char*)d + ((n_srs * sizeof(Fr) + 255) & ~(size_t)255);
+  if (sizeof(F) == sizeof(Fq))
+    OK(ripp_msm_g1_dev(ctx, srs_dev, d, n_srs, res));
+  else
+    OK(ripp_msm_g2_dev(ctx, srs_dev, d, n_srs, res));
+  CU(cudaMemcpyAsync(out_host, res, sizeof(Aff<F>), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RIPP_OK;
+}
+
+extern "C" int ripp_kzg_open_g1_dev(ripp_ctx* ctx, const void* srs_g1_dev, size_t n_srs, const void* transcript, size_t k,
+                                    const void* r_shift, const void* z, void* g1_aff_out) {
+  if (!ctx || !srs_g1_dev || !transcript || !r_shift || !z || !g1_aff_out) return fail(RIPP_ERR_ARG, "null argument");
+  if (n_srs != 2 * ((size_t)1 << k) - 1) return fail(RIPP_ERR_ARG, "SRS length must be 2*2^k - 1");
+  std::vector<Fr> t(k);
+  memcpy(t.data(), transcript, k * sizeof(Fr));
+  Fr rs, zz;
+  memcpy(rs.v, r_shift, 32);
+  memcpy(zz.v, z, 32);
+  return kzg_open<Fq>(ctx, srs_g1_dev, n_srs, t, rs, zz, (G1Aff*)g1_aff_out);
+}
+extern "C" int ripp_kzg_open_g2_dev(ripp_ctx* ctx, const void* srs_g2_dev, size_t n_srs, const void* transcript, size_t k,
+                                    const void* r_shift, const void* z, void* g2_aff_out) {
+  if (!ctx || !srs_g2_dev || !transcript || !r_shift || !z || !g2_aff_out) return fail(RIPP_ERR_ARG, "null argument");
+  if (n_srs != 2 * ((size_t)1 << k) - 1) return fail(RIPP_ERR_ARG, "SRS length must be 2*2^k - 1");
+  std::vector<Fr> t(k);
+  memcpy(t.data(), transcript, k * sizeof(Fr));
+  Fr rs, zz;
+  memcpy(rs.v, r_shift, 32);
+  memcpy(zz.v, z, 32);
+  return kzg_open<Fq2>(ctx, srs_g2_dev, n_srs, t, rs, zz, (G2Aff*)g2_aff_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TIPA (tipa/mod.rs:176-231) and TIPA with structured scalar message (structured_scalar_message.rs:211-268)
+// ------------------------------------------------------------------------------------------------
+// srs_g1 = g^{alpha^i}, srs_g2 = h^{beta^i}, i < 2n-1, device resident (tipa/mod.rs:96-111).
+static int tipa_prove(ripp_ctx* ctx, int kind, const void* srs_g1, const void* srs_g2, const void* a, const void* b,
+                      const void* v, const void* w, size_t n, const Fr& r_shift, Bytes* proof) {
+  GipaSpec sp;
+  if (!gipa_spec(kind, &sp)) return fail(RIPP_ERR_ARG, "bad GIPA kind");
+  if (sp.v != VT_G2 || (sp.w != VT_G1 && sp.w != VT_NONE)) return fail(RIPP_ERR_ARG, "TIPA needs keys in (G2, G1)");
+  GipaOut g;
+  OK(gipa_prove(ctx, sp, a, b, v, w, n, &g));
+  size_t n_srs = 2 * n - 1;
+  std::vector<Fr> tinv(g.transcript.size());
+  for (size_t i = 0; i < tinv.size(); i++) tinv[i] = g.transcript[i].inv();
+  // KZG challenge (tipa/mod.rs:195-209 / structured_scalar_message.rs:238-251)
+  Bytes parts;
+  put_fr(parts, g.transcript[0]);
+  put_val(parts, g.v0);
+  if (sp.w != VT_NONE) put_val(parts, g.w0);
+  Fr c = challenge_from_random_bytes(parts);
+  G2Aff open_a;
+  G1Aff open_b;
+  Fr shift_a = sp.w != VT_NONE ? r_shift.inv() : Fr::one();  // SSM variant opens with shift 1
+  OK(kzg_open<Fq2>(ctx, srs_g2, n_srs, tinv, shift_a, c, &open_a));
+  *proof = g.proof;
+  put_val(*proof, g.v0);
+  if (sp.w != VT_NONE) {
+    OK(kzg_open<Fq>(ctx, srs_g1, n_srs, g.transcript, Fr::one(), c, &open_b));
+    put_val(*proof, g.w0);
+    put_g2(*proof, open_a);
+    put_g1(*proof, open_b);
+  } else {
+    put_g2(*proof, open_a);
+  }
+  return RIPP_OK;
+}
+
+extern "C" int ripp_tipa_prove_dev(ripp_ctx* ctx, int kind, const void* srs_g1_dev, const void* srs_g2_dev, const void* a_dev,
+                                   const void* b_dev, const void* v_dev, const void* w_dev, size_t n, const void* r_shift,
+                                   uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+  if (!ctx || !srs_g2_dev || !a_dev || !b_dev || !v_dev) return fail(RIPP_ERR_ARG, "null argument");
+  Fr rs = Fr::one();
+  if (r_shift) memcpy(rs.v, r_shift, 32);
+  Bytes proof;
+  OK(tipa_prove(ctx, kind, srs_g1_dev, srs_g2_dev, a_dev, b_dev, v_dev, w_dev, n, rs, &proof));
+  return copy_out(proof, proof_out, proof_cap, proof_len);
+}
+
+// ------------------------------------------------------------------------------------------------
+// TIPP Groth16 aggregation (applications/groth16_aggregation.rs:77-160)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fr_powers(Fr r, size_t n, Fr* __restrict__ pw, Fr* __restrict__ pw_inv, Fr r_inv) {
+  // r^i and r^-i by square-and-multiply on the index (n threads, log n products each)
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr acc = Fr::one(), acci = Fr::one(), b = r, bi = r_inv;
+  for (size_t e = i; e; e >>= 1) {
+    if (e & 1) {
+      acc = acc * b;
+      acci = acci * bi;
+    }
+    b = b * b;
+    bi = bi * bi;
+  }
+  pw[i] = acc;
+  pw_inv[i] = acci;
+}
+template <class T>
+__global__ void k_gather_stride2(const T* __restrict__ in, size_t n, T* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[2 * i];
+}
+
+extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, const void* srs_g2_dev, const void* a_dev,
+                                       const void* b_dev, const void* c_dev, size_t n, uint8_t* proof_out, size_t proof_cap,
+                                       size_t* proof_len) {
+  if (!ctx || !srs_g1_dev || !srs_g2_dev || !a_dev || !b_dev || !c_dev) return fail(RIPP_ERR_ARG, "null argument");
+  if (n == 0 || (n & (n - 1))) return fail(RIPP_ERR_NOT_POW2, "number of proofs must be a power of two");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // layout of the aggregation workspace
+  void* ws;
+  size_t o_ck1 = 0, o_ck2 = o_ck1 + n * 192, o_ar = o_ck2 + n * 96, o_ck1r = o_ar + n * 96, o_pw = o_ck1r + n * 192,
+         o_pwi = o_pw + n * 32, o_res = o_pwi + n * 32;
+  OK(scratch(ctx, 13, o_res + 8 * 576, &ws));
+  char* W = (char*)ws;
+  unsigned nb = (unsigned)((n + 127) / 128);
+  // :98 commitment keys = even SRS powers (tipa/mod.rs:114-118)
+  k_gather_stride2<G2Aff><<<nb, 128, 0, st>>>((const G2Aff*)srs_g2_dev, n, (G2Aff*)(W + o_ck1));
+  LAUNCHED(ctx);
+  k_gather_stride2<G1Aff><<<nb, 128, 0, st>>>((const G1Aff*)srs_g1_dev, n, (G1Aff*)(W + o_ck2));
+  LAUNCHED(ctx);
+  const void* ck1 = W + o_ck1;
+  const void* ck2 = W + o_ck2;
+  // :100-102 com_a = IP(a, ck_1), com_b = IP(ck_2, b), com_c = IP(c, ck_1)
+  Val com[3];
+  {
+    Slice xs[3] = {Slice{VT_G1, (const char*)a_dev}, Slice{VT_G1, (const char*)ck2}, Slice{VT_G1, (const char*)c_dev}};
+    Slice ys[3] = {Slice{VT_G2, (const char*)ck1}, Slice{VT_G2, (const char*)b_dev}, Slice{VT_G2, (const char*)ck1}};
+    OK(eval_products(ctx, 3, xs, ys, n, com));
+  }
+  // :105-116 r
+  Bytes parts;
+  for (int i = 0; i < 3; i++) put_val(parts, com[i]);
+  Fr r = challenge_from_random_bytes(parts);
+  Fr r_inv = r.inv();
+  // :118-131 r_vec, a_r = a * r^i, ck_1_r = ck_1 * r^-i
+  k_fr_powers<<<nb, 128, 0, st>>>(r, n, (Fr*)(W + o_pw), (Fr*)(W + o_pwi), r_inv);
+  LAUNCHED(ctx);
+  OK(ripp_g1_scale_dev(ctx, a_dev, W + o_pw, n, W + o_ar));
+  OK(ripp_g2_scale_dev(ctx, ck1, W + o_pwi, n, W + o_ck1r));
+  // :124 ip_ab = IP(a_r, b); :133-136 sanity com_a == IP(a_r, ck_1_r)
+  Val ipv[2];
+  {
+    Slice xs[2] = {Slice{VT_G1, W + o_ar}, Slice{VT_G1, W + o_ar}};
+    Slice ys[2] = {Slice{VT_G2, (const char*)b_dev}, Slice{VT_G2, W + o_ck1r}};
+    OK(eval_products(ctx, 2, xs, ys, n, ipv));
+  }
+  if (memcmp(ipv[1].raw, com[0].raw, 576) != 0)
+    return fail(RIPP_ERR_INNER_PRODUCT, "com_a != IP(a_r, ck_1_r) (groth16_aggregation.rs:133-136)");
+  // :125 agg_c = MSM(c, r_vec)
+  Val agg_c;
+  agg_c.t = VT_G1;
+  memset(agg_c.raw, 0, 576);
+  OK(ripp_msm_g1_dev(ctx, c_dev, W + o_pw, n, W + o_res));
+  CU(cudaMemcpyAsync(agg_c.raw, W + o_res, 96, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  // :138-149 the two TIPA proofs
+  Bytes proof_ab, proof_c;
+  OK(tipa_prove(ctx, RIPP_GIPA_PAIRING, srs_g1_dev, srs_g2_dev, W + o_ar, b_dev, W + o_ck1r, ck2, n, r, &proof_ab));
+  OK(tipa_prove(ctx, RIPP_GIPA_MULTIEXP_SSM, srs_g1_dev, srs_g2_dev, c_dev, W + o_pw, ck1, nullptr, n, Fr::one(), &proof_c));
+  // AggregateProof { com_a, com_b, com_c, ip_ab, agg_c, tipa_proof_ab, tipa_proof_c } (:58-66)
+  Bytes out;
+  for (int i = 0; i < 3; i++) put_val(out, com[i]);
+  put_val(out, ipv[0]);
+  put_val(out, agg_c);
+  out.insert(out.end(), proof_ab.begin(), proof_ab.end());
+  out.insert(out.end(), proof_c.begin(), proof_c.end());
+  return copy_out(out, proof_out, proof_cap, proof_len);
+}

@@ -394,6 +394,95 @@ static int miller_partial(ripp_ctx* ctx, const G1Aff* p, const G2Aff* q, size_t 
   return RIPP_OK;
 }
 
+// ---- batched products: several equal-length (G1, G2) vector pairs in one Miller launch ----------
+struct MillerBatch {
+  const G1Aff* p[RIPP_MAX_BATCH];
+  const G2Aff* q[RIPP_MAX_BATCH];
+  uint32_t n, wps;  // pairs per segment, warps per segment
+  int nseg;
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, RIPP_MILLER_THREADS_PER_SM / BLOCK) k_miller_batch(MillerBatch b, Fq12* __restrict__ partials) {
+  uint32_t gw = (blockIdx.x * BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  uint32_t seg = gw / b.wps, i = (gw % b.wps) * 32 + lane;
+  Fq12 f = Fq12::one();
+  if (seg < (uint32_t)b.nseg && i < b.n) f = miller_loop(b.p[seg][i], b.q[seg][i]);
+#pragma unroll 1
+  for (int m = 16; m >= 1; m >>= 1) f = f * shfl_xor_fq12(f, m);
+  if (lane == 0 && seg < (uint32_t)b.nseg) partials[gw] = f;
+}
+
+// out[s][k] = prod in[s][k*R .. min(T, k*R+R))
+__global__ void k_fq12_reduce_seg(const Fq12* __restrict__ in, uint32_t T, uint32_t R, uint32_t To, Fq12* __restrict__ out,
+                                  size_t total) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t s = (uint32_t)(t / To), k = (uint32_t)(t % To);
+  uint32_t lo = k * R, hi = lo + R < T ? lo + R : T;
+  Fq12 f = in[(size_t)s * T + lo];
+  for (uint32_t j = lo + 1; j < hi; j++) f = f * in[(size_t)s * T + j];
+  out[t] = f;
+}
+
+// out[s] = final_exp(prod_j in[s][j]), j < T (T small)
+__global__ void k_final_exp_seg(const Fq12* __restrict__ in, uint32_t T, Fq12* __restrict__ out, int nseg) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  Fq12 f = in[(size_t)s * T];
+  for (uint32_t j = 1; j < T; j++) f = f * in[(size_t)s * T + j];
+  out[s] = final_exponentiation(f);
+}
+
+int ripp_pairing_batch_internal(ripp_ctx* ctx, int nseg, const void* const* g1, const void* const* g2, size_t n, void* out) {
+  if (nseg <= 0 || nseg > RIPP_MAX_BATCH) return fail(RIPP_ERR_ARG, "bad segment count");
+  CU(cudaSetDevice(ctx->device));
+  if (n == 0) {
+    Fq12 one[RIPP_MAX_BATCH];
+    for (int s = 0; s < nseg; s++) one[s] = Fq12::one();
+    CU(cudaMemcpyAsync(out, one, nseg * sizeof(Fq12), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RIPP_OK;
+  }
+  MillerBatch b;
+  b.nseg = nseg;
+  b.n = (uint32_t)n;
+  b.wps = (uint32_t)((n + 31) / 32);
+  for (int s = 0; s < nseg; s++) {
+    b.p[s] = (const G1Aff*)g1[s];
+    b.q[s] = (const G2Aff*)g2[s];
+  }
+  size_t nwarps = (size_t)b.wps * nseg;
+  void *bufA, *bufB;
+  OK(scratch(ctx, 2, nwarps * sizeof(Fq12), &bufA));
+  OK(scratch(ctx, 3, nwarps * sizeof(Fq12) / 4 + 4096, &bufB));
+  const int WPB = MILLER_BLOCK / 32;
+  k_miller_batch<MILLER_BLOCK><<<(unsigned)((nwarps + WPB - 1) / WPB), MILLER_BLOCK, 0, ctx->stream>>>(b, (Fq12*)bufA);
+  LAUNCHED(ctx);
+  uint32_t T = b.wps;
+  const uint32_t R = 8;
+  Fq12 *src = (Fq12*)bufA, *dst = (Fq12*)bufB;
+  while (T > R) {
+    uint32_t To = (T + R - 1) / R;
+    size_t tot = (size_t)nseg * To;
+    k_fq12_reduce_seg<<<(unsigned)((tot + 63) / 64), 64, 0, ctx->stream>>>(src, T, R, To, dst, tot);
+    LAUNCHED(ctx);
+    Fq12* t = src;
+    src = dst;
+    dst = t;
+    T = To;
+  }
+  k_final_exp_seg<<<1, 32, 0, ctx->stream>>>(src, T, (Fq12*)out, nseg);
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}
+
+extern "C" int ripp_pairing_ip_batch_dev(ripp_ctx* ctx, int nseg, const void* const* g1_aff_dev, const void* const* g2_aff_dev,
+                                         size_t n, void* gt_out_dev) {
+  if (!ctx || !g1_aff_dev || !g2_aff_dev || !gt_out_dev) return fail(RIPP_ERR_ARG, "null argument");
+  return ripp_pairing_batch_internal(ctx, nseg, g1_aff_dev, g2_aff_dev, n, gt_out_dev);
+}
+
 extern "C" int ripp_miller_partial_dev(ripp_ctx* ctx, const void* g1, const void* g2, size_t n, void* out) {
   if (!ctx || !out || (n && (!g1 || !g2))) return fail(RIPP_ERR_ARG, "null argument");
   CU(cudaSetDevice(ctx->device));
