@@ -1,18 +1,26 @@
 #!/usr/bin/env python3
 """bench.py -- RIPP inner-pairing-product hot path on B200 (contract: see the task statement).
 
-Workload at N GPUs (weak scaling): BASELINE.json configs[1], `PairingInnerProduct` + AFGHO16
-commitment of 2^16 (G1, G2) BLS12-381 pairs PER GPU (afgho16/mod.rs:30-32 ->
-inner_products/src/lib.rs:77-116).  A step = one commitment: multi-Miller loop over the rank's
-slice, one Fq12 partial per rank, all-gather of the partials (NCCL) when N > 1, one shared final
-exponentiation.  Metric: Miller-loop pairs per second, whole job.
+Headline workload (BASELINE.json `metric`, configs[3]): TIPP aggregation of 2^12 Groth16 proofs on
+BLS12-381 -- `aggregate_proofs` (ip_proofs/src/applications/groth16_aggregation.rs:77-160) on
+trapdoor-simulated proofs and a powers-of-tau SRS.  One step = one aggregation:
+5 multi-pairings of 2^12 pairs, two device-resident GIPA recursions (12 rounds each), three KZG
+opening MSMs, Fiat-Shamir hashing on the host.  Metric: prove seconds (lower is better).
 
-  value     device-resident inputs, CUDA-event timed, L2 flushed between steps
-  e2e       the same commitment through the host-pointer C-ABI call (ripp_pairing_ip, arkworks
-            Jacobian layout in pinned host memory): H2D + normalise + kernels + D2H of the GT result
-  roofline  integer-pipe (IMAD.WIDE) roofline of the Miller kernel: algorithmic MAC32 per pair x
-            pairs / kernel time, against the IMAD.WIDE peak measured live by ripp_bench_imad
-  cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/), see DESIGN.md
+  value        device-resident inputs, CUDA events on the library's stream, L2 flushed between steps
+  e2e          the same aggregation through the host-pointer C-ABI call (ripp_tipp_aggregate): Groth16
+               proofs in pinned host memory, H2D + kernels + D2H of the proof bytes, wall clock
+  sub_metrics  the two leaf throughputs the metric string also names, measured in the same run:
+               multi-Miller pairs/s (configs[1], 2^16 pairs per GPU) and G1 MSM points/s (configs[2] leaf,
+               2^18 points per GPU), sharded by input slices with an NCCL all-gather of the per-rank
+               partials when N > 1
+  roofline     integer-pipe (IMAD.WIDE) roofline of the dominant kernel class of the step, plus the
+               Miller kernel at 2^16; peak = ripp_bench_imad measured live in this run
+  cpu_baseline the compiled CPU restatement of the reference path (oracle/cpu, OpenMP on all host
+               cores) running the same 2^12 aggregation once
+
+N > 1 (weak scaling): every rank aggregates its own batch of 2^12 proofs; `value` is the max over
+ranks of seconds per aggregation and `proofs_per_s` the whole-job rate.
 """
 import argparse
 import json
@@ -25,16 +33,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# Algorithmic op counts of the reference algorithm (own Fq12 accumulator per pair), measured by
-# tests/test_hostsim.py::test_op_counts; one Fq Montgomery product = 2*12^2 + 12 = 300 MAC32.
+# Algorithmic Fq-product counts of the reference algorithm, measured by tests/test_hostsim.py::test_op_counts
+# (own Fq12 accumulator per pair); one Fq Montgomery product = 2*12^2 + 12 = 300 MAC32.
 FQ_MUL_PER_MILLER_PAIR = 6700
 FQ_MUL_PER_FINAL_EXP = 8276
+FQ_MUL_PER_G1_MUL_255 = 255 * 7 + 127 * 11 + 4        # dbl-2009-l 2M+5S, madd-2007-bl 7M+4S, + to-affine products
+FQ_MUL_PER_G2_MUL_128 = (128 * 16 + 64 * 29 + 10)     # same formulas over Fq2 (M2 = 3, S2 = 2 Fq products)
+FQ_MUL_PER_G1_MSM_POINT = 26 * 11                      # c = 10 -> 26 windows x one mixed addition per point
 MAC32_PER_FQ_MUL = 300
-LOG_N = 16
+LOG_PROOFS = 12
+LOG_PAIRS = 16
+LOG_MSM = 18
+METRIC = "tipp_groth16_aggregate_prove_seconds_at_2^12_proofs"
+DTYPE = "u32-limb Montgomery (BLS12-381 Fq 381-bit / Fr 255-bit)"
 
 
 def _clock_sampler(stop, samples):
-    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     idx = os.environ.get("LOCAL_RANK", "0")
     while not stop.is_set():
         try:
@@ -56,41 +72,44 @@ def _clocks_summary(samples):
         for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
             if v.lower().startswith("active"):
                 reasons.add(name)
-    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None,
-            "reasons": sorted(reasons)}
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None, "reasons": sorted(reasons)}
 
 
-def cpu_reference_pairs_per_s(sample_pairs):
-    """CPU restatement of cfg_multi_pairing timed on a bounded sample of the same workload."""
-    from oracle import cpu_baseline
-
-    return cpu_baseline.pairing_pairs_per_s(sample_pairs)
+def tipp_algorithmic_macs(n):
+    """MAC32 per aggregation by kernel class (SURVEY.md App. C op inventory)."""
+    lg = n.bit_length() - 1
+    return {
+        "miller": (13 * n - 8) * FQ_MUL_PER_MILLER_PAIR * MAC32_PER_FQ_MUL,
+        "final_exp": (5 + 8 * lg) * FQ_MUL_PER_FINAL_EXP * MAC32_PER_FQ_MUL,
+        "fold": (3 * (n - 1) * FQ_MUL_PER_G1_MUL_255 + 3 * (n - 1) * FQ_MUL_PER_G2_MUL_128) * MAC32_PER_FQ_MUL,
+        "scale": (n * FQ_MUL_PER_G1_MUL_255 + n * 2 * FQ_MUL_PER_G2_MUL_128) * MAC32_PER_FQ_MUL,
+        "msm": ((n + 2 * (n - 1) + (2 * n - 1)) * FQ_MUL_PER_G1_MSM_POINT + 2 * (2 * n - 1) * 3 * FQ_MUL_PER_G1_MSM_POINT) * MAC32_PER_FQ_MUL,
+    }
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """The reference's CPU path (compiled restatement, all host cores) on the same workload."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import cpu_baseline
 
-    vals = []
-    for _ in range(args.warmup):
-        cpu_baseline.pairing_pairs_per_s(cpu_baseline.SAMPLE_PAIRS)
-    t_total = 0.0
-    info = None
-    for _ in range(args.steps):
-        info = cpu_baseline.pairing_pairs_per_s(cpu_baseline.SAMPLE_PAIRS)
-        vals.append(info["value"])
-        t_total += info["seconds"]
-    v = sum(vals) / len(vals)
+    n = 1 << args.logn
+    work = cpu_baseline.TippWorkload(n)
+    for _ in range(min(args.warmup, 1)):
+        work.run()
+    times = [work.run() for _ in range(args.steps)]
+    v = sum(times) / len(times)
+    info = work.info()
     line = {
-        "impl": "reference", "metric": "miller_pairs_per_s", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32-limb modular (BLS12-381 Fq)",
-        "data": "synthetic",
-        "config": {"workload": "PairingInnerProduct + AFGHO16 commit, 2^%d pairs per GPU (bounded CPU sample per step)" % LOG_N},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
-        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * v, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": {"workload": "TIPP aggregate_proofs of 2^%d Groth16 proofs, BLS12-381 (BASELINE configs[3]); CPU restatement of the reference path" % args.logn,
+                   "proofs": n},
+        "cpu_baseline": {"value": v, "unit": "s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+        "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "proofs_per_s": n / v,
     }
     print(json.dumps(line))
 
@@ -101,8 +120,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--logn", type=int, default=LOG_N)
+    ap.add_argument("--logn", type=int, default=LOG_PROOFS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-metrics", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -123,25 +143,9 @@ def main():
     # one non-default stream shared by torch (events, NCCL ordering) and the library's kernels
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
+    warmup = max(args.warmup, 3)
     n = 1 << args.logn
-
-    # ---- inputs: this rank's slice of the global vectors, generated on the GPU -----------------
-    a_dev = synth.g1_points_dev(ctx, "cfg2-m", n, seed=rank)
-    b_dev = synth.g2_points_dev(ctx, "cfg2-k", n, seed=rank)
-    partial = torch.zeros(144, dtype=torch.int32, device="cuda")
-    gathered = torch.zeros(world * 144, dtype=torch.int32, device="cuda")
-    result = torch.zeros(144, dtype=torch.int32, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
-    def step():
-        if world == 1:
-            ctx.pairing_ip_dev(a_dev, b_dev, n, result.data_ptr())
-        else:
-            ctx.miller_partial_dev(a_dev, b_dev, n, partial.data_ptr())
-            dist.all_gather_into_tensor(gathered, partial)
-            ctx.gt_combine_dev(gathered.data_ptr(), world, result.data_ptr())
 
     def barrier():
         torch.cuda.synchronize()
@@ -149,15 +153,27 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    # ---- headline: TIPP aggregation, this rank's batch of 2^12 proofs generated on the GPU -------
+    inst = synth.tipp_instance_dev(ctx, n, seed=rank)
+
+    def step():
+        return ctx.tipp_aggregate_dev(inst["srs_g1"], inst["srs_g2"], inst["a"], inst["b"], inst["c"], n)
+
+    for _ in range(warmup):
+        proof = step()
+    barrier()
     stop, samples = threading.Event(), []
     th = threading.Thread(target=_clock_sampler, args=(stop, samples), daemon=True)
     th.start()
 
-    # ---- device-resident timing: K steps, each bracketed by events, L2 flushed in between ---------
     launches0 = ctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -168,83 +184,144 @@ def main():
         e.record()
     barrier()
     launches = ctx.launches - launches0
-    ms_total = sum(s.elapsed_time(e) for s, e in ev)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * n * args.steps / (ms_total * 1e-3)
+    ms_total = max_over_ranks(sum(s.elapsed_time(e) for s, e in ev))
+    value_s = ms_total / args.steps / 1e3
 
-    # ---- dominant kernel alone (Miller loop + warp/tree product, no final exp) ------------------
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for s, e in kev:
-        flush.zero_()
-        s.record()
-        ctx.miller_partial_dev(a_dev, b_dev, n, partial.data_ptr())
-        e.record()
-    torch.cuda.synchronize()
-    k_ms = sum(s.elapsed_time(e) for s, e in kev) / args.steps
+    # per-class device time of one aggregation (instrumented pass, outside the timed region)
+    ctx.set_timing(True)
+    ctx.timing()
+    step()
+    breakdown = ctx.timing()
+    ctx.set_timing(False)
 
-    # ---- end to end through the host-pointer C ABI ---------------------------------------------
-    a_aff = a_dev.download((n, 24))
-    b_aff = b_dev.download((n, 48))
-    one_q = codec.fq_enc(1)
-    g1_jac = torch.empty((n, 36), dtype=torch.int32).pin_memory()
-    g2_jac = torch.empty((n, 72), dtype=torch.int32).pin_memory()
-    g1_np, g2_np = g1_jac.numpy().view(np.uint32), g2_jac.numpy().view(np.uint32)
-    g1_np[:, :24] = a_aff
-    g1_np[:, 24:] = one_q
-    g2_np[:, :48] = b_aff
-    g2_np[:, 48:60] = one_q
-    g2_np[:, 60:] = 0
-    for _ in range(2):
-        host_out = ctx.pairing_ip(g1_np, g2_np)
-    assert (host_out.view(np.int32) == result.cpu().numpy()).all() or world > 1
-    barrier()
+    # ---- end to end through the host-pointer C ABI ------------------------------------------------
+    a_h = torch.from_numpy(inst["a"].download((n, 24)).view(np.int32)).pin_memory()
+    b_h = torch.from_numpy(inst["b"].download((n, 48)).view(np.int32)).pin_memory()
+    c_h = torch.from_numpy(inst["c"].download((n, 24)).view(np.int32)).pin_memory()
+    a_np, b_np, c_np = (t.numpy().view(np.uint32) for t in (a_h, b_h, c_h))
+    host_proof = ctx.tipp_aggregate(inst["srs_g1"], inst["srs_g2"], a_np, b_np, c_np)
+    assert host_proof == proof, "host-pointer and device-resident entry points disagree"
     e2e_steps = max(2, min(args.steps, 5))
+    barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        host_out = ctx.pairing_ip(g1_np, g2_np)
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / float(t.item())
+        host_proof = ctx.tipp_aggregate(inst["srs_g1"], inst["srs_g2"], a_np, b_np, c_np)
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+
+    # ---- leaf throughputs (sharded by input slices; one partial per rank all-gathered) -------------
+    sub = {}
+    miller_k_ms = None
+    if not args.no_sub_metrics:
+        npairs = 1 << LOG_PAIRS
+        pa = synth.g1_points_dev(ctx, "cfg2-m", npairs, seed=rank)
+        pb = synth.g2_points_dev(ctx, "cfg2-k", npairs, seed=rank)
+        partial = torch.zeros(144, dtype=torch.int32, device="cuda")
+        gathered = torch.zeros(world * 144, dtype=torch.int32, device="cuda")
+        result = torch.zeros(144, dtype=torch.int32, device="cuda")
+
+        def pairing_step():
+            if world == 1:
+                ctx.pairing_ip_dev(pa, pb, npairs, result.data_ptr())
+            else:
+                ctx.miller_partial_dev(pa, pb, npairs, partial.data_ptr())
+                dist.all_gather_into_tensor(gathered, partial)
+                ctx.gt_combine_dev(gathered.data_ptr(), world, result.data_ptr())
+
+        def timed(fn, reps):
+            for _ in range(3):
+                fn()
+            barrier()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for s, e in evs:
+                flush.zero_()
+                s.record()
+                fn()
+                e.record()
+            barrier()
+            return max_over_ranks(sum(s.elapsed_time(e) for s, e in evs)) / reps
+
+        reps = max(3, min(args.steps, 5))
+        ms = timed(pairing_step, reps)
+        miller_k_ms = timed(lambda: ctx.miller_partial_dev(pa, pb, npairs, partial.data_ptr()), reps)
+        sub["miller_pairs_per_s"] = {"value": world * npairs / (ms * 1e-3), "pairs_per_gpu": npairs, "ms_per_step": ms,
+                                     "miller_kernel_ms": miller_k_ms}
+        pa.free()
+        pb.free()
+        nmsm = 1 << LOG_MSM
+        bases = synth.g1_points_dev(ctx, "cfg3-a", nmsm, seed=rank)
+        sc = ctx.to_device(synth.scalars_mont("cfg3-b", nmsm, seed=rank))
+        part_pt = torch.zeros(24, dtype=torch.int32, device="cuda")
+        gath_pt = torch.zeros(world * 24, dtype=torch.int32, device="cuda")
+        ones = ctx.to_device(codec.fr_vec_enc([1] * world))
+        res_pt = torch.zeros(24, dtype=torch.int32, device="cuda")
+
+        def msm_step():
+            if world == 1:
+                ctx.msm_g1_dev(bases, sc, nmsm, res_pt.data_ptr())
+            else:
+                ctx.msm_g1_dev(bases, sc, nmsm, part_pt.data_ptr())
+                dist.all_gather_into_tensor(gath_pt, part_pt)
+                ctx.msm_g1_dev(gath_pt.data_ptr(), ones, world, res_pt.data_ptr())
+
+        ms = timed(msm_step, reps)
+        sub["msm_g1_points_per_s"] = {"value": world * nmsm / (ms * 1e-3), "points_per_gpu": nmsm, "ms_per_step": ms}
+        bases.free()
+        sc.free()
 
     stop.set()
     th.join(timeout=2)
 
-    # ---- roofline ------------------------------------------------------------------------------
+    # ---- roofline ----------------------------------------------------------------------------------
     imad_peak, _ = ctx.bench_imad(0, 4096)
     imad32_peak, _ = ctx.bench_imad(1, 4096)
     chain_peak, _ = ctx.bench_imad(2, 4096)
-    macs_per_launch = n * FQ_MUL_PER_MILLER_PAIR * MAC32_PER_FQ_MUL
-    achieved = macs_per_launch / (k_ms * 1e-3)
+    macs = tipp_algorithmic_macs(n)
+    dom = max((c for c in macs), key=lambda c: breakdown[c][0])
+    dom_ms, dom_launches = breakdown[dom]
+    achieved = macs[dom] / (dom_ms * 1e-3) if dom_ms else 0.0
+    roofline = {
+        "bound": "int32 multiply pipe (IMAD.WIDE.U32: one 32x32+64 MAC per lane-instruction)",
+        "kernel": "%s kernels of one aggregation (%d timed scopes)" % (dom, dom_launches),
+        "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TMAC32/s", "frac": achieved / imad_peak,
+        "traffic": None, "kernel_ms": dom_ms,
+        "peak_source": "ripp_bench_imad in this run: independent IMAD.WIDE.U32 chains, all SMs",
+        "peak_imad32_tmacs": imad32_peak / 1e12, "peak_carry_chain_tmacs": chain_peak / 1e12,
+        "step_breakdown_ms": {c: round(breakdown[c][0], 3) for c in breakdown},
+        "step_frac_by_class": {c: (macs[c] / (breakdown[c][0] * 1e-3) / imad_peak if breakdown[c][0] else None) for c in macs},
+        "whole_step_frac": sum(macs.values()) / value_s / imad_peak,
+    }
+    if miller_k_ms:
+        m = (1 << LOG_PAIRS) * FQ_MUL_PER_MILLER_PAIR * MAC32_PER_FQ_MUL / (miller_k_ms * 1e-3)
+        roofline["miller_2^16"] = {"kernel": "k_miller + Fq12 product tree", "kernel_ms": miller_k_ms,
+                                   "achieved": m / 1e12, "frac": m / imad_peak,
+                                   "mac32_per_pair": FQ_MUL_PER_MILLER_PAIR * MAC32_PER_FQ_MUL}
 
     if rank == 0:
         line = {
-            "metric": "miller_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32-limb modular (BLS12-381 Fq)", "data": "synthetic",
-            "config": {"workload": "PairingInnerProduct + AFGHO16 commit, 2^%d (G1,G2) pairs per GPU, BLS12-381 (BASELINE configs[1])" % args.logn,
-                       "pairs_per_gpu": n, "l2": "flushed between steps (256 MiB memset)",
-                       "parallelism": "input slices per GPU, all-gather of one Fq12 partial per rank"},
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": n * (144 + 288), "d2h_bytes_per_step": 576},
+            "metric": METRIC, "value": value_s, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": DTYPE, "data": "synthetic",
+            "config": {"workload": "TIPP aggregate_proofs of 2^%d Groth16 proofs per GPU, BLS12-381, Blake2b (BASELINE configs[3])" % args.logn,
+                       "proofs_per_gpu": n, "l2": "flushed between steps (256 MiB memset)",
+                       "parallelism": "one 2^%d-proof aggregation per GPU (weak); leaf ops sharded by slices in sub_metrics" % args.logn},
+            "proofs_per_s": world * n / value_s,
+            "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": n * 384, "d2h_bytes_per_step": len(host_proof)},
             "gpu_launches": launches,
             "clocks": _clocks_summary(samples),
-            "roofline": {"bound": "int32 multiply pipe (IMAD.WIDE)", "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
-                         "unit": "TMAC32/s", "frac": achieved / imad_peak, "traffic": None,
-                         "kernel": "k_miller (+ Fq12 product tree)", "kernel_ms": k_ms,
-                         "peak_source": "ripp_bench_imad measured in this run (independent IMAD.WIDE.U32 chains)",
-                         "peak_imad32_tmacs": imad32_peak / 1e12, "peak_carry_chain_tmacs": chain_peak / 1e12,
-                         "mac32_per_pair": FQ_MUL_PER_MILLER_PAIR * MAC32_PER_FQ_MUL},
+            "roofline": roofline,
+            "sub_metrics": sub,
         }
         if not args.no_cpu_baseline and world == 1:
             try:
-                info = cpu_reference_pairs_per_s(None)
-                line["cpu_baseline"] = {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                from oracle import cpu_baseline
+
+                work = cpu_baseline.TippWorkload(n)
+                secs = work.run()
+                info = work.info()
+                line["cpu_baseline"] = {"value": secs, "unit": "s", "cores": info["cores"], "kind": info["kind"],
+                                        "sample": info["sample"]}
             except Exception as ex:  # the GPU numbers stand on their own
-                line["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+                line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -56,6 +56,13 @@ int ripp_ctx_set_stream(ripp_ctx* ctx, void* cuda_stream);
 /* Number of kernels launched by this context so far (bench.py's gpu_launches). */
 uint64_t ripp_ctx_launch_count(ripp_ctx* ctx);
 
+/* Per-category device-time accounting with CUDA events on the context's stream (off by default).
+ * Categories: 0 Miller loops (+ Fq12 product tree), 1 final exponentiations, 2 MSMs, 3 folds,
+ * 4 element-wise scalar muls, 5 other.  ripp_ctx_timing synchronises, returns the sums since the
+ * last call (arrays of 6) and resets them. */
+int ripp_ctx_set_timing(ripp_ctx* ctx, int on);
+int ripp_ctx_timing(ripp_ctx* ctx, double* ms_by_cat, uint64_t* count_by_cat);
+
 /* ---- device memory (residency; SURVEY.md §8b "residency") -------------------------------- */
 int ripp_dev_alloc(ripp_ctx* ctx, size_t bytes, void** dev_out);
 int ripp_dev_free(ripp_ctx* ctx, void* dev);
@@ -164,6 +171,14 @@ int ripp_tipa_prove_dev(ripp_ctx* ctx, int kind, const void* srs_g1_dev, const v
 int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, const void* srs_g2_dev, const void* a_dev,
                             const void* b_dev, const void* c_dev, size_t n, uint8_t* proof_out, size_t proof_cap,
                             size_t* proof_len);
+
+/* aggregate_proofs with the Groth16 proofs in HOST memory, exactly as arkworks holds
+ * `Proof { a: G1Affine, b: G2Affine, c: G1Affine }` split into three packed arrays (n x 96 B, n x 192 B,
+ * n x 96 B); the SRS is long-lived and stays device resident.  This is the end-to-end entry point
+ * bench.py times (H2D of the proofs + all kernels + D2H of the proof bytes). */
+int ripp_tipp_aggregate(ripp_ctx* ctx, const void* srs_g1_dev, const void* srs_g2_dev, const void* a_host,
+                        const void* b_host, const void* c_host, size_t n, uint8_t* proof_out, size_t proof_cap,
+                        size_t* proof_len);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* Element-wise primitive ops on device, used by the GPU parity tests to pin the PTX limb layer:

@@ -62,10 +62,20 @@ BACKEND = PyBackend()
 
 
 # ----------------------------------------------------------------------------- algebraic types
+def _vec(be, name, x):
+    """Backend-native container for a vector (packed limb arrays on the compiled backend)."""
+    f = getattr(be, name, None)
+    return f(x) if f else list(x)
+
+
 class G1T:
     ser = staticmethod(ser_g1)
     add = staticmethod(E.g1_add)
     mul = staticmethod(E.g1_mul)
+
+    @staticmethod
+    def vec(x, be):
+        return _vec(be, "vec_g1", x)
 
     @staticmethod
     def fold(hi, lo, c, be):
@@ -80,6 +90,10 @@ class G2T:
     ser = staticmethod(ser_g2)
     add = staticmethod(E.g2_add)
     mul = staticmethod(E.g2_mul)
+
+    @staticmethod
+    def vec(x, be):
+        return _vec(be, "vec_g2", x)
 
     @staticmethod
     def fold(hi, lo, c, be):
@@ -101,6 +115,10 @@ class GTT:
     def fold(hi, lo, c, be):
         return [E.gt_mul(E.gt_pow(h, c), l) for h, l in zip(hi, lo)]
 
+    @staticmethod
+    def vec(x, be):
+        return list(x)
+
 
 class FrT:
     ser = staticmethod(ser_fr)
@@ -115,7 +133,13 @@ class FrT:
 
     @staticmethod
     def fold(hi, lo, c, be):
+        if hasattr(be, "fold_fr"):
+            return be.fold_fr(hi, lo, c)
         return [(h * c + l) % R for h, l in zip(hi, lo)]
+
+    @staticmethod
+    def vec(x, be):
+        return _vec(be, "vec_fr", x)
 
 
 class PlaceholderT:
@@ -136,6 +160,10 @@ class PlaceholderT:
     @staticmethod
     def fold(hi, lo, c, be):
         return [None] * len(hi)
+
+    @staticmethod
+    def vec(x, be):
+        return list(x)
 
 
 def IdentityOutT(T):
@@ -307,9 +335,9 @@ class GIPA:
 
     # gipa.rs:162-312
     def prove_with_aux(self, values, ck):
-        m_a, m_b = list(values[0]), list(values[1])
-        ck_a, ck_b, ck_t = list(ck[0]), list(ck[1]), list(ck[2])
         IP, LMC, RMC, IPC, be = self.IP, self.LMC, self.RMC, self.IPC, self.be
+        m_a, m_b = LMC.Message.vec(values[0], be), RMC.Message.vec(values[1], be)
+        ck_a, ck_b, ck_t = LMC.Key.vec(ck[0], be), RMC.Key.vec(ck[1], be), list(ck[2])
         steps, transcript = [], []
         assert len(m_a) & (len(m_a) - 1) == 0 and len(m_a) > 0
         while len(m_a) > 1:
@@ -430,8 +458,8 @@ def tipa_setup(size, alpha, beta, be=None):
     """tipa/mod.rs:150-164 with alpha, beta supplied instead of drawn from an rng."""
     be = be or BACKEND
     n = 2 * size - 1
-    ga = be.mul_vec_g1([E.G1_GEN] * n, structured_scalar_power(n, alpha))
-    hb = be.mul_vec_g2([E.G2_GEN] * n, structured_scalar_power(n, beta))
+    ga = be.mul_vec_g1(G1T.vec([E.G1_GEN] * n, be), structured_scalar_power(n, alpha))
+    hb = be.mul_vec_g2(G2T.vec([E.G2_GEN] * n, be), structured_scalar_power(n, beta))
     return SRS(ga, hb, E.g1_mul(E.G1_GEN, beta), E.g2_mul(E.G2_GEN, alpha))
 
 
@@ -476,7 +504,7 @@ def kzg_quotient_coeffs(transcript, r_shift, z, n_srs):
 def prove_commitment_key_kzg_opening(G, srs_powers, transcript, r_shift, z, be=None):
     """tipa/mod.rs:304-337."""
     q = kzg_quotient_coeffs(transcript, r_shift, z, len(srs_powers))
-    return MultiexponentiationInnerProduct(G).inner_product(srs_powers, q, be)
+    return MultiexponentiationInnerProduct(G).inner_product(srs_powers, FrT.vec(q, be or BACKEND), be)
 
 
 def verify_commitment_key_g2_kzg_opening(v_srs, ck_final, ck_opening, transcript, r_shift, z):
@@ -674,20 +702,26 @@ class AggregateProof:
 def aggregate_proofs(srs, proofs, digest=blake2b, be=None):
     """groth16_aggregation.rs:77-160.  proofs = list of (A in G1, B in G2, C in G1)."""
     be = be or BACKEND
-    a = [p[0] for p in proofs]
-    b = [p[1] for p in proofs]
-    c = [p[2] for p in proofs]
+    if hasattr(proofs, "column"):  # columnar container of packed vectors (oracle/cpu_baseline.py)
+        a, b, c = proofs.column(0), proofs.column(1), proofs.column(2)
+    else:
+        a = G1T.vec([p[0] for p in proofs], be)
+        b = G2T.vec([p[1] for p in proofs], be)
+        c = G1T.vec([p[2] for p in proofs], be)
     ck_1, ck_2 = srs.get_commitment_keys()
+    ck_1, ck_2 = G2T.vec(ck_1, be), G1T.vec(ck_2, be)
     IP = PairingInnerProduct
     com_a = IP.inner_product(a, ck_1, be)
     com_b = IP.inner_product(ck_2, b, be)
     com_c = IP.inner_product(c, ck_1, be)
     r = _agg_challenge(digest, com_a, com_b, com_c)
     r_vec = structured_scalar_power(len(proofs), r)
+    r_inv_vec = FrT.vec([E.fr_inv(x) for x in r_vec], be)
+    r_vec = FrT.vec(r_vec, be)
     a_r = be.mul_vec_g1(a, r_vec)
     ip_ab = IP.inner_product(a_r, b, be)
     agg_c = MultiexponentiationInnerProduct(G1T).inner_product(c, r_vec, be)
-    ck_1_r = be.mul_vec_g2(ck_1, [E.fr_inv(x) for x in r_vec])
+    ck_1_r = be.mul_vec_g2(ck_1, r_inv_vec)
     assert com_a == IP.inner_product(a_r, ck_1_r, be)
     tipa_proof_ab = _tipp_ab(digest, be).prove_with_srs_shift(srs, (a_r, b), (ck_1_r, ck_2, None), r)
     tipa_proof_c = _tipp_c(digest, be).prove_with_structured_scalar_message(srs, (c, r_vec), (ck_1, None))

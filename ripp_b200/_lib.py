@@ -135,6 +135,18 @@ class Context:
     def set_stream(self, cuda_stream):
         check(lib().ripp_ctx_set_stream(self.handle, ctypes.c_void_p(int(cuda_stream) if cuda_stream else 0)))
 
+    TIMING_CATS = ("miller", "final_exp", "msm", "fold", "scale", "other")
+
+    def set_timing(self, on):
+        check(lib().ripp_ctx_set_timing(self.handle, int(on)))
+
+    def timing(self):
+        """-> {category: (ms, scopes)} since the last call (synchronises)."""
+        ms = (ctypes.c_double * 6)()
+        cnt = (ctypes.c_uint64 * 6)()
+        check(lib().ripp_ctx_timing(self.handle, ms, cnt))
+        return {c: (ms[i], int(cnt[i])) for i, c in enumerate(self.TIMING_CATS)}
+
     @property
     def launches(self):
         return int(lib().ripp_ctx_launch_count(self.handle))
@@ -243,6 +255,16 @@ class Context:
         plen = ctypes.c_size_t()
         check(lib().ripp_tipp_aggregate_dev(self.handle, _p(srs_g1), _p(srs_g2), _p(a), _p(b), _p(c), ctypes.c_size_t(n),
                                             _p(proof), ctypes.c_size_t(cap), ctypes.byref(plen)))
+        return proof[: plen.value].tobytes()
+
+    def tipp_aggregate(self, srs_g1, srs_g2, a_host, b_host, c_host):
+        n = len(a_host)
+        k = max(n.bit_length() - 1, 0)
+        cap = 8 * 600 + 2 * (64 + k * 6 * 600 + 8 * 600)
+        proof = np.empty(cap, dtype=np.uint8)
+        plen = ctypes.c_size_t()
+        check(lib().ripp_tipp_aggregate(self.handle, _p(srs_g1), _p(srs_g2), _p(a_host), _p(b_host), _p(c_host),
+                                        ctypes.c_size_t(n), _p(proof), ctypes.c_size_t(cap), ctypes.byref(plen)))
         return proof[: plen.value].tobytes()
 
     # ---- diagnostics ----------------------------------------------------------------------

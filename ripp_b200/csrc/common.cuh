@@ -19,11 +19,20 @@ std::string& ripp_err_slot();
 
 #define RIPP_SCRATCH_SLOTS 16
 #define RIPP_MAX_BATCH 8
+// per-category device-time accounting (CUDA events on the context's stream; off by default)
+enum { RIPP_T_MILLER = 0, RIPP_T_FINAL_EXP, RIPP_T_MSM, RIPP_T_FOLD, RIPP_T_SCALE, RIPP_T_OTHER, RIPP_T_NCAT };
+struct TimingRec {
+  int cat;
+  cudaEvent_t a, b;
+};
+
 struct ripp_ctx {
   int device;
   cudaStream_t stream;
   cudaStream_t own_stream;
   uint64_t launches;
+  int timing;
+  std::vector<TimingRec>* recs;
   // scratch (grown on demand)
   void* scratch[RIPP_SCRATCH_SLOTS];
   size_t scratch_bytes[RIPP_SCRATCH_SLOTS];
@@ -63,6 +72,23 @@ static inline int scratch(ripp_ctx* ctx, int slot, size_t bytes, void** out) {
   return RIPP_OK;
 }
 
+
+struct TimeScope {
+  ripp_ctx* c;
+  long idx;
+  TimeScope(ripp_ctx* ctx, int cat) : c(ctx), idx(-1) {
+    if (!c->timing || !c->recs) return;
+    TimingRec r;
+    r.cat = cat;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, c->stream);
+    c->recs->push_back(r);
+    idx = (long)c->recs->size() - 1;
+  }
+  ~TimeScope() {
+    if (idx >= 0) cudaEventRecord((*c->recs)[idx].b, c->stream);
+  }
+};
 
 // cross-file internals
 int ripp_pairing_batch_internal(ripp_ctx* ctx, int nseg, const void* const* g1, const void* const* g2, size_t n, void* out);

@@ -521,3 +521,17 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
   out.insert(out.end(), proof_c.begin(), proof_c.end());
   return copy_out(out, proof_out, proof_cap, proof_len);
 }
+
+extern "C" int ripp_tipp_aggregate(ripp_ctx* ctx, const void* srs_g1_dev, const void* srs_g2_dev, const void* a_host,
+                                   const void* b_host, const void* c_host, size_t n, uint8_t* proof_out, size_t proof_cap,
+                                   size_t* proof_len) {
+  if (!ctx || !a_host || !b_host || !c_host) return fail(RIPP_ERR_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  void* d;
+  OK(scratch(ctx, 14, n * (96 + 192 + 96) + 1024, &d));
+  char* p = (char*)d;
+  CU(cudaMemcpyAsync(p, a_host, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(p + n * 96, c_host, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(p + n * 192, b_host, n * 192, cudaMemcpyHostToDevice, ctx->stream));
+  return ripp_tipp_aggregate_dev(ctx, srs_g1_dev, srs_g2_dev, p, p + n * 192, p + n * 96, n, proof_out, proof_cap, proof_len);
+}

@@ -165,6 +165,7 @@ static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, A
     CU(cudaMemsetAsync(out, 0, sizeof(Aff<F>), ctx->stream));
     return RIPP_OK;
   }
+  TimeScope ts_(ctx, RIPP_T_MSM);
   MsmPlan p = msm_plan(n);
   size_t WB = (size_t)p.nw * p.B;
   void *canon, *cnt, *idx, *bkt, *parts;
@@ -302,6 +303,7 @@ static int fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c
   if (!ctx || !c || (n && (!hi || !lo || !out))) return fail(RIPP_ERR_ARG, "null argument");
   if (n == 0) return RIPP_OK;
   CU(cudaSetDevice(ctx->device));
+  TimeScope ts_(ctx, RIPP_T_FOLD);
   k_fold<F><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const Aff<F>*)hi, (const Aff<F>*)lo, scalar_bits(c), n,
                                                             (Aff<F>*)out);
   LAUNCHED(ctx);

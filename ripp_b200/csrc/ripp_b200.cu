@@ -19,6 +19,7 @@ extern "C" int ripp_ctx_create(int device, ripp_ctx** out) {
   c->device = device;
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
+  c->recs = new std::vector<TimingRec>();
   *out = c;
   return RIPP_OK;
 }
@@ -30,6 +31,13 @@ extern "C" void ripp_ctx_destroy(ripp_ctx* ctx) {
   for (int i = 0; i < RIPP_SCRATCH_SLOTS; i++)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   cudaStreamDestroy(ctx->own_stream);
+  if (ctx->recs) {
+    for (auto& r : *ctx->recs) {
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    delete ctx->recs;
+  }
   delete ctx;
 }
 
@@ -45,6 +53,30 @@ extern "C" int ripp_ctx_set_stream(ripp_ctx* ctx, void* s) {
   return RIPP_OK;
 }
 extern "C" uint64_t ripp_ctx_launch_count(ripp_ctx* ctx) { return ctx->launches; }
+extern "C" int ripp_ctx_set_timing(ripp_ctx* ctx, int on) {
+  if (!ctx) return fail(RIPP_ERR_ARG, "null ctx");
+  ctx->timing = on;
+  return RIPP_OK;
+}
+extern "C" int ripp_ctx_timing(ripp_ctx* ctx, double* ms_by_cat, uint64_t* count_by_cat) {
+  if (!ctx || !ms_by_cat || !count_by_cat) return fail(RIPP_ERR_ARG, "null argument");
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < RIPP_T_NCAT; i++) {
+    ms_by_cat[i] = 0;
+    count_by_cat[i] = 0;
+  }
+  for (auto& r : *ctx->recs) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms_by_cat[r.cat] += ms;
+      count_by_cat[r.cat]++;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  ctx->recs->clear();
+  return RIPP_OK;
+}
 
 extern "C" int ripp_dev_alloc(ripp_ctx* ctx, size_t bytes, void** dev_out) {
   CU(cudaSetDevice(ctx->device));
@@ -147,6 +179,7 @@ static int scale_dev(ripp_ctx* ctx, const void* pts, const void* sc, size_t n, v
   if (!ctx || (n && (!sc || !out))) return fail(RIPP_ERR_ARG, "null argument");
   if (n == 0) return RIPP_OK;
   CU(cudaSetDevice(ctx->device));
+  TimeScope ts_(ctx, RIPP_T_SCALE);
   unsigned blocks = (unsigned)((n + 63) / 64);
   if (pts)
     k_scale<F, false><<<blocks, 64, 0, ctx->stream>>>((const Aff<F>*)pts, (const Fr*)sc, n, (Aff<F>*)out, gen);
@@ -376,6 +409,7 @@ static int miller_partial(ripp_ctx* ctx, const G1Aff* p, const G2Aff* q, size_t 
   void *bufA, *bufB;
   OK(scratch(ctx, 2, nwarps * sizeof(Fq12), &bufA));
   OK(scratch(ctx, 3, ((nwarps + R - 1) / R) * sizeof(Fq12) + 256, &bufB));
+  TimeScope ts_(ctx, RIPP_T_MILLER);
   k_miller<MILLER_BLOCK><<<(unsigned)nblocks, MILLER_BLOCK, 0, ctx->stream>>>(p, q, n, (Fq12*)bufA);
   LAUNCHED(ctx);
   size_t m = nwarps;
@@ -457,21 +491,25 @@ int ripp_pairing_batch_internal(ripp_ctx* ctx, int nseg, const void* const* g1, 
   OK(scratch(ctx, 2, nwarps * sizeof(Fq12), &bufA));
   OK(scratch(ctx, 3, nwarps * sizeof(Fq12) / 4 + 4096, &bufB));
   const int WPB = MILLER_BLOCK / 32;
-  k_miller_batch<MILLER_BLOCK><<<(unsigned)((nwarps + WPB - 1) / WPB), MILLER_BLOCK, 0, ctx->stream>>>(b, (Fq12*)bufA);
-  LAUNCHED(ctx);
   uint32_t T = b.wps;
   const uint32_t R = 8;
   Fq12 *src = (Fq12*)bufA, *dst = (Fq12*)bufB;
-  while (T > R) {
-    uint32_t To = (T + R - 1) / R;
-    size_t tot = (size_t)nseg * To;
-    k_fq12_reduce_seg<<<(unsigned)((tot + 63) / 64), 64, 0, ctx->stream>>>(src, T, R, To, dst, tot);
+  {
+    TimeScope ts_(ctx, RIPP_T_MILLER);
+    k_miller_batch<MILLER_BLOCK><<<(unsigned)((nwarps + WPB - 1) / WPB), MILLER_BLOCK, 0, ctx->stream>>>(b, (Fq12*)bufA);
     LAUNCHED(ctx);
-    Fq12* t = src;
-    src = dst;
-    dst = t;
-    T = To;
+    while (T > R) {
+      uint32_t To = (T + R - 1) / R;
+      size_t tot = (size_t)nseg * To;
+      k_fq12_reduce_seg<<<(unsigned)((tot + 63) / 64), 64, 0, ctx->stream>>>(src, T, R, To, dst, tot);
+      LAUNCHED(ctx);
+      Fq12* t = src;
+      src = dst;
+      dst = t;
+      T = To;
+    }
   }
+  TimeScope ts2_(ctx, RIPP_T_FINAL_EXP);
   k_final_exp_seg<<<1, 32, 0, ctx->stream>>>(src, T, (Fq12*)out, nseg);
   LAUNCHED(ctx);
   return RIPP_OK;
@@ -494,6 +532,7 @@ extern "C" int ripp_gt_combine_dev(ripp_ctx* ctx, const void* partials, size_t c
   CU(cudaSetDevice(ctx->device));
   void* tmp;
   OK(scratch(ctx, 3, sizeof(Fq12) + 256, &tmp));
+  TimeScope ts_(ctx, RIPP_T_FINAL_EXP);
   k_fq12_reduce<<<1, 32, 0, ctx->stream>>>((const Fq12*)partials, count, (int)count, (Fq12*)tmp);
   LAUNCHED(ctx);
   k_final_exp<<<1, 32, 0, ctx->stream>>>((const Fq12*)tmp, (Fq12*)out, 1);
@@ -507,6 +546,7 @@ extern "C" int ripp_pairing_ip_dev(ripp_ctx* ctx, const void* g1, const void* g2
   void* part;
   OK(scratch(ctx, 1, sizeof(Fq12) + 256, &part));
   OK(miller_partial(ctx, (const G1Aff*)g1, (const G2Aff*)g2, n, (Fq12*)part));
+  TimeScope ts_(ctx, RIPP_T_FINAL_EXP);
   k_final_exp<<<1, 32, 0, ctx->stream>>>((const Fq12*)part, (Fq12*)out, 1);
   LAUNCHED(ctx);
   return RIPP_OK;

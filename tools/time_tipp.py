@@ -1,0 +1,13 @@
+"""Quick timing of ripp_tipp_aggregate_dev (dev tool; bench.py is the contract)."""
+import sys, time
+sys.path.insert(0, ".")
+from ripp_b200 import _lib, synth
+logn = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+ctx = _lib.Context(0)
+n = 1 << logn
+t0 = time.time(); inst = synth.tipp_instance_dev(ctx, n); print("setup s", time.time() - t0)
+for i in range(reps):
+    l0 = ctx.launches; t0 = time.time()
+    proof = ctx.tipp_aggregate_dev(inst["srs_g1"], inst["srs_g2"], inst["a"], inst["b"], inst["c"], n)
+    print("aggregate n=%d: %.1f ms, %d launches, %d proof bytes" % (n, 1e3 * (time.time() - t0), ctx.launches - l0, len(proof)))
