@@ -19,6 +19,7 @@ std::string& ripp_err_slot();
 
 #define RIPP_SCRATCH_SLOTS 16
 #define RIPP_MAX_BATCH 8
+#define RIPP_MAX_CHILD 8
 // per-category device-time accounting (CUDA events on the context's stream; off by default)
 enum { RIPP_T_MILLER = 0, RIPP_T_FINAL_EXP, RIPP_T_MSM, RIPP_T_FOLD, RIPP_T_SCALE, RIPP_T_OTHER, RIPP_T_NCAT };
 struct TimingRec {
@@ -33,6 +34,10 @@ struct ripp_ctx {
   uint64_t launches;
   int timing;
   std::vector<TimingRec>* recs;
+  // child contexts (own stream + scratch, same device) for work that may overlap on the GPU
+  ripp_ctx* child[RIPP_MAX_CHILD];
+  ripp_ctx* parent;
+  cudaEvent_t ev;
   // scratch (grown on demand)
   void* scratch[RIPP_SCRATCH_SLOTS];
   size_t scratch_bytes[RIPP_SCRATCH_SLOTS];
@@ -91,4 +96,11 @@ struct TimeScope {
 };
 
 // cross-file internals
+ripp_ctx* ripp_child(ripp_ctx* ctx, int idx);          // lazily created; NULL on failure
+int ripp_fork(ripp_ctx* ctx, ripp_ctx* child);         // child's stream waits for everything queued on ctx's
+int ripp_join(ripp_ctx* ctx, ripp_ctx* child);         // ctx's stream waits for everything queued on child's
 int ripp_pairing_batch_internal(ripp_ctx* ctx, int nseg, const void* const* g1, const void* const* g2, size_t n, void* out);
+int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const void* const* g2, size_t n, void* out,
+                          bool with_final_exp);
+int ripp_final_exp_l6(ripp_ctx* ctx, const void* in, uint32_t T, void* out, int nseg);
+bool ripp_use_l6();

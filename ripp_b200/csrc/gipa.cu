@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "hash.h"
 
+#include <thread>
+
 typedef std::vector<uint8_t> Bytes;
 
 // ------------------------------------------------------------------------------------------------
@@ -150,25 +152,36 @@ static int eval_products(ripp_ctx* ctx, int k, const Slice* xs, const Slice* ys,
       pair_slot[np++] = i;
     }
   }
+  // children see the state the caller queued on ctx's stream (previous folds) before they start
+  for (int j = 0; j < 6; j++)
+    if (ctx->child[j]) OK(ripp_fork(ctx, ctx->child[j]));
   if (np) OK(ripp_pairing_batch_internal(ctx, np, g1, g2, n, r));
   for (int j = 0; j < np; j++)
     CU(cudaMemcpyAsync(out[pair_slot[j]].raw, r + 576 * j, 576, cudaMemcpyDeviceToHost, ctx->stream));
+  // MSM-type products run on child streams, overlapping each other and the pairing batch
+  ripp_ctx* kids[8];
+  int nk = 0;
   for (int i = 0; i < k; i++) {
     int a = xs[i].t, b = ys[i].t;
     if (out[i].t == VT_GT || a == VT_NONE || b == VT_NONE) continue;
     char* dst = r + 8 * 576 + 576 * i;
     if (a == VT_FR && b == VT_FR) {
       OK(ripp_scalar_ip_dev(ctx, xs[i].p, ys[i].p, n, dst));
-    } else {
-      const char* pts = a == VT_FR ? ys[i].p : xs[i].p;
-      const char* sc = a == VT_FR ? xs[i].p : ys[i].p;
-      if (out[i].t == VT_G1)
-        OK(ripp_msm_g1_dev(ctx, pts, sc, n, dst));
-      else
-        OK(ripp_msm_g2_dev(ctx, pts, sc, n, dst));
+      CU(cudaMemcpyAsync(out[i].raw, dst, 32, cudaMemcpyDeviceToHost, ctx->stream));
+      continue;
     }
-    CU(cudaMemcpyAsync(out[i].raw, dst, vt_size(out[i].t), cudaMemcpyDeviceToHost, ctx->stream));
+    ripp_ctx* kid = ripp_child(ctx, nk % 6);
+    if (!kid) return fail(RIPP_ERR_CUDA, "child context");
+    kids[nk++] = kid;
+    const char* pts = a == VT_FR ? ys[i].p : xs[i].p;
+    const char* sc = a == VT_FR ? xs[i].p : ys[i].p;
+    if (out[i].t == VT_G1)
+      OK(ripp_msm_g1_dev(kid, pts, sc, n, dst));
+    else
+      OK(ripp_msm_g2_dev(kid, pts, sc, n, dst));
+    CU(cudaMemcpyAsync(out[i].raw, dst, vt_size(out[i].t), cudaMemcpyDeviceToHost, kid->stream));
   }
+  for (int j = 0; j < nk; j++) CU(cudaStreamSynchronize(kids[j]->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return RIPP_OK;
 }
@@ -254,10 +267,22 @@ static int gipa_prove(ripp_ctx* ctx, const GipaSpec& sp, const void* a_in, const
       }
     }
     // gipa.rs:261-291 -- rescale
-    OK(fold_typed(ctx, sp.a, A, split, c));
-    OK(fold_typed(ctx, sp.b, B, split, c_inv));
-    OK(fold_typed(ctx, sp.v, V, split, c_inv));
-    OK(fold_typed(ctx, sp.w, W, split, c));
+    {
+      ripp_ctx* k1 = ripp_child(ctx, 0);
+      ripp_ctx* k2 = ripp_child(ctx, 1);
+      ripp_ctx* k3 = ripp_child(ctx, 2);
+      if (!k1 || !k2 || !k3) return fail(RIPP_ERR_CUDA, "child context");
+      OK(ripp_fork(ctx, k1));
+      OK(ripp_fork(ctx, k2));
+      OK(ripp_fork(ctx, k3));
+      OK(fold_typed(ctx, sp.a, A, split, c));
+      OK(fold_typed(k1, sp.b, B, split, c_inv));
+      OK(fold_typed(k2, sp.v, V, split, c_inv));
+      OK(fold_typed(k3, sp.w, W, split, c));
+      OK(ripp_join(ctx, k1));
+      OK(ripp_join(ctx, k2));
+      OK(ripp_join(ctx, k3));
+    }
     steps.push_back(com);
     transcript.push_back(c);
     len = split;
@@ -509,9 +534,28 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
   CU(cudaMemcpyAsync(agg_c.raw, W + o_res, 96, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   // :138-149 the two TIPA proofs
+  // ... which are independent: run them from two host threads on two child contexts so their
+  // (latency-bound) rounds overlap on the GPU
   Bytes proof_ab, proof_c;
-  OK(tipa_prove(ctx, RIPP_GIPA_PAIRING, srs_g1_dev, srs_g2_dev, W + o_ar, b_dev, W + o_ck1r, ck2, n, r, &proof_ab));
-  OK(tipa_prove(ctx, RIPP_GIPA_MULTIEXP_SSM, srs_g1_dev, srs_g2_dev, c_dev, W + o_pw, ck1, nullptr, n, Fr::one(), &proof_c));
+  {
+    ripp_ctx* ka = ripp_child(ctx, 6);
+    ripp_ctx* kc = ripp_child(ctx, 7);
+    if (!ka || !kc) return fail(RIPP_ERR_CUDA, "child context");
+    OK(ripp_fork(ctx, ka));
+    OK(ripp_fork(ctx, kc));
+    int st_c = RIPP_OK;
+    std::string err_c;
+    std::thread tc([&] {
+      st_c = tipa_prove(kc, RIPP_GIPA_MULTIEXP_SSM, srs_g1_dev, srs_g2_dev, c_dev, W + o_pw, ck1, nullptr, n, Fr::one(), &proof_c);
+      if (st_c != RIPP_OK) err_c = ripp_err_slot();
+    });
+    int st_a = tipa_prove(ka, RIPP_GIPA_PAIRING, srs_g1_dev, srs_g2_dev, W + o_ar, b_dev, W + o_ck1r, ck2, n, r, &proof_ab);
+    tc.join();
+    if (st_a != RIPP_OK) return st_a;
+    if (st_c != RIPP_OK) return fail(st_c, err_c);
+    OK(ripp_join(ctx, ka));
+    OK(ripp_join(ctx, kc));
+  }
   // AggregateProof { com_a, com_b, com_c, ip_ab, agg_c, tipa_proof_ab, tipa_proof_c } (:58-66)
   Bytes out;
   for (int i = 0; i < 3; i++) put_val(out, com[i]);

@@ -1,0 +1,398 @@
+// "L6": an Fq12 value spread over six lanes of a warp, one Fq2 coefficient of the flat basis
+// 1, w, ..., w^5 (w^6 = xi) per lane, with the group's shared-memory scratch as the exchange medium.
+//
+// Why: a thread-per-pairing Miller loop needs ~250 live 32-bit registers of state and ends up
+// streaming its tower through local memory; worse, at the small vector lengths of the late GIPA
+// rounds (and for the final exponentiation, of which there is one per product) a single thread is a
+// ~10^7-instruction serial chain.  Spreading one Fq12 over six lanes keeps every coefficient in
+// registers, turns Fq12 products into six independent Fq2 accumulations (schoolbook in w, which is as
+// cheap as the Karatsuba tower once the outputs are computed in parallel) and cuts the latency of a
+// Miller loop / final exponentiation by ~4-5x while staying work-efficient at large n.
+//
+// Five groups (30 lanes) per warp; the last two lanes run the same instruction stream on a junk slot.
+// All lanes execute identical code: per-lane differences are data (smem addresses, selects), never
+// branches.  Host build (tests/hostsim): each lane is a std::thread, sync() is a barrier.
+#pragma once
+#include "pairing.cuh"
+
+namespace ripp {
+namespace l6 {
+
+// ---- group scratch layout (32-bit words) ---------------------------------------------------------
+constexpr int FQ2W = 24;
+constexpr int F12W = 6 * FQ2W;
+constexpr int OFF_T = 0;                  // running point T: x, y, z
+constexpr int OFF_R = OFF_T + 3 * FQ2W;   // round results R0..R5
+constexpr int OFF_LINE = OFF_R + F12W;    // line coefficients d0, d1, d4
+constexpr int OFF_P = OFF_LINE + 3 * FQ2W;  // xP, yP (Fq each)
+constexpr int OFF_Q = OFF_P + FQ2W;       // xQ, yQ
+constexpr int OFF_F = OFF_Q + 2 * FQ2W;   // Fq12 registers F0..F(NREG-1)
+constexpr int NREG = 5;
+constexpr int GROUP_WORDS = OFF_F + NREG * F12W;  // 1104 words = 4416 B
+
+struct Ctx {
+  int k;          // lane within the group, 0..5
+  uint32_t* sm;   // group scratch
+#if !defined(__CUDA_ARCH__)
+  void* bar;      // host: barrier object
+#endif
+};
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void sync(const Ctx&) { __syncwarp(); }
+#else
+void host_barrier(void* bar);
+inline void sync(const Ctx& c) { host_barrier(c.bar); }
+#endif
+
+// ---- force-inlined field helpers (everything stays in registers inside an L6 kernel) -------------
+RIPP_HD Fq fqmul(const Fq& a, const Fq& b) {
+  Fq r;
+  detail::mont_mul<FqParams>(r.v, a.v, b.v);
+  return r;
+}
+RIPP_HD Fq2 f2add(const Fq2& a, const Fq2& b) { return {a.c0 + b.c0, a.c1 + b.c1}; }
+RIPP_HD Fq2 f2sub(const Fq2& a, const Fq2& b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
+RIPP_HD Fq2 f2neg(const Fq2& a) { return {-a.c0, -a.c1}; }
+RIPP_HD Fq2 f2dbl(const Fq2& a) { return {a.c0 + a.c0, a.c1 + a.c1}; }
+RIPP_HD Fq2 f2half(const Fq2& a) { return {a.c0.half(), a.c1.half()}; }
+RIPP_HD Fq2 f2xi(const Fq2& a) { return {a.c0 - a.c1, a.c0 + a.c1}; }
+RIPP_HD Fq2 f2conj(const Fq2& a) { return {a.c0, -a.c1}; }
+RIPP_HD Fq2 f2mul(const Fq2& a, const Fq2& b) {
+  Fq t0 = fqmul(a.c0, b.c0);
+  Fq t1 = fqmul(a.c1, b.c1);
+  Fq t2 = fqmul(a.c0 + a.c1, b.c0 + b.c1);
+  return {t0 - t1, t2 - t0 - t1};
+}
+RIPP_HD Fq2 f2sel(bool c, const Fq2& a, const Fq2& b) {  // c ? a : b, branch-free
+  Fq2 r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    r.c0.v[i] = c ? a.c0.v[i] : b.c0.v[i];
+    r.c1.v[i] = c ? a.c1.v[i] : b.c1.v[i];
+  }
+  return r;
+}
+RIPP_HD Fq2 ld2(const uint32_t* p) {
+  Fq2 r;
+#if defined(__CUDA_ARCH__)
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    uint4 v = q[i];
+    uint32_t* d = (i < 3 ? r.c0.v : r.c1.v) + 4 * (i % 3);
+    d[0] = v.x;
+    d[1] = v.y;
+    d[2] = v.z;
+    d[3] = v.w;
+  }
+#else
+  for (int i = 0; i < 12; i++) {
+    r.c0.v[i] = p[i];
+    r.c1.v[i] = p[12 + i];
+  }
+#endif
+  return r;
+}
+RIPP_HD void st2(uint32_t* p, const Fq2& a) {
+#if defined(__CUDA_ARCH__)
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const uint32_t* s = (i < 3 ? a.c0.v : a.c1.v) + 4 * (i % 3);
+    q[i] = make_uint4(s[0], s[1], s[2], s[3]);
+  }
+#else
+  for (int i = 0; i < 12; i++) {
+    p[i] = a.c0.v[i];
+    p[12 + i] = a.c1.v[i];
+  }
+#endif
+}
+
+RIPP_HD uint32_t* freg(const Ctx& c, int r) { return c.sm + OFF_F + r * F12W; }
+
+// ---- Fq12 ops on smem registers (collective: all six lanes call with the same arguments) ---------
+// D = A * B on raw coefficient arrays (6 x Fq2, flat w-basis); D may alias A or B
+RIPP_HD void mul_p(const Ctx& c, uint32_t* D, const uint32_t* A, const uint32_t* B);
+// dst = a * b;  dst may alias a or b
+RIPP_HD void mul(const Ctx& c, int dst, int a, int b) { mul_p(c, freg(c, dst), freg(c, a), freg(c, b)); }
+RIPP_HD void mul_p(const Ctx& c, uint32_t* D, const uint32_t* A, const uint32_t* B) {
+  Fq2 acc = Fq2::zero();
+#pragma unroll 1
+  for (int i = 0; i < 6; i++) {
+    int j = c.k - i;
+    bool wrap = j < 0;
+    j += wrap ? 6 : 0;
+    Fq2 t = f2mul(ld2(A + i * FQ2W), ld2(B + j * FQ2W));
+    acc = f2add(acc, f2sel(wrap, f2xi(t), t));
+  }
+  sync(c);
+  st2(D + c.k * FQ2W, acc);
+  sync(c);
+}
+// dst = a^2: 21 distinct products over six lanes (cross terms doubled)
+RIPP_HD void sqr(const Ctx& c, int dst, int a) {
+  const uint32_t* A = freg(c, a);
+  Fq2 acc = Fq2::zero();
+  // pairs (i, j), i <= j, i + j = k or k + 6:  i runs over 0..3 slots; slots beyond the lane's count are masked
+#pragma unroll 1
+  for (int s = 0; s < 4; s++) {
+    // s-th solution for this lane: enumerate i = 0..5 with j = (k - i) mod 6 >= i
+    int cnt = -1, ii = 0, jj = 0;
+    bool wrap = false, found = false;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      int j = c.k - i;
+      bool w = j < 0;
+      j += w ? 6 : 0;
+      bool ok = j >= i;
+      cnt += ok ? 1 : 0;
+      bool take = ok && cnt == s && !found;
+      ii = take ? i : ii;
+      jj = take ? j : jj;
+      wrap = take ? w : wrap;
+      found = found || take;
+    }
+    Fq2 x = ld2(A + ii * FQ2W), y = ld2(A + jj * FQ2W);
+    Fq2 t = f2mul(x, y);
+    t = f2sel(ii != jj, f2dbl(t), t);
+    t = f2sel(wrap, f2xi(t), t);
+    acc = f2sel(found, f2add(acc, t), acc);
+  }
+  sync(c);
+  st2(freg(c, dst) + c.k * FQ2W, acc);
+  sync(c);
+}
+// dst = a * (d0 + d1 w^2 + d4 w^3), line coefficients at OFF_LINE (the ark-ec `mul_by_014` shape)
+RIPP_HD void mul_line(const Ctx& c, int dst, int a) {
+  const uint32_t* A = freg(c, a);
+  const uint32_t* L = c.sm + OFF_LINE;
+  int k = c.k;
+  int k2 = k - 2, k3 = k - 3;
+  bool w2 = k2 < 0, w3 = k3 < 0;
+  k2 += w2 ? 6 : 0;
+  k3 += w3 ? 6 : 0;
+  Fq2 acc = f2mul(ld2(A + k * FQ2W), ld2(L));
+  Fq2 t = f2mul(ld2(A + k2 * FQ2W), ld2(L + FQ2W));
+  acc = f2add(acc, f2sel(w2, f2xi(t), t));
+  t = f2mul(ld2(A + k3 * FQ2W), ld2(L + 2 * FQ2W));
+  acc = f2add(acc, f2sel(w3, f2xi(t), t));
+  sync(c);
+  st2(freg(c, dst) + k * FQ2W, acc);
+  sync(c);
+}
+// dst = conj(a)  (w -> -w)
+RIPP_HD void conj(const Ctx& c, int dst, int a) {
+  Fq2 v = ld2(freg(c, a) + c.k * FQ2W);
+  v = f2sel(c.k & 1, f2neg(v), v);
+  sync(c);
+  st2(freg(c, dst) + c.k * FQ2W, v);
+  sync(c);
+}
+RIPP_HD void copy(const Ctx& c, int dst, int a) {
+  Fq2 v = ld2(freg(c, a) + c.k * FQ2W);
+  sync(c);
+  st2(freg(c, dst) + c.k * FQ2W, v);
+  sync(c);
+}
+RIPP_HD void set_one(const Ctx& c, int dst) {
+  st2(freg(c, dst) + c.k * FQ2W, f2sel(c.k == 0, Fq2::one(), Fq2::zero()));
+  sync(c);
+}
+RIPP_HD Fq2 frob_gamma(int npow, int k) {
+  Fq2 g;
+#pragma unroll 1
+  for (int i = 0; i < 12; i++) {
+    g.c0.v[i] = npow == 1 ? k::FROB1(24 * k + i) : k::FROB2(24 * k + i);
+    g.c1.v[i] = npow == 1 ? k::FROB1(24 * k + 12 + i) : k::FROB2(24 * k + 12 + i);
+  }
+  return g;
+}
+// dst = a^(p^npow), npow in {1, 2}: lane-local
+RIPP_HD void frob(const Ctx& c, int dst, int a, int npow) {
+  Fq2 v = ld2(freg(c, a) + c.k * FQ2W);
+  v = f2sel(npow & 1, f2conj(v), v);
+  v = f2mul(v, frob_gamma(npow, c.k));
+  sync(c);
+  st2(freg(c, dst) + c.k * FQ2W, v);
+  sync(c);
+}
+// dst = a^-1 via the norm to Fq2: N = a conj(a) in Fq6, d = N N^(p^2) N^(p^4) in Fq2, a^-1 = conj(a) N^(p^2) N^(p^4) / d.
+// Clobbers registers t0, t1, t2 (all distinct from a and dst).
+RIPP_HD void inv(const Ctx& c, int dst, int a, int t0, int t1, int t2) {
+  conj(c, t0, a);
+  mul(c, t1, a, t0);      // N
+  frob(c, t2, t1, 2);     // N^(p^2)
+  frob(c, dst, t2, 2);    // N^(p^4)
+  mul(c, t2, t2, dst);    // T = N^(p^2) N^(p^4)
+  mul(c, dst, t1, t2);    // d = N T, only the w^0 coefficient is non-zero
+  Fq2 d = ld2(freg(c, dst));
+  Fq dn = (fqmul(d.c0, d.c0) + fqmul(d.c1, d.c1)).inv();
+  Fq2 dinv = {fqmul(d.c0, dn), -fqmul(d.c1, dn)};
+  Fq2 tk = f2mul(ld2(freg(c, t2) + c.k * FQ2W), dinv);
+  sync(c);
+  st2(freg(c, t2) + c.k * FQ2W, tk);  // N^-1
+  sync(c);
+  mul(c, dst, t0, t2);
+}
+
+// a^x (x = -|x|) for a in the cyclotomic subgroup; dst != a; clobbers nothing else
+RIPP_HD void exp_by_x(const Ctx& c, int dst, int a) {
+  copy(c, dst, a);
+#pragma unroll 1
+  for (int i = 62; i >= 0; i--) {
+    sqr(c, dst, dst);
+    if ((k::X_ABS >> i) & 1) mul(c, dst, dst, a);
+  }
+  conj(c, dst, dst);
+}
+
+// Register 0 <- final_exponentiation(register 0) (ark-ec convention, see pairing.cuh); needs 8 registers.
+RIPP_HD void final_exp(const Ctx& c) {
+  enum { F = 0, R = 1, Y0 = 2, Y1 = 3, Y2 = 4, T0 = 5, T1 = 6, T2 = 7 };
+  inv(c, R, F, T0, T1, T2);   // R = f^-1
+  conj(c, Y0, F);
+  mul(c, R, Y0, R);           // f^(p^6 - 1)
+  frob(c, Y0, R, 2);
+  mul(c, R, Y0, R);           // ^(p^2 + 1)
+  sqr(c, Y0, R);              // y0 = r^2
+  exp_by_x(c, Y1, R);         // y1 = r^x
+  conj(c, Y2, R);
+  mul(c, Y1, Y1, Y2);
+  exp_by_x(c, Y2, Y1);
+  conj(c, Y1, Y1);
+  mul(c, Y1, Y1, Y2);
+  exp_by_x(c, Y2, Y1);
+  frob(c, Y1, Y1, 1);
+  mul(c, Y1, Y1, Y2);
+  mul(c, R, R, Y0);
+  exp_by_x(c, Y0, Y1);
+  exp_by_x(c, Y2, Y0);
+  frob(c, Y0, Y1, 2);
+  conj(c, Y1, Y1);
+  mul(c, Y1, Y1, Y2);
+  mul(c, Y1, Y1, Y0);
+  mul(c, F, R, Y1);
+}
+
+// ---- Miller loop --------------------------------------------------------------------------------
+// smem: T = (x, y, z) at OFF_T, P = (xP, yP) at OFF_P, Q = (xQ, yQ) at OFF_Q, accumulator in register 0.
+// One doubling step: two rounds of at most six parallel Fq2 products.
+RIPP_HD void dbl_step(const Ctx& c) {
+  uint32_t* T = c.sm + OFF_T;
+  uint32_t* R = c.sm + OFF_R;
+  const int k = c.k;
+  Fq2 x = ld2(T), y = ld2(T + FQ2W), z = ld2(T + 2 * FQ2W);
+  // round 1: R0 = x y, R1 = y^2, R2 = z^2, R3 = (y + z)^2, R4 = x^2, R5 = unused
+  Fq2 yz = f2add(y, z);
+  Fq2 u = f2sel(k == 0 || k == 4, x, f2sel(k == 3, yz, f2sel(k == 2, z, y)));
+  Fq2 v = f2sel(k == 0 || k == 1, y, f2sel(k == 3, yz, f2sel(k == 2, z, x)));
+  st2(R + k * FQ2W, f2mul(u, v));
+  sync(c);
+  Fq2 a = f2half(ld2(R)), b = ld2(R + FQ2W), cc = ld2(R + 2 * FQ2W), d = ld2(R + 3 * FQ2W), j = ld2(R + 4 * FQ2W);
+  Fq2 e = f2dbl(f2dbl(f2xi(f2add(f2dbl(cc), cc))));  // 4 xi * 3 z^2
+  Fq2 f = f2add(f2dbl(e), e);
+  Fq2 g = f2half(f2add(b, f));
+  Fq2 h = f2sub(d, f2add(b, cc));
+  Fq2 j3 = f2add(f2dbl(j), j);
+  sync(c);
+  // round 2: R0 = a (b - f), R1 = g^2, R2 = b h, R3 = e^2, R4 = 3j * xP, R5 = -h * yP
+  Fq xp = ld2(c.sm + OFF_P).c0, yp = ld2(c.sm + OFF_P).c1;
+  Fq2 sxp = {xp, Fq::zero()}, syp = {yp, Fq::zero()};
+  u = f2sel(k == 0, a, f2sel(k == 1, g, f2sel(k == 2, b, f2sel(k == 3, e, f2sel(k == 4, j3, f2neg(h))))));
+  v = f2sel(k == 0, f2sub(b, f), f2sel(k == 1, g, f2sel(k == 2, h, f2sel(k == 3, e, f2sel(k == 4, sxp, syp)))));
+  st2(R + k * FQ2W, f2mul(u, v));
+  sync(c);
+  // new T and the line (d0, d1, d4) = (e - b, 3j xP, -h yP)
+  Fq2 e2 = ld2(R + 3 * FQ2W);
+  Fq2 nx = ld2(R), ny = f2sub(ld2(R + FQ2W), f2add(f2dbl(e2), e2)), nz = ld2(R + 2 * FQ2W);
+  Fq2 d1 = ld2(R + 4 * FQ2W), d4 = ld2(R + 5 * FQ2W);
+  sync(c);
+  if (k == 0) {
+    st2(T, nx);
+    st2(T + FQ2W, ny);
+    st2(T + 2 * FQ2W, nz);
+  }
+  if (k == 1) {
+    st2(c.sm + OFF_LINE, f2sub(e, b));
+    st2(c.sm + OFF_LINE + FQ2W, d1);
+    st2(c.sm + OFF_LINE + 2 * FQ2W, d4);
+  }
+  sync(c);
+}
+
+// One addition step T <- T + Q with the chord line.
+RIPP_HD void add_step(const Ctx& c) {
+  uint32_t* T = c.sm + OFF_T;
+  uint32_t* R = c.sm + OFF_R;
+  const int k = c.k;
+  Fq2 x = ld2(T), y = ld2(T + FQ2W), z = ld2(T + 2 * FQ2W);
+  Fq2 qx = ld2(c.sm + OFF_Q), qy = ld2(c.sm + OFF_Q + FQ2W);
+  // round 1: R0 = qy z, R1 = qx z
+  st2(R + k * FQ2W, f2mul(f2sel(k == 0, qy, qx), z));
+  sync(c);
+  Fq2 theta = f2sub(y, ld2(R)), lambda = f2sub(x, ld2(R + FQ2W));
+  sync(c);
+  // round 2: R0 = theta^2, R1 = lambda^2, R2 = theta qx, R3 = lambda qy
+  Fq2 u = f2sel(k == 0 || k == 2, theta, lambda);
+  Fq2 v = f2sel(k == 0, theta, f2sel(k == 1, lambda, f2sel(k == 2, qx, qy)));
+  st2(R + k * FQ2W, f2mul(u, v));
+  sync(c);
+  Fq2 cc = ld2(R), d = ld2(R + FQ2W), jv = f2sub(ld2(R + 2 * FQ2W), ld2(R + 3 * FQ2W));
+  sync(c);
+  // round 3: R0 = lambda d (= e), R1 = z c (= f), R2 = x d (= g)
+  u = f2sel(k == 0, lambda, f2sel(k == 1, z, x));
+  v = f2sel(k == 1, cc, d);
+  st2(R + k * FQ2W, f2mul(u, v));
+  sync(c);
+  Fq2 e = ld2(R), f = ld2(R + FQ2W), g = ld2(R + 2 * FQ2W);
+  Fq2 h = f2sub(f2add(e, f), f2dbl(g));
+  sync(c);
+  // round 4: R0 = lambda h, R1 = theta (g - h), R2 = e y, R3 = z e, R4 = -theta xP, R5 = lambda yP
+  Fq xp = ld2(c.sm + OFF_P).c0, yp = ld2(c.sm + OFF_P).c1;
+  Fq2 sxp = {xp, Fq::zero()}, syp = {yp, Fq::zero()};
+  u = f2sel(k == 0, lambda, f2sel(k == 1, theta, f2sel(k == 2, e, f2sel(k == 3, z, f2sel(k == 4, f2neg(theta), lambda)))));
+  v = f2sel(k == 0, h, f2sel(k == 1, f2sub(g, h), f2sel(k == 2, y, f2sel(k == 3, e, f2sel(k == 4, sxp, syp)))));
+  st2(R + k * FQ2W, f2mul(u, v));
+  sync(c);
+  Fq2 nx = ld2(R), ny = f2sub(ld2(R + FQ2W), ld2(R + 2 * FQ2W)), nz = ld2(R + 3 * FQ2W);
+  Fq2 d1 = ld2(R + 4 * FQ2W), d4 = ld2(R + 5 * FQ2W);
+  sync(c);
+  if (k == 0) {
+    st2(T, nx);
+    st2(T + FQ2W, ny);
+    st2(T + 2 * FQ2W, nz);
+  }
+  if (k == 1) {
+    st2(c.sm + OFF_LINE, jv);
+    st2(c.sm + OFF_LINE + FQ2W, d1);
+    st2(c.sm + OFF_LINE + 2 * FQ2W, d4);
+  }
+  sync(c);
+}
+
+// Register 0 <- f_{|x|,Q}(P) conjugated.  P, Q must be loaded at OFF_P / OFF_Q (finite points).
+RIPP_HD void miller(const Ctx& c) {
+  uint32_t* T = c.sm + OFF_T;
+  if (c.k == 0) {
+    st2(T, ld2(c.sm + OFF_Q));
+    st2(T + FQ2W, ld2(c.sm + OFF_Q + FQ2W));
+    st2(T + 2 * FQ2W, Fq2::one());
+  }
+  set_one(c, 0);
+#pragma unroll 1
+  for (int i = 62; i >= 0; i--) {
+    sqr(c, 0, 0);
+    dbl_step(c);
+    mul_line(c, 0, 0);
+    if ((k::X_ABS >> i) & 1) {
+      add_step(c);
+      mul_line(c, 0, 0);
+    }
+  }
+  conj(c, 0, 0);
+}
+
+}  // namespace l6
+}  // namespace ripp

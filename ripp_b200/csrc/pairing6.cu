@@ -1,0 +1,199 @@
+// Multi-Miller loop and final exponentiation on the six-lane Fq12 engine (l6.cuh).
+// Replaces cfg_multi_pairing's hot loop (inner_products/src/lib.rs:83-115): one (G1, G2) pair per
+// six-lane group, five groups per warp, the warp's five Miller values multiplied in shared memory,
+// one Fq12 partial per warp, a tree of group products, and one group per final exponentiation.
+#include "common.cuh"
+#include "l6.cuh"
+
+using namespace ripp::l6;
+
+static __device__ __forceinline__ int tower_slot(int k) { return (k & 1) * 3 + (k >> 1); }
+
+struct Miller6Batch {
+  const G1Aff* p[RIPP_MAX_BATCH];
+  const G2Aff* q[RIPP_MAX_BATCH];
+  uint32_t n, wps;  // pairs per segment, warps per segment (5 pairs per warp)
+  int nseg;
+};
+
+constexpr int M6_NREG = 2;
+constexpr int M6_GROUP_WORDS = OFF_F + M6_NREG * F12W;
+constexpr int M6_WARP_WORDS = 6 * M6_GROUP_WORDS;  // five groups + one junk slot for lanes 30, 31
+
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_miller6(Miller6Batch b, Fq12* __restrict__ partials) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / 6;
+  uint32_t* wsm = smem + warp * M6_WARP_WORDS;
+  Ctx c{lane % 6, wsm + g * M6_GROUP_WORDS};
+  const uint32_t gw = blockIdx.x * WARPS + warp;
+  const uint32_t seg = gw / b.wps, wl = gw % b.wps;
+  const uint32_t i = wl * 5 + g;
+  // lane 0 of each real group stages its pair; identities / padding run on the generators and are masked
+  int valid = 0;
+  if (c.k == 0) {
+    G1Aff P = g1_generator();
+    G2Aff Q = g2_generator();
+    if (g < 5 && seg < (uint32_t)b.nseg && i < b.n) {
+      G1Aff p = b.p[seg][i];
+      G2Aff q = b.q[seg][i];
+      if (!p.is_inf() && !q.is_inf()) {
+        P = p;
+        Q = q;
+        valid = 1;
+      }
+    }
+    st2(c.sm + OFF_P, Fq2{P.x, P.y});
+    st2(c.sm + OFF_Q, Q.x);
+    st2(c.sm + OFF_Q + FQ2W, Q.y);
+  }
+  valid = __shfl_sync(0xffffffffu, valid, (g * 6) & 31);
+  __syncwarp();
+  miller(c);
+  // masked groups contribute 1
+  {
+    Fq2 v = ld2(freg(c, 0) + c.k * FQ2W);
+    v = f2sel(valid, v, f2sel(c.k == 0, Fq2::one(), Fq2::zero()));
+    __syncwarp();
+    st2(freg(c, 0) + c.k * FQ2W, v);
+    __syncwarp();
+  }
+  // product of the five groups' values: (0 <- 0*1, 2 <- 2*3), 0 <- 0*2, 0 <- 0*4; idle groups write their junk register
+  uint32_t* F0 = freg(c, 0);
+  uint32_t* J = freg(c, 1);
+  auto other = [&](int gg) { return wsm + gg * M6_GROUP_WORDS + OFF_F; };
+  mul_p(c, (g == 0 || g == 2) ? F0 : J, F0, other(g == 0 ? 1 : (g == 2 ? 3 : g)));
+  mul_p(c, g == 0 ? F0 : J, F0, other(g == 0 ? 2 : g));
+  mul_p(c, g == 0 ? F0 : J, F0, other(g == 0 ? 4 : g));
+  if (g == 0 && seg < (uint32_t)b.nseg) {
+    Fq2* out = reinterpret_cast<Fq2*>(&partials[gw]);
+    out[tower_slot(c.k)] = ld2(F0 + c.k * FQ2W);
+  }
+}
+
+// out[s][j] = prod in[s][j*R .. min(T, j*R+R)) ; one group per output, five groups per warp
+constexpr int R6_GROUP_WORDS = OFF_F + 2 * F12W;
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_reduce6(const Fq12* __restrict__ in, uint32_t T, uint32_t R, uint32_t To,
+                                                       Fq12* __restrict__ out, uint32_t total) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / 6;
+  Ctx c{lane % 6, smem + (warp * 6 + g) * R6_GROUP_WORDS};
+  uint32_t t = (blockIdx.x * WARPS + warp) * 5 + g;
+  bool live = g < 5 && t < total;
+  uint32_t s = live ? t / To : 0, j = live ? t % To : 0;
+  uint32_t lo = j * R, hi = lo + R < T ? lo + R : T;
+  const Fq2* src = reinterpret_cast<const Fq2*>(in + (size_t)s * T);
+  st2(freg(c, 0) + c.k * FQ2W, src[(size_t)lo * 6 + tower_slot(c.k)]);
+  __syncwarp();
+  for (uint32_t r = 1; r < R; r++) {  // uniform trip count; rows past `hi` multiply by one
+    bool on = lo + r < hi;
+    Fq2 v = on ? src[(size_t)(lo + r) * 6 + tower_slot(c.k)] : f2sel(c.k == 0, Fq2::one(), Fq2::zero());
+    st2(freg(c, 1) + c.k * FQ2W, v);
+    __syncwarp();
+    mul(c, 0, 0, 1);
+  }
+  if (live) reinterpret_cast<Fq2*>(out + t)[tower_slot(c.k)] = ld2(freg(c, 0) + c.k * FQ2W);
+}
+
+// out[s] = final_exponentiation(prod_j in[s][j]), j < T (T <= 8); one group per value
+constexpr int FE_NREG = 9;
+constexpr int FE_GROUP_WORDS = OFF_F + FE_NREG * F12W;
+__global__ void __launch_bounds__(64) k_final_exp6(const Fq12* __restrict__ in, uint32_t T, Fq12* __restrict__ out, int nseg) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / 6;
+  Ctx c{lane % 6, smem + (warp * 6 + g) * FE_GROUP_WORDS};
+  int s = (blockIdx.x * 2 + warp) * 5 + g;
+  bool live = g < 5 && s < nseg;
+  const Fq2* src = reinterpret_cast<const Fq2*>(in + (size_t)(live ? s : 0) * T);
+  st2(freg(c, 0) + c.k * FQ2W, src[tower_slot(c.k)]);
+  __syncwarp();
+  for (uint32_t r = 1; r < T; r++) {
+    st2(freg(c, 8) + c.k * FQ2W, src[(size_t)r * 6 + tower_slot(c.k)]);
+    __syncwarp();
+    mul(c, 0, 0, 8);
+  }
+  final_exp(c);
+  if (live) reinterpret_cast<Fq2*>(out + s)[tower_slot(c.k)] = ld2(freg(c, 0) + c.k * FQ2W);
+}
+
+static const int M6_WARPS = 4;
+
+int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const void* const* g2, size_t n, void* out,
+                          bool with_final_exp) {
+  if (nseg <= 0 || nseg > RIPP_MAX_BATCH) return fail(RIPP_ERR_ARG, "bad segment count");
+  CU(cudaSetDevice(ctx->device));
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(k_miller6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * M6_WARP_WORDS * 4));
+    CU(cudaFuncSetAttribute(k_reduce6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * R6_GROUP_WORDS * 4));
+    CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
+    attr_done = true;
+  }
+  Fq12 one = Fq12::one();
+  if (n == 0) {
+    for (int s = 0; s < nseg; s++)
+      CU(cudaMemcpyAsync((char*)out + 576 * s, &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RIPP_OK;
+  }
+  Miller6Batch b;
+  b.nseg = nseg;
+  b.n = (uint32_t)n;
+  b.wps = (uint32_t)((n + 4) / 5);
+  for (int s = 0; s < nseg; s++) {
+    b.p[s] = (const G1Aff*)g1[s];
+    b.q[s] = (const G2Aff*)g2[s];
+  }
+  size_t nwarps = (size_t)b.wps * nseg;
+  void *bufA, *bufB;
+  OK(scratch(ctx, 2, nwarps * sizeof(Fq12) + 4096, &bufA));
+  OK(scratch(ctx, 3, nwarps * sizeof(Fq12) / 4 + 8192, &bufB));
+  uint32_t T = b.wps;
+  const uint32_t R = 8;
+  Fq12 *src = (Fq12*)bufA, *dst = (Fq12*)bufB;
+  {
+    TimeScope ts_(ctx, RIPP_T_MILLER);
+    unsigned blocks = (unsigned)((nwarps + M6_WARPS - 1) / M6_WARPS);
+    k_miller6<M6_WARPS><<<blocks, 32 * M6_WARPS, M6_WARPS * M6_WARP_WORDS * 4, ctx->stream>>>(b, src);
+    LAUNCHED(ctx);
+    uint32_t stop = with_final_exp ? R : 1;
+    while (T > stop) {
+      uint32_t To = (T + R - 1) / R;
+      uint32_t tot = (uint32_t)nseg * To;
+      Fq12* o = (!with_final_exp && To == 1) ? (Fq12*)out : dst;
+      unsigned blk = (tot + 5 * M6_WARPS - 1) / (5 * M6_WARPS);
+      k_reduce6<M6_WARPS><<<blk, 32 * M6_WARPS, M6_WARPS * 6 * R6_GROUP_WORDS * 4, ctx->stream>>>(src, T, R, To, o, tot);
+      LAUNCHED(ctx);
+      Fq12* t = src;
+      src = dst;
+      dst = t;
+      T = To;
+    }
+  }
+  if (!with_final_exp) {
+    if (b.wps == 1) CU(cudaMemcpyAsync(out, bufA, (size_t)nseg * sizeof(Fq12), cudaMemcpyDeviceToDevice, ctx->stream));
+    return RIPP_OK;
+  }
+  TimeScope ts2_(ctx, RIPP_T_FINAL_EXP);
+  k_final_exp6<<<(nseg + 9) / 10, 64, 2 * 6 * FE_GROUP_WORDS * 4, ctx->stream>>>(src, T, (Fq12*)out, nseg);
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}
+
+// out[s] = final_exponentiation(prod_j in[s*T + j])
+int ripp_final_exp_l6(ripp_ctx* ctx, const void* in, uint32_t T, void* out, int nseg) {
+  CU(cudaSetDevice(ctx->device));
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
+    attr_done = true;
+  }
+  TimeScope ts_(ctx, RIPP_T_FINAL_EXP);
+  k_final_exp6<<<(nseg + 9) / 10, 64, 2 * 6 * FE_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, T, (Fq12*)out, nseg);
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}

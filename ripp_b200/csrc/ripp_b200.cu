@@ -20,7 +20,30 @@ extern "C" int ripp_ctx_create(int device, ripp_ctx** out) {
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   c->recs = new std::vector<TimingRec>();
+  CU(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
   *out = c;
+  return RIPP_OK;
+}
+
+ripp_ctx* ripp_child(ripp_ctx* ctx, int idx) {
+  if (idx < 0 || idx >= RIPP_MAX_CHILD) return nullptr;
+  if (!ctx->child[idx]) {
+    ripp_ctx* c = nullptr;
+    if (ripp_ctx_create(ctx->device, &c) != RIPP_OK) return nullptr;
+    c->parent = ctx;
+    ctx->child[idx] = c;
+  }
+  ctx->child[idx]->timing = ctx->timing;
+  return ctx->child[idx];
+}
+int ripp_fork(ripp_ctx* ctx, ripp_ctx* child) {
+  CU(cudaEventRecord(ctx->ev, ctx->stream));
+  CU(cudaStreamWaitEvent(child->stream, ctx->ev, 0));
+  return RIPP_OK;
+}
+int ripp_join(ripp_ctx* ctx, ripp_ctx* child) {
+  CU(cudaEventRecord(child->ev, child->stream));
+  CU(cudaStreamWaitEvent(ctx->stream, child->ev, 0));
   return RIPP_OK;
 }
 
@@ -28,6 +51,9 @@ extern "C" void ripp_ctx_destroy(ripp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < RIPP_MAX_CHILD; i++)
+    if (ctx->child[i]) ripp_ctx_destroy(ctx->child[i]);
+  cudaEventDestroy(ctx->ev);
   for (int i = 0; i < RIPP_SCRATCH_SLOTS; i++)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   cudaStreamDestroy(ctx->own_stream);
@@ -48,23 +74,26 @@ extern "C" int ripp_ctx_sync(ripp_ctx* ctx) {
 extern "C" void* ripp_ctx_stream(ripp_ctx* ctx) { return (void*)ctx->stream; }
 extern "C" int ripp_ctx_set_stream(ripp_ctx* ctx, void* s) {
   if (!ctx) return fail(RIPP_ERR_ARG, "null ctx");
+  CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
   return RIPP_OK;
 }
-extern "C" uint64_t ripp_ctx_launch_count(ripp_ctx* ctx) { return ctx->launches; }
+extern "C" uint64_t ripp_ctx_launch_count(ripp_ctx* ctx) {
+  uint64_t n = ctx->launches;
+  for (int i = 0; i < RIPP_MAX_CHILD; i++)
+    if (ctx->child[i]) n += ripp_ctx_launch_count(ctx->child[i]);
+  return n;
+}
 extern "C" int ripp_ctx_set_timing(ripp_ctx* ctx, int on) {
   if (!ctx) return fail(RIPP_ERR_ARG, "null ctx");
   ctx->timing = on;
   return RIPP_OK;
 }
-extern "C" int ripp_ctx_timing(ripp_ctx* ctx, double* ms_by_cat, uint64_t* count_by_cat) {
-  if (!ctx || !ms_by_cat || !count_by_cat) return fail(RIPP_ERR_ARG, "null argument");
+static int timing_collect(ripp_ctx* ctx, double* ms_by_cat, uint64_t* count_by_cat) {
   CU(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < RIPP_T_NCAT; i++) {
-    ms_by_cat[i] = 0;
-    count_by_cat[i] = 0;
-  }
+  for (int i = 0; i < RIPP_MAX_CHILD; i++)
+    if (ctx->child[i]) OK(timing_collect(ctx->child[i], ms_by_cat, count_by_cat));
   for (auto& r : *ctx->recs) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
@@ -76,6 +105,14 @@ extern "C" int ripp_ctx_timing(ripp_ctx* ctx, double* ms_by_cat, uint64_t* count
   }
   ctx->recs->clear();
   return RIPP_OK;
+}
+extern "C" int ripp_ctx_timing(ripp_ctx* ctx, double* ms_by_cat, uint64_t* count_by_cat) {
+  if (!ctx || !ms_by_cat || !count_by_cat) return fail(RIPP_ERR_ARG, "null argument");
+  for (int i = 0; i < RIPP_T_NCAT; i++) {
+    ms_by_cat[i] = 0;
+    count_by_cat[i] = 0;
+  }
+  return timing_collect(ctx, ms_by_cat, count_by_cat);
 }
 
 extern "C" int ripp_dev_alloc(ripp_ctx* ctx, size_t bytes, void** dev_out) {
@@ -397,6 +434,11 @@ extern "C" int ripp_bench_imad(ripp_ctx* ctx, int kind, int iters, double* macs_
 static const int MILLER_BLOCK = 64;
 
 static int miller_partial(ripp_ctx* ctx, const G1Aff* p, const G2Aff* q, size_t n, Fq12* out_dev) {
+  if (ripp_use_l6()) {
+    const void* g1[1] = {p};
+    const void* g2[1] = {q};
+    return ripp_pairing_batch_l6(ctx, 1, g1, g2, n, out_dev, false);
+  }
   if (n == 0) {
     Fq12 one = Fq12::one();
     CU(cudaMemcpyAsync(out_dev, &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
@@ -468,7 +510,17 @@ __global__ void k_final_exp_seg(const Fq12* __restrict__ in, uint32_t T, Fq12* _
   out[s] = final_exponentiation(f);
 }
 
+bool ripp_use_l6() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RIPP_B200_PAIRING");  // "thread" selects the one-thread-per-pair kernels (A/B runs)
+    v = (e && strcmp(e, "thread") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int ripp_pairing_batch_internal(ripp_ctx* ctx, int nseg, const void* const* g1, const void* const* g2, size_t n, void* out) {
+  if (ripp_use_l6()) return ripp_pairing_batch_l6(ctx, nseg, g1, g2, n, out, true);
   if (nseg <= 0 || nseg > RIPP_MAX_BATCH) return fail(RIPP_ERR_ARG, "bad segment count");
   CU(cudaSetDevice(ctx->device));
   if (n == 0) {
@@ -531,6 +583,7 @@ extern "C" int ripp_gt_combine_dev(ripp_ctx* ctx, const void* partials, size_t c
   if (!ctx || !out || !partials || count == 0) return fail(RIPP_ERR_ARG, "bad argument");
   CU(cudaSetDevice(ctx->device));
   void* tmp;
+  if (ripp_use_l6() && count <= 8) return ripp_final_exp_l6(ctx, partials, (uint32_t)count, out, 1);
   OK(scratch(ctx, 3, sizeof(Fq12) + 256, &tmp));
   TimeScope ts_(ctx, RIPP_T_FINAL_EXP);
   k_fq12_reduce<<<1, 32, 0, ctx->stream>>>((const Fq12*)partials, count, (int)count, (Fq12*)tmp);
@@ -545,6 +598,11 @@ extern "C" int ripp_pairing_ip_dev(ripp_ctx* ctx, const void* g1, const void* g2
   CU(cudaSetDevice(ctx->device));
   void* part;
   OK(scratch(ctx, 1, sizeof(Fq12) + 256, &part));
+  if (ripp_use_l6()) {
+    const void* a1[1] = {g1};
+    const void* a2[1] = {g2};
+    return ripp_pairing_batch_l6(ctx, 1, a1, a2, n, out, true);
+  }
   OK(miller_partial(ctx, (const G1Aff*)g1, (const G2Aff*)g2, n, (Fq12*)part));
   TimeScope ts_(ctx, RIPP_T_FINAL_EXP);
   k_final_exp<<<1, 32, 0, ctx->stream>>>((const Fq12*)part, (Fq12*)out, 1);

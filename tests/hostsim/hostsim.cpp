@@ -3,7 +3,10 @@
 // and pairing code that the kernels inline can be unit-tested against the Python oracle on a
 // CPU-only box (the carry flag is emulated, see ripp_b200/csrc/limb.cuh).  Built by tests/conftest.py.
 #define RIPP_HOSTSIM 1
-#include "../../ripp_b200/csrc/pairing.cuh"
+#include "../../ripp_b200/csrc/l6.cuh"
+#include <pthread.h>
+#include <thread>
+#include <vector>
 #include <string.h>
 using namespace ripp;
 
@@ -61,5 +64,79 @@ void hs_pairing_product(int n, const uint32_t* ps, const uint32_t* qs, uint32_t*
   Fq12 f = Fq12::one();
   for (int i = 0; i < n; i++) f = f * miller_loop(ld<G1Aff>(ps + 24 * i), ld<G2Aff>(qs + 48 * i));
   st(r, final_exponentiation(f));
+}
+}
+
+// ---- L6 (six-lane Fq12) code paths: each lane is a host thread, sync() a pthread barrier ----------
+namespace ripp { namespace l6 {
+void host_barrier(void* bar) { pthread_barrier_wait((pthread_barrier_t*)bar); }
+}}
+static inline int tower_slot(int k) { return (k & 1) * 3 + (k >> 1); }
+
+template <class Fn>
+static void run_group(Fn fn, int nreg = 8) {
+  std::vector<uint32_t> sm(l6::OFF_F + nreg * l6::F12W, 0);
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, 6);
+  std::vector<std::thread> th;
+  for (int k = 0; k < 6; k++) th.emplace_back([&, k] { l6::Ctx c{k, sm.data(), &bar}; fn(c); });
+  for (auto& t : th) t.join();
+  pthread_barrier_destroy(&bar);
+}
+static void l6_load_reg(const l6::Ctx& c, int reg, const uint32_t* fq12_tower) {
+  l6::st2(l6::freg(c, reg) + c.k * l6::FQ2W, ld<Fq2>(fq12_tower + 24 * tower_slot(c.k)));
+  l6::sync(c);
+}
+static void l6_store_reg(const l6::Ctx& c, int reg, uint32_t* fq12_tower) {
+  st<Fq2>(fq12_tower + 24 * tower_slot(c.k), l6::ld2(l6::freg(c, reg) + c.k * l6::FQ2W));
+  l6::sync(c);
+}
+extern "C" {
+// op: 0 mul, 1 sqr, 2 conj, 3 frob1, 4 frob2, 5 inv, 6 exp_by_x, 7 final_exp
+void hs_l6_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  run_group([&](const l6::Ctx& c) {
+    l6_load_reg(c, 0, a);
+    l6_load_reg(c, 1, b);
+    switch (op) {
+      case 0: l6::mul(c, 2, 0, 1); break;
+      case 1: l6::sqr(c, 2, 0); break;
+      case 2: l6::conj(c, 2, 0); break;
+      case 3: l6::frob(c, 2, 0, 1); break;
+      case 4: l6::frob(c, 2, 0, 2); break;
+      case 5: l6::inv(c, 2, 0, 3, 4, 5); break;
+      case 6: l6::exp_by_x(c, 2, 0); break;
+      case 7: l6::final_exp(c); l6::copy(c, 2, 0); break;
+    }
+    l6_store_reg(c, 2, r);
+  });
+}
+void hs_l6_mul_line(const uint32_t* f, const uint32_t* d0, const uint32_t* d1, const uint32_t* d4, uint32_t* r) {
+  run_group([&](const l6::Ctx& c) {
+    l6_load_reg(c, 0, f);
+    if (c.k == 0) {
+      l6::st2(c.sm + l6::OFF_LINE, ld<Fq2>(d0));
+      l6::st2(c.sm + l6::OFF_LINE + 24, ld<Fq2>(d1));
+      l6::st2(c.sm + l6::OFF_LINE + 48, ld<Fq2>(d4));
+    }
+    l6::sync(c);
+    l6::mul_line(c, 0, 0);
+    l6_store_reg(c, 0, r);
+  });
+}
+// Miller loop (+ optional final exponentiation) of one finite pair
+void hs_l6_miller(const uint32_t* p, const uint32_t* q, int with_final_exp, uint32_t* r) {
+  run_group([&](const l6::Ctx& c) {
+    if (c.k == 0) {
+      G1Aff P = ld<G1Aff>(p);
+      l6::st2(c.sm + l6::OFF_P, Fq2{P.x, P.y});
+      G2Aff Q = ld<G2Aff>(q);
+      l6::st2(c.sm + l6::OFF_Q, Q.x);
+      l6::st2(c.sm + l6::OFF_Q + 24, Q.y);
+    }
+    l6::sync(c);
+    l6::miller(c);
+    if (with_final_exp) l6::final_exp(c);
+    l6_store_reg(c, 0, r);
+  });
 }
 }
