@@ -180,6 +180,16 @@ int ripp_tipp_aggregate(ripp_ctx* ctx, const void* srs_g1_dev, const void* srs_g
                         const void* b_host, const void* c_host, size_t n, uint8_t* proof_out, size_t proof_cap,
                         size_t* proof_len);
 
+/* ---- SIPP (sipp/src/lib.rs; E = BLS12-381, D = Blake2s) ---------------------------------------- */
+/* product_of_pairings_with_coeffs (lib.rs:184-217): prod_i e(r_i a_i, b_i).  Affine host inputs
+ * exactly as the reference takes them (&[G1Affine], &[G2Affine], &[Fr]). */
+int ripp_sipp_product_with_coeffs(ripp_ctx* ctx, const void* a_aff, const void* b_aff, const void* r, size_t n,
+                                  void* gt_out);
+/* SIPP::prove (lib.rs:42-106).  value = the claimed product (GT, host).  proof_out receives
+ * log2(n) pairs (z_l, z_r) in serialize_uncompressed form (Proof::gt_elems, lib.rs:32-34). */
+int ripp_sipp_prove(ripp_ctx* ctx, const void* a_aff, const void* b_aff, const void* r, size_t n,
+                    const void* value_gt, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* Element-wise primitive ops on device, used by the GPU parity tests to pin the PTX limb layer:
  * op in ripp_test_op; a, b, r are HOST arrays of n elements of the op's operand size. */

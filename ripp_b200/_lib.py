@@ -267,6 +267,20 @@ class Context:
                                         ctypes.c_size_t(n), _p(proof), ctypes.c_size_t(cap), ctypes.byref(plen)))
         return proof[: plen.value].tobytes()
 
+    def sipp_product_with_coeffs(self, a, b, r):
+        out = np.empty(144, dtype=np.uint32)
+        check(lib().ripp_sipp_product_with_coeffs(self.handle, _p(a), _p(b), _p(r), ctypes.c_size_t(len(a)), _p(out)))
+        return out
+
+    def sipp_prove(self, a, b, r, value):
+        n = len(a)
+        cap = max(n.bit_length() - 1, 0) * 1152 + 16
+        proof = np.empty(cap, dtype=np.uint8)
+        plen = ctypes.c_size_t()
+        check(lib().ripp_sipp_prove(self.handle, _p(a), _p(b), _p(r), ctypes.c_size_t(n), _p(value), _p(proof),
+                                    ctypes.c_size_t(cap), ctypes.byref(plen)))
+        return proof[: plen.value].tobytes()
+
     # ---- diagnostics ----------------------------------------------------------------------
     def test_elementwise(self, op, a, b, out_words):
         a = np.ascontiguousarray(a, dtype=np.uint32)

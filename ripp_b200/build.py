@@ -42,8 +42,9 @@ def build_lib(force=False, verbose=False):
     from concurrent.futures import ThreadPoolExecutor
 
     nvcc = os.environ.get("NVCC", "nvcc")
-    flags = [f for f in NVCC_FLAGS if f != "-shared"]
-    objdir = os.path.join(CSRC, "build")
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("RIPP_B200_EXTRA_FLAGS", "").split()
+    objdir = os.path.join(CSRC, os.environ.get("RIPP_B200_OBJDIR", "build"))
+    out_lib = os.environ.get("RIPP_B200_OUT", LIB)
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):
@@ -55,10 +56,10 @@ def build_lib(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs
+    cmd = [nvcc, "-shared", "-o", out_lib] + objs
     print("[ripp_b200.build]", " ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=CSRC)
-    return LIB
+    return out_lib
 
 
 if __name__ == "__main__":

@@ -82,11 +82,11 @@ inline thread_local uint64_t mul_count_[2] = {0, 0};  // [Fr, Fq] products, test
 #endif
 
 template <class P>
-RIPP_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+RIPP_HD void mont_mul_chain(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   constexpr int N = P::N;
   constexpr int H = N / 2;
   static_assert(N % 2 == 0, "even limb count");
-#if defined(RIPP_HOSTSIM)
+#if defined(RIPP_HOSTSIM) && !defined(RIPP_FP_UNSATURATED)
   mul_count_[N == 12]++;
 #endif
   uint64_t ev[H], od[H];
@@ -118,6 +118,123 @@ RIPP_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
   for (int k = 1; k < N - 1; k++) addc_cc(r[k], e[k], o[k + 1]);
   addc(r[N - 1], e[N - 1], 0);
+  final_sub<P>(r);
+}
+
+
+// ---- carry-free product on unsaturated limbs -------------------------------------------------------
+// IMAD.WIDE.U32 with carry-in/out (the .X form the 32-bit-limb chains above compile to) issues at half
+// the rate of a plain IMAD.WIDE.U32 on sm_100 (ripp_bench_imad: 9.2 vs 17.2 TMAC/s) and serialises a
+// warp on the carry predicate.  Here the operands are re-sliced into NL = ceil(32 N / W) limbs of W = 28
+// bits so that 64-bit column accumulators absorb a whole column of the product AND of the reduction
+// (<= 2 NL products < 2^56 each) without any carry: every multiply is an independent full-rate
+// IMAD.WIDE.U32.  The Montgomery radix stays R = 2^(32 N): NL - 1 reduction rounds retire W bits each
+// and the last one the remaining 32 N - W (NL - 1) bits, so values remain bit-compatible with arkworks.
+#ifndef RIPP_LIMB_BITS
+#define RIPP_LIMB_BITS 28
+#endif
+template <class P>
+struct LimbW {
+  static constexpr int W = RIPP_LIMB_BITS;
+  static constexpr int N = P::N;
+  static constexpr int NL = (32 * N + W - 1) / W;
+  static constexpr int WL = 32 * N - W * (NL - 1);  // bits retired by the last round
+  static constexpr uint32_t MW = (1u << W) - 1;
+  // a column collects <= NL products of the multiplication and <= NL of the reduction, each < 2^(2W)
+  static constexpr bool MID_NORMALISE = (2 * W + 5) > 63 || ((uint64_t)(2 * NL) << (2 * W)) >= ((uint64_t)1 << 63);
+  RIPP_HD static uint32_t pw(int j) {  // limb j of the modulus; folds to an immediate after unrolling
+    int bit = W * j, w = bit >> 5, sh = bit & 31;
+    uint64_t v = P::p(w);
+    if (w + 1 < N) v |= (uint64_t)P::p(w + 1) << 32;
+    return (uint32_t)(v >> sh) & MW;
+  }
+  RIPP_HD static void unpack(uint32_t* L, const uint32_t* a) {
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+      int bit = W * j, w = bit >> 5, sh = bit & 31;
+      uint32_t lo = a[w], hi = (w + 1 < N) ? a[w + 1] : 0u;
+      uint32_t v = sh == 0 ? lo : ((lo >> sh) | (sh > 32 - W ? (hi << (32 - sh)) : 0u));
+      L[j] = v & MW;
+    }
+  }
+};
+
+template <class P>
+RIPP_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+#if !defined(RIPP_FP_UNSATURATED)
+  // Default: the carry-chain product.  The carry-free variant below is kept for the record: it is
+  // bit-exact (tests pass with -DRIPP_FP_UNSATURATED) but measured 1.5x SLOWER on B200 (Miller 2^16:
+  // 65.6 ms vs 40.9 ms; TIPP 2^12: 607 ms vs 401 ms, profiles/README.md): 406 full-rate IMAD.WIDE plus
+  // ~370 shift/mask/64-bit-add ALU instructions lose to 300 half-rate IMAD.WIDE.X plus ~30 -- at the
+  // occupancies these kernels run at, instruction count, not the .X issue rate, is what matters.
+  mont_mul_chain<P>(r, a, b);
+  return;
+#endif
+  using L = LimbW<P>;
+  constexpr int N = P::N, NL = L::NL, WL = L::WL, W = L::W;
+  constexpr uint32_t MW = L::MW;
+#if defined(RIPP_HOSTSIM)
+  mul_count_[N == 12]++;
+#endif
+  uint32_t A[NL], B[NL];
+  L::unpack(A, a);
+  L::unpack(B, b);
+  uint64_t acc[2 * NL + 1];
+#pragma unroll
+  for (int k = 0; k < 2 * NL + 1; k++) acc[k] = 0;
+  // schoolbook columns, no carries
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+#pragma unroll
+    for (int j = 0; j < NL; j++) acc[i + j] += (uint64_t)A[j] * B[i];
+  }
+  if (L::MID_NORMALISE) {
+#pragma unroll
+    for (int k = 0; k < 2 * NL; k++) {
+      acc[k + 1] += acc[k] >> W;
+      acc[k] &= MW;
+    }
+  }
+  // NL - 1 rounds retire W bits each
+#pragma unroll
+  for (int i = 0; i < NL - 1; i++) {
+    uint32_t m = ((uint32_t)acc[i] * P::M0) & MW;
+#pragma unroll
+    for (int j = 0; j < NL; j++) acc[i + j] += (uint64_t)m * L::pw(j);
+    acc[i + 1] += acc[i] >> W;
+  }
+  // last round retires the remaining WL bits
+  {
+    constexpr int i = NL - 1;
+    uint32_t m = ((uint32_t)acc[i] * P::M0) & ((1u << WL) - 1);
+#pragma unroll
+    for (int j = 0; j < NL; j++) acc[i + j] += (uint64_t)m * L::pw(j);
+  }
+  // value = sum_{k >= NL-1} acc[k] 2^(W (k - NL + 1)), divisible by 2^WL; normalise and repack to 32-bit words
+#pragma unroll
+  for (int k = NL - 1; k < 2 * NL; k++) {
+    acc[k + 1] += acc[k] >> W;
+    acc[k] &= MW;
+  }
+  {
+    uint64_t buf = acc[NL - 1] >> WL;  // bit buffer holding `have` valid bits
+    int have = W - WL;
+    int k = NL;
+#pragma unroll
+    for (int w = 0; w < N; w++) {
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        if (have < 32 && k <= 2 * NL) {
+          buf |= acc[k] << have;
+          have += W;
+          k++;
+        }
+      }
+      r[w] = (uint32_t)buf;
+      buf >>= 32;
+      have -= 32;
+    }
+  }
   final_sub<P>(r);
 }
 

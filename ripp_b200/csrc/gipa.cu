@@ -579,3 +579,111 @@ extern "C" int ripp_tipp_aggregate(ripp_ctx* ctx, const void* srs_g1_dev, const 
   CU(cudaMemcpyAsync(p + n * 192, b_host, n * 192, cudaMemcpyHostToDevice, ctx->stream));
   return ripp_tipp_aggregate_dev(ctx, srs_g1_dev, srs_g2_dev, p, p + n * 192, p + n * 96, n, proof_out, proof_cap, proof_len);
 }
+
+// ------------------------------------------------------------------------------------------------
+// SIPP (sipp/src/lib.rs:42-106, 184-224; FiatShamirRng sipp/src/rng.rs:12-73), D = Blake2s
+// ------------------------------------------------------------------------------------------------
+struct SippRng {
+  uint8_t seed[32];
+  void init(const Bytes& material) { ripp_hash::blake2s256(material.data(), material.size(), seed); }
+  // seed = D(new || seed); the ChaCha20 stream restarts from block 0 with the new key (rng.rs:64-72)
+  void absorb(const Bytes& fresh) {
+    Bytes b(fresh);
+    b.insert(b.end(), seed, seed + 32);
+    ripp_hash::blake2s256(b.data(), b.size(), seed);
+  }
+  // u128::rand = next_u64() | next_u64() << 64 = first 16 keystream bytes, little-endian (lib.rs:85)
+  Fr next_u128() const {
+    uint8_t ks[64];
+    ripp_hash::chacha20_block(seed, 0, ks);
+    Fr c = Fr::zero();
+    memcpy(c.v, ks, 16);
+    return c.to_mont();
+  }
+};
+
+// product_of_pairings_with_coeffs (sipp/src/lib.rs:184-217): prod e(r_i a_i, b_i); affine host inputs
+extern "C" int ripp_sipp_product_with_coeffs(ripp_ctx* ctx, const void* a_aff, const void* b_aff, const void* r, size_t n,
+                                             void* gt_out) {
+  if (!ctx || !gt_out || (n && (!a_aff || !b_aff || !r))) return fail(RIPP_ERR_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  void* d;
+  OK(scratch(ctx, 14, n * (96 + 192 + 32 + 96) + 2048, &d));
+  char* A = (char*)d;
+  char* Bp = A + n * 96;
+  char* Rp = Bp + n * 192;
+  char* AR = Rp + n * 32;
+  char* out = AR + n * 96;
+  CU(cudaMemcpyAsync(A, a_aff, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(Bp, b_aff, n * 192, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(Rp, r, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  OK(ripp_g1_scale_dev(ctx, A, Rp, n, AR));
+  OK(ripp_pairing_ip_dev(ctx, AR, Bp, n, out));
+  CU(cudaMemcpyAsync(gt_out, out, 576, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RIPP_OK;
+}
+
+// SIPP::prove.  a: n G1 affine, b: n G2 affine, r: n Fr, value: GT (all host, Montgomery limbs).
+// proof_out: log2(n) pairs (z_l, z_r), each GT serialize_uncompressed (2 * 576 B per round).
+extern "C" int ripp_sipp_prove(ripp_ctx* ctx, const void* a_aff, const void* b_aff, const void* r, size_t n,
+                               const void* value_gt, uint8_t* proof_out, size_t proof_cap, size_t* proof_len) {
+  if (!ctx || !a_aff || !b_aff || !r || !value_gt) return fail(RIPP_ERR_ARG, "null argument");
+  if (n == 0 || (n & (n - 1))) return fail(RIPP_ERR_NOT_POW2, "SIPP needs a power-of-two length");
+  CU(cudaSetDevice(ctx->device));
+  // lib.rs:56-60: rng seeded with the uncompressed serialisation of (a, b, r, value)
+  SippRng rng;
+  {
+    Bytes seed;
+    const G1Aff* a = (const G1Aff*)a_aff;
+    const G2Aff* b = (const G2Aff*)b_aff;
+    const Fr* rr = (const Fr*)r;
+    put_u64_le(seed, n);
+    for (size_t i = 0; i < n; i++) put_g1(seed, a[i]);
+    put_u64_le(seed, n);
+    for (size_t i = 0; i < n; i++) put_g2(seed, b[i]);
+    put_u64_le(seed, n);
+    for (size_t i = 0; i < n; i++) put_fr(seed, rr[i]);
+    put_gt(seed, *(const Fq12*)value_gt);
+    rng.init(seed);
+  }
+  void* d;
+  OK(scratch(ctx, 14, n * (96 + 192 + 32 + 96) + 4096, &d));
+  char* A0 = (char*)d;
+  char* Bv = A0 + n * 96;
+  char* Rp = Bv + n * 192;
+  char* Av = Rp + n * 32;
+  char* res = Av + n * 96;
+  CU(cudaMemcpyAsync(A0, a_aff, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(Bv, b_aff, n * 192, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(Rp, r, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  OK(ripp_g1_scale_dev(ctx, A0, Rp, n, Av));  // lib.rs:61-66: a_i <- a_i r_i
+  Bytes proof;
+  size_t len = n;
+  while (len != 1) {
+    len /= 2;
+    // lib.rs:77-78: z_l = prod e(a_R, b_L), z_r = prod e(a_L, b_R)
+    const void* g1[2] = {Av + len * 96, Av};
+    const void* g2[2] = {Bv, Bv + len * 192};
+    OK(ripp_pairing_batch_internal(ctx, 2, g1, g2, len, res));
+    Fq12 z[2];
+    CU(cudaMemcpyAsync(z, res, 2 * 576, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    Bytes buf;
+    put_gt(buf, z[0]);
+    put_gt(buf, z[1]);
+    proof.insert(proof.end(), buf.begin(), buf.end());
+    rng.absorb(buf);                 // lib.rs:80-84
+    Fr x = rng.next_u128();          // lib.rs:85
+    Fr x_inv = x.inv();
+    // lib.rs:87-100: a <- a_R x + a_L ; b <- b_R x^-1 + b_L   (on two streams)
+    ripp_ctx* kid = ripp_child(ctx, 0);
+    if (!kid) return fail(RIPP_ERR_CUDA, "child context");
+    OK(ripp_fork(ctx, kid));
+    OK(ripp_g1_fold_dev(ctx, Av + len * 96, Av, x.v, len, Av));
+    OK(ripp_g2_fold_dev(kid, Bv + len * 192, Bv, x_inv.v, len, Bv));
+    OK(ripp_join(ctx, kid));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return copy_out(proof, proof_out, proof_cap, proof_len);
+}

@@ -145,3 +145,17 @@ def test_aggregate_proofs_bytes_match_oracle(ctx, n):
     got = aggregate_proofs((srs.g_alpha_powers, srs.h_beta_powers), proofs, ctx)
     assert got == O.ser_aggregate_proof(want)
     assert O.verify_aggregate_proof(srs.get_verifier_key(), vk, inputs, want)
+
+
+@pytest.mark.parametrize("n", [2, 8, 32])
+def test_sipp_prove_matches_oracle(ctx, n):
+    """sipp/src/lib.rs:233-254 (n = 32 there), on BLS12-381 + Blake2s (BASELINE configs[0])."""
+    from ripp_b200.sipp import SIPP, product_of_pairings_with_coeffs
+
+    a, b, r = OS.g1_points("sipp-a", n), OS.g2_points("sipp-b", n), OS.scalars("sipp-r", n)
+    z = product_of_pairings_with_coeffs(a, b, r, ctx)
+    assert z == O.product_of_pairings_with_coeffs(a, b, r)
+    got = SIPP.prove(a, b, r, z, ctx)
+    want = O.sipp_prove(a, b, r, z)
+    assert got == O.ser_sipp_proof(want)
+    assert O.sipp_verify(a, b, r, z, want)
