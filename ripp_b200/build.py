@@ -11,9 +11,6 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    # 128 registers/thread -> 16 warps/SM: the tower lives in local memory (L1) between calls anyway,
-    # and the carry chains need >= 4 warps per scheduler to keep the IMAD pipe fed
-    "-maxrregcount=128",
     "-shared", "-Xcompiler", "-fPIC",
 ]
 

@@ -312,11 +312,13 @@ struct alignas(16) Fp {
     r.v[N - 1] >>= 1;
     return r;
   }
-  RIPP_FN Fp operator*(const Fp& b) const {
+  // one out-of-line copy of the product; operands and result travel in registers (by value)
+  static RIPP_FN Fp mul_fn(Fp a, Fp b) {
     Fp r;
-    detail::mont_mul<P>(r.v, v, b.v);
+    detail::mont_mul<P>(r.v, a.v, b.v);
     return r;
   }
+  RIPP_HD Fp operator*(const Fp& b) const { return mul_fn(*this, b); }
   RIPP_HD Fp sqr() const { return *this * *this; }
   RIPP_HD Fp& operator+=(const Fp& b) { return *this = *this + b; }
   RIPP_HD Fp& operator-=(const Fp& b) { return *this = *this - b; }

@@ -289,7 +289,7 @@ static ScalarBits scalar_bits(const void* fr_mont_host) {
 }
 
 template <class F>
-__global__ void __launch_bounds__(64, 8) k_fold(const Aff<F>* __restrict__ hi, const Aff<F>* __restrict__ lo, ScalarBits c,
+__global__ void __launch_bounds__(64, 4) k_fold(const Aff<F>* __restrict__ hi, const Aff<F>* __restrict__ lo, ScalarBits c,
                                                 size_t n, Aff<F>* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -202,7 +202,7 @@ __global__ void k_final_exp(const Fq12* __restrict__ in, Fq12* __restrict__ out,
 // kernels: element-wise scalar multiplication with distinct scalars (K8)
 // ------------------------------------------------------------------------------------------------
 template <class F, bool GEN>
-__global__ void __launch_bounds__(64, 8) k_scale(const Aff<F>* __restrict__ pts, const Fr* __restrict__ sc, size_t n,
+__global__ void __launch_bounds__(64, 4) k_scale(const Aff<F>* __restrict__ pts, const Fr* __restrict__ sc, size_t n,
                                               Aff<F>* __restrict__ out, Aff<F> gen) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -17,27 +17,30 @@ struct Fq2 {
   RIPP_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
   RIPP_HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
   RIPP_HD bool operator!=(const Fq2& b) const { return !(*this == b); }
-  RIPP_FN Fq2 operator+(const Fq2& b) const { return {c0 + b.c0, c1 + b.c1}; }
-  RIPP_FN Fq2 operator-(const Fq2& b) const { return {c0 - b.c0, c1 - b.c1}; }
-  RIPP_FN Fq2 operator-() const { return {-c0, -c1}; }
-  RIPP_FN Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+  RIPP_HD Fq2 operator+(const Fq2& b) const { return {c0 + b.c0, c1 + b.c1}; }
+  RIPP_HD Fq2 operator-(const Fq2& b) const { return {c0 - b.c0, c1 - b.c1}; }
+  RIPP_HD Fq2 operator-() const { return {-c0, -c1}; }
+  RIPP_HD Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
   RIPP_HD Fq2 conj() const { return {c0, -c1}; }
   // Karatsuba: 3 Fq products
-  RIPP_FN Fq2 operator*(const Fq2& b) const {
-    Fq t0 = c0 * b.c0;
-    Fq t1 = c1 * b.c1;
-    Fq t2 = (c0 + c1) * (b.c0 + b.c1);
+  // (operands and results of the out-of-line products travel in registers)
+  static RIPP_FN Fq2 mul_fn(Fq2 a, Fq2 b) {
+    Fq t0 = a.c0 * b.c0;
+    Fq t1 = a.c1 * b.c1;
+    Fq t2 = (a.c0 + a.c1) * (b.c0 + b.c1);
     return {t0 - t1, t2 - t0 - t1};
   }
+  RIPP_HD Fq2 operator*(const Fq2& b) const { return mul_fn(*this, b); }
   // complex squaring: 2 Fq products
-  RIPP_FN Fq2 sqr() const {
-    Fq t = c0 * c1;
-    return {(c0 + c1) * (c0 - c1), t.dbl()};
+  static RIPP_FN Fq2 sqr_fn(Fq2 a) {
+    Fq t = a.c0 * a.c1;
+    return {(a.c0 + a.c1) * (a.c0 - a.c1), t.dbl()};
   }
-  RIPP_FN Fq2 mul_fq(const Fq& s) const { return {c0 * s, c1 * s}; }
-  RIPP_FN Fq2 half() const { return {c0.half(), c1.half()}; }
+  RIPP_HD Fq2 sqr() const { return sqr_fn(*this); }
+  RIPP_HD Fq2 mul_fq(const Fq& s) const { return {c0 * s, c1 * s}; }
+  RIPP_HD Fq2 half() const { return {c0.half(), c1.half()}; }
   // times xi = 1 + u
-  RIPP_FN Fq2 mul_xi() const { return {c0 - c1, c0 + c1}; }
+  RIPP_HD Fq2 mul_xi() const { return {c0 - c1, c0 + c1}; }
   RIPP_HD Fq2 inv() const {
     Fq d = (c0.sqr() + c1.sqr()).inv();
     return {c0 * d, -(c1 * d)};
