@@ -27,7 +27,8 @@ struct Jac {
   RIPP_HD Jac neg() const { return {x, -y, z}; }
 
   // dbl-2009-l (a = 0): 2M + 5S
-  RIPP_FN Jac dbl() const {
+  RIPP_FN Jac dbl() const { return dbl_body(); }
+  RIPP_HD Jac dbl_body() const {
     F A = x.sqr(), B = y.sqr(), C = B.sqr();
     F D = ((x + B).sqr() - A - C).dbl();
     F E = A.dbl() + A;
@@ -39,7 +40,8 @@ struct Jac {
     return r;
   }
   // madd-2007-bl: 7M + 4S
-  RIPP_FN Jac add_mixed(const Aff<F>& q) const {
+  RIPP_FN Jac add_mixed(const Aff<F>& q) const { return add_mixed_body(q); }
+  RIPP_HD Jac add_mixed_body(const Aff<F>& q) const {
     if (q.is_inf()) return *this;
     if (is_inf()) return {q.x, q.y, F::one()};
     F Z1Z1 = z.sqr();
@@ -48,7 +50,7 @@ struct Jac {
     F H = U2 - x;
     F rr = S2 - y;
     if (H.is_zero()) {
-      if (rr.is_zero()) return dbl();
+      if (rr.is_zero()) return dbl_body();
       return inf();
     }
     rr = rr.dbl();
@@ -85,6 +87,10 @@ struct Jac {
     r.z = ((z + q.z).sqr() - Z1Z1 - Z2Z2) * H;
     return r;
   }
+  // register-resident variants: operands and result by value, so a running accumulator never
+  // round-trips through local memory between iterations
+  static RIPP_FN Jac dbl_fn(Jac a) { return a.dbl_body(); }
+  static RIPP_FN Jac add_mixed_fn(Jac a, Aff<F> q) { return a.add_mixed_body(q); }
   // affine coordinates given zinv = 1/z (caller handles infinity)
   RIPP_HD Aff<F> to_affine_with(const F& zinv) const {
     F zi2 = zinv.sqr();

@@ -17,6 +17,17 @@
 
 typedef std::vector<uint8_t> Bytes;
 
+// RIPP_B200_TRACE=1: host wall-clock phase trace on stderr (development aid)
+#include <chrono>
+static bool trace_on() {
+  static int v = -1;
+  if (v < 0) v = getenv("RIPP_B200_TRACE") ? 1 : 0;
+  return v == 1;
+}
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side serialisation (ark-serialize 0.4 uncompressed)
 // ------------------------------------------------------------------------------------------------
@@ -247,7 +258,9 @@ static int gipa_prove(ripp_ctx* ctx, const GipaSpec& sp, const void* a_in, const
     Slice ys[6] = {at(sp.v, V, 0), at(sp.b, B, 0), at(sp.b, B, 0), at(sp.v, V, split), at(sp.b, B, split), at(sp.b, B, split)};
     if (sp.w == VT_NONE) xs[1].t = xs[4].t = VT_NONE;
     std::vector<Val> com(6);
+    double t_r0 = now_ms();
     OK(eval_products(ctx, 6, xs, ys, split, com.data()));
+    if (trace_on()) fprintf(stderr, "[trace] gipa(a=%d,b=%d) n'=%zu products+prev folds %.2f ms\n", sp.a, sp.b, split, now_ms() - t_r0);
     // gipa.rs:235-258 -- Fiat-Shamir challenge
     Fr c, c_inv;
     for (uint64_t nonce = 0;; nonce++) {
@@ -416,7 +429,9 @@ static int tipa_prove(ripp_ctx* ctx, int kind, const void* srs_g1, const void* s
   if (!gipa_spec(kind, &sp)) return fail(RIPP_ERR_ARG, "bad GIPA kind");
   if (sp.v != VT_G2 || (sp.w != VT_G1 && sp.w != VT_NONE)) return fail(RIPP_ERR_ARG, "TIPA needs keys in (G2, G1)");
   GipaOut g;
+  double t_g0 = now_ms();
   OK(gipa_prove(ctx, sp, a, b, v, w, n, &g));
+  double t_g1 = now_ms();
   size_t n_srs = 2 * n - 1;
   std::vector<Fr> tinv(g.transcript.size());
   for (size_t i = 0; i < tinv.size(); i++) tinv[i] = g.transcript[i].inv();
@@ -440,6 +455,7 @@ static int tipa_prove(ripp_ctx* ctx, int kind, const void* srs_g1, const void* s
   } else {
     put_g2(*proof, open_a);
   }
+  if (trace_on()) fprintf(stderr, "[trace] tipa kind=%d: gipa %.2f ms, kzg openings %.2f ms\n", kind, t_g1 - t_g0, now_ms() - t_g1);
   return RIPP_OK;
 }
 
@@ -493,6 +509,7 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
   OK(scratch(ctx, 13, o_res + 8 * 576, &ws));
   char* W = (char*)ws;
   unsigned nb = (unsigned)((n + 127) / 128);
+  double t_a0 = now_ms();
   // :98 commitment keys = even SRS powers (tipa/mod.rs:114-118)
   k_gather_stride2<G2Aff><<<nb, 128, 0, st>>>((const G2Aff*)srs_g2_dev, n, (G2Aff*)(W + o_ck1));
   LAUNCHED(ctx);
@@ -533,6 +550,7 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
   OK(ripp_msm_g1_dev(ctx, c_dev, W + o_pw, n, W + o_res));
   CU(cudaMemcpyAsync(agg_c.raw, W + o_res, 96, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (trace_on()) fprintf(stderr, "[trace] aggregate prologue (3 commitments, r, scalings, ip_ab, agg_c) %.2f ms\n", now_ms() - t_a0);
   // :138-149 the two TIPA proofs
   // ... which are independent: run them from two host threads on two child contexts so their
   // (latency-bound) rounds overlap on the GPU

@@ -237,12 +237,43 @@ RIPP_HD void inv(const Ctx& c, int dst, int a, int t0, int t1, int t2) {
   mul(c, dst, t0, t2);
 }
 
+// dst = a^2 for a in the cyclotomic subgroup (Granger-Scott): ONE Fq2 product per lane.
+// In the flat basis the three Fq4 pairs are (a0, a3), (a1, a4), (a2, a5); lane k < 3 forms a_k a_{k+3},
+// lane k >= 3 forms (a_{k-3} + a_k)(a_{k-3} + xi a_k), and with
+//   t_even(pair) = (ra + rb)(ra + xi rb) - (1 + xi) ra rb,  t_odd(pair) = 2 ra rb
+// the outputs are  a0' = 3 t_even(A) - 2 a0,  a3' = 3 t_odd(A) + 2 a3,  a1' = 3 xi t_odd(C) + 2 a1,
+// a4' = 3 t_even(C) - 2 a4,  a2' = 3 t_even(B) - 2 a2,  a5' = 3 t_odd(B) + 2 a5   (A, B, C = pairs 0, 1, 2).
+RIPP_HD void cyc_sqr(const Ctx& c, int dst, int a) {
+  const uint32_t* A = freg(c, a);
+  uint32_t* R = c.sm + OFF_R;
+  const int k = c.k, pr = k % 3;
+  Fq2 ra = ld2(A + pr * FQ2W), rb = ld2(A + (pr + 3) * FQ2W);
+  Fq2 u = f2sel(k < 3, ra, f2add(ra, rb));
+  Fq2 v = f2sel(k < 3, rb, f2add(ra, f2xi(rb)));
+  Fq2 own = ld2(A + k * FQ2W);
+  st2(R + k * FQ2W, f2mul(u, v));
+  sync(c);
+  // source pair of this lane's output: a0,a3 <- A(0); a2,a5 <- B(1); a1,a4 <- C(2)
+  const int src = (k % 3 == 0) ? 0 : (k % 3 == 2 ? 1 : 2);
+  Fq2 prod = ld2(R + src * FQ2W), cross = ld2(R + (src + 3) * FQ2W);
+  Fq2 t_even = f2sub(cross, f2add(prod, f2xi(prod)));
+  Fq2 t_odd = f2dbl(prod);
+  // k = 0, 2, 4 take 3 t_even - 2 own; k = 3, 5 take 3 t_odd + 2 own; k = 1 takes 3 xi t_odd + 2 own
+  Fq2 t = f2sel(k == 0 || k == 2 || k == 4, t_even, f2sel(k == 1, f2xi(t_odd), t_odd));
+  Fq2 s2 = f2dbl(own);
+  Fq2 three_t = f2add(f2dbl(t), t);
+  Fq2 out = f2sel(k == 0 || k == 2 || k == 4, f2sub(three_t, s2), f2add(three_t, s2));
+  sync(c);
+  st2(freg(c, dst) + k * FQ2W, out);
+  sync(c);
+}
+
 // a^x (x = -|x|) for a in the cyclotomic subgroup; dst != a; clobbers nothing else
 RIPP_HD void exp_by_x(const Ctx& c, int dst, int a) {
   copy(c, dst, a);
 #pragma unroll 1
   for (int i = 62; i >= 0; i--) {
-    sqr(c, dst, dst);
+    cyc_sqr(c, dst, dst);
     if ((k::X_ABS >> i) & 1) mul(c, dst, dst, a);
   }
   conj(c, dst, dst);
@@ -256,7 +287,7 @@ RIPP_HD void final_exp(const Ctx& c) {
   mul(c, R, Y0, R);           // f^(p^6 - 1)
   frob(c, Y0, R, 2);
   mul(c, R, Y0, R);           // ^(p^2 + 1)
-  sqr(c, Y0, R);              // y0 = r^2
+  cyc_sqr(c, Y0, R);          // y0 = r^2
   exp_by_x(c, Y1, R);         // y1 = r^x
   conj(c, Y2, R);
   mul(c, Y1, Y1, Y2);

@@ -21,14 +21,16 @@ static MsmPlan msm_plan(size_t n) {
   int lg = 0;
   while (((size_t)2 << lg) <= n) lg++;
   MsmPlan p;
-  p.c = lg - 2;
+  // ~32 points per bucket: long enough that the Poisson spread of bucket sizes does not idle most of a
+  // warp (at 4 per bucket a warp runs at max/mean ~ 2.5x), short enough for the small MSMs of late rounds
+  p.c = lg - 5;
   if (p.c < 4) p.c = 4;
-  if (p.c > 16) p.c = 16;
+  if (p.c > 14) p.c = 14;
   p.nw = (255 + p.c - 1) / p.c;
   p.B = 1u << p.c;
-  p.L = p.B / 256;
+  p.L = p.B / 256;  // short chunks: the running-sum chains are latency, not throughput
   if (p.L < 2) p.L = 2;
-  if (p.L > 32) p.L = 32;
+  if (p.L > 8) p.L = 8;
   p.T = p.B / p.L;
   return p;
 }
@@ -55,9 +57,23 @@ __global__ void k_msm_prepare(const Fr* __restrict__ sc, size_t n, Fr* __restric
   }
 }
 
+// Buckets with more than MSM_FAT points (the top window of any 255-bit scalar set is always skewed:
+// it has few significant bits, hence few, huge buckets) are split into chunks of MSM_FAT_CHUNK points
+// summed by whole blocks; everything else is one thread per bucket.
+#define MSM_FAT 96u
+#define MSM_FAT_CHUNK 2048u
+struct FatItem {
+  uint32_t bucket;  // w * B + digit
+  uint32_t chunk;   // chunk index within the bucket
+};
+struct FatBucket {
+  uint32_t bucket, first_item, nchunks;
+};
+
 // exclusive scan of counts within each window (one block per window) -> offsets into idx[w*n ..]
 __global__ void k_msm_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                           uint32_t* __restrict__ cursor, uint32_t B, size_t n) {
+                           uint32_t* __restrict__ cursor, uint32_t B, size_t n, uint32_t* __restrict__ fat_counters,
+                           FatItem* __restrict__ items, FatBucket* __restrict__ fats, uint32_t max_items) {
   __shared__ uint32_t part[256];
   int w = blockIdx.x;
   uint32_t per = (B + 255) / 256;
@@ -77,9 +93,19 @@ __global__ void k_msm_scan(const uint32_t* __restrict__ counts, uint32_t* __rest
   __syncthreads();
   uint32_t run = part[threadIdx.x] + (uint32_t)((size_t)w * n);
   for (uint32_t j = lo; j < hi; j++) {
+    uint32_t cnt = counts[(size_t)w * B + j];
     offsets[(size_t)w * B + j] = run;
     cursor[(size_t)w * B + j] = run;
-    run += counts[(size_t)w * B + j];
+    run += cnt;
+    if (cnt > MSM_FAT) {
+      uint32_t nch = (cnt + MSM_FAT_CHUNK - 1) / MSM_FAT_CHUNK;
+      uint32_t first = atomicAdd(&fat_counters[0], nch);
+      uint32_t fb = atomicAdd(&fat_counters[1], 1u);
+      if (first + nch <= max_items) {
+        fats[fb] = FatBucket{(uint32_t)((size_t)w * B + j), first, nch};
+        for (uint32_t k = 0; k < nch; k++) items[first + k] = FatItem{(uint32_t)((size_t)w * B + j), k};
+      }
+    }
   }
 }
 
@@ -104,9 +130,47 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const Aff<F>* __restrict
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   uint32_t start = offsets[t], cnt = counts[t];
+  if (cnt > MSM_FAT) return;  // summed by k_msm_fat_*
   Jac<F> acc = Jac<F>::inf();
   for (uint32_t j = 0; j < cnt; j++) acc = acc.add_mixed(bases[idx[start + j]]);
   buckets[t] = acc;
+}
+
+// one block per (fat bucket, chunk): strided partial sums, then a shared-memory tree
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_fat_chunks(const Aff<F>* __restrict__ bases, const uint32_t* __restrict__ idx,
+                                                        const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ counts,
+                                                        const uint32_t* __restrict__ fat_counters,
+                                                        const FatItem* __restrict__ items, Jac<F>* __restrict__ partials) {
+  __shared__ Jac<F> sh[128];
+  for (uint32_t it = blockIdx.x; it < fat_counters[0]; it += gridDim.x) {
+    FatItem w = items[it];
+    uint32_t start = offsets[w.bucket] + w.chunk * MSM_FAT_CHUNK;
+    uint32_t end = offsets[w.bucket] + counts[w.bucket];
+    if (end > start + MSM_FAT_CHUNK) end = start + MSM_FAT_CHUNK;
+    Jac<F> acc = Jac<F>::inf();
+    for (uint32_t j = start + threadIdx.x; j < end; j += 128) acc = acc.add_mixed(bases[idx[j]]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 64; s >= 1; s >>= 1) {
+      if ((int)threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + s]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[it] = sh[0];
+    __syncthreads();
+  }
+}
+// one thread per fat bucket: sum of its chunk partials
+template <class F>
+__global__ void k_msm_fat_combine(const uint32_t* __restrict__ fat_counters, const FatBucket* __restrict__ fats,
+                                  const Jac<F>* __restrict__ partials, Jac<F>* __restrict__ buckets) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= fat_counters[1]) return;
+  FatBucket fb = fats[t];
+  Jac<F> acc = partials[fb.first_item];
+  for (uint32_t k = 1; k < fb.nchunks; k++) acc = acc.add(partials[fb.first_item + k]);
+  buckets[fb.bucket] = acc;
 }
 
 // one thread per (window, chunk of L buckets): sum_b b * bucket[b] restricted to the chunk
@@ -178,16 +242,34 @@ static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, A
   uint32_t* offsets = counts + WB;
   uint32_t* cursor = offsets + WB;
   cudaStream_t st = ctx->stream;
+  // fat-bucket bookkeeping: at most nw*n/MSM_FAT fat buckets, nw*(n/CHUNK + n/FAT) chunk items
+  uint32_t max_fat = (uint32_t)((size_t)p.nw * n / MSM_FAT + p.nw + 1);
+  uint32_t max_items = (uint32_t)((size_t)p.nw * n / MSM_FAT_CHUNK + max_fat + 1);
+  void* fatbuf;
+  OK(scratch(ctx, 15, 64 + (size_t)max_items * (sizeof(FatItem) + sizeof(Jac<F>)) + (size_t)max_fat * sizeof(FatBucket) + 1024, &fatbuf));
+  uint32_t* fat_counters = (uint32_t*)fatbuf;
+  Jac<F>* fat_partials = (Jac<F>*)((char*)fatbuf + 64);
+  FatItem* fat_items = (FatItem*)(fat_partials + max_items);
+  FatBucket* fat_buckets = (FatBucket*)(fat_items + max_items);
+  CU(cudaMemsetAsync(fat_counters, 0, 64, st));
   CU(cudaMemsetAsync(counts, 0, WB * sizeof(uint32_t), st));
   k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, n, (Fr*)canon, counts, p.c, p.nw);
   LAUNCHED(ctx);
-  k_msm_scan<<<p.nw, 256, 0, st>>>(counts, offsets, cursor, p.B, n);
+  k_msm_scan<<<p.nw, 256, 0, st>>>(counts, offsets, cursor, p.B, n, fat_counters, fat_items, fat_buckets, max_items);
   LAUNCHED(ctx);
   k_msm_scatter<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const Fr*)canon, n, cursor, (uint32_t*)idx, p.c, p.nw);
   LAUNCHED(ctx);
   k_msm_accumulate<F><<<(unsigned)((WB + 127) / 128), 128, 0, st>>>(bases, (const uint32_t*)idx, offsets, counts,
                                                                    (Jac<F>*)bkt, WB);
   LAUNCHED(ctx);
+  {
+    unsigned fat_grid = max_items < 1184u ? max_items : 1184u;  // grid-stride over the item list; 8 blocks per SM
+    k_msm_fat_chunks<F><<<fat_grid, 128, 0, st>>>(bases, (const uint32_t*)idx, offsets, counts, fat_counters, fat_items,
+                                                  fat_partials);
+    LAUNCHED(ctx);
+    k_msm_fat_combine<F><<<(max_fat + 63) / 64, 64, 0, st>>>(fat_counters, fat_buckets, fat_partials, (Jac<F>*)bkt);
+    LAUNCHED(ctx);
+  }
   size_t WT = (size_t)p.nw * p.T;
   Jac<F>* pa = (Jac<F>*)parts;
   Jac<F>* pb = pa + WT;

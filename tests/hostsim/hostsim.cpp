@@ -106,6 +106,7 @@ void hs_l6_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
       case 5: l6::inv(c, 2, 0, 3, 4, 5); break;
       case 6: l6::exp_by_x(c, 2, 0); break;
       case 7: l6::final_exp(c); l6::copy(c, 2, 0); break;
+      case 8: l6::cyc_sqr(c, 2, 0); break;
     }
     l6_store_reg(c, 2, r);
   });

@@ -125,3 +125,33 @@ def test_op_counts(hostsim):
 
     assert miller == bench.FQ_MUL_PER_MILLER_PAIR
     assert fexp == bench.FQ_MUL_PER_FINAL_EXP
+
+
+def test_l6_six_lane_fq12(hostsim):
+    """The six-lane Fq12 engine (l6.cuh), each lane a host thread, against the oracle."""
+    a, b = rf12(), rf12()
+    ea, eb = C.gt_enc(a), C.gt_enc(b)
+    op = lambda code, x, y: C.gt_dec(hostsim.call("hs_l6_op", code, x, y, out=144))
+    assert op(0, ea, eb) == E.f12_mul(a, b)
+    assert op(1, ea, eb) == E.f12_sqr(a)
+    assert op(2, ea, eb) == E.f12_conj(a)
+    assert op(3, ea, eb) == E.f12_frob(a, 1)
+    assert op(4, ea, eb) == E.f12_frob(a, 2)
+    assert op(5, ea, eb) == E.f12_inv(a)
+    d0, d1, d4 = rf2(), rf2(), rf2()
+    got = hostsim.call("hs_l6_mul_line", ea, C.fq2_enc(d0), C.fq2_enc(d1), C.fq2_enc(d4), out=144)
+    assert C.gt_dec(got) == E.f12_mul(a, (d0, (0, 0), d1, d4, (0, 0), (0, 0)))
+    c = E.f12_mul(E.f12_conj(a), E.f12_inv(a))
+    c = E.f12_mul(E.f12_frob(c, 2), c)
+    ec = C.gt_enc(c)
+    assert op(8, ec, ec) == E.f12_sqr(c)  # Granger-Scott squaring in the flat basis
+    assert op(6, ec, ec) == E.f12_cyc_pow(c, E.X)
+
+
+def test_l6_miller_and_final_exp(hostsim):
+    p, q = E.g1_mul(E.G1_GEN, 123), E.g2_mul(E.G2_GEN, 456)
+    f = E.miller_loop(p, q)
+    ef = C.gt_enc(f)
+    assert C.gt_dec(hostsim.call("hs_l6_op", 7, ef, ef, out=144)) == E.final_exponentiation(f)
+    got = hostsim.call("hs_l6_miller", C.g1_enc(p), C.g2_enc(q), 1, out=144)
+    assert C.gt_dec(got) == E.pairing(p, q)
