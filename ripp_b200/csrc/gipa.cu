@@ -166,23 +166,25 @@ static int eval_products(ripp_ctx* ctx, int k, const Slice* xs, const Slice* ys,
   // children see the state the caller queued on ctx's stream (previous folds) before they start
   for (int j = 0; j < 6; j++)
     if (ctx->child[j]) OK(ripp_fork(ctx, ctx->child[j]));
-  if (np) OK(ripp_pairing_batch_internal(ctx, np, g1, g2, n, r));
-  for (int j = 0; j < np; j++)
-    CU(cudaMemcpyAsync(out[pair_slot[j]].raw, r + 576 * j, 576, cudaMemcpyDeviceToHost, ctx->stream));
-  // MSM-type products run on child streams, overlapping each other and the pairing batch
+  // MSM-type products go to child streams FIRST, then the pairing batch on ctx's stream; result copies
+  // (which block the host on pageable memory) only after everything has been queued, so the launches overlap
   ripp_ctx* kids[8];
+  int kid_of[8];
   int nk = 0;
   for (int i = 0; i < k; i++) {
     int a = xs[i].t, b = ys[i].t;
+    kid_of[i] = -1;
     if (out[i].t == VT_GT || a == VT_NONE || b == VT_NONE) continue;
     char* dst = r + 8 * 576 + 576 * i;
     if (a == VT_FR && b == VT_FR) {
       OK(ripp_scalar_ip_dev(ctx, xs[i].p, ys[i].p, n, dst));
-      CU(cudaMemcpyAsync(out[i].raw, dst, 32, cudaMemcpyDeviceToHost, ctx->stream));
       continue;
     }
     ripp_ctx* kid = ripp_child(ctx, nk % 6);
     if (!kid) return fail(RIPP_ERR_CUDA, "child context");
+    if (nk >= 6) return fail(RIPP_ERR_ARG, "too many MSM-type products in one batch");
+    OK(ripp_fork(ctx, kid));
+    kid_of[i] = nk;
     kids[nk++] = kid;
     const char* pts = a == VT_FR ? ys[i].p : xs[i].p;
     const char* sc = a == VT_FR ? xs[i].p : ys[i].p;
@@ -190,8 +192,17 @@ static int eval_products(ripp_ctx* ctx, int k, const Slice* xs, const Slice* ys,
       OK(ripp_msm_g1_dev(kid, pts, sc, n, dst));
     else
       OK(ripp_msm_g2_dev(kid, pts, sc, n, dst));
-    CU(cudaMemcpyAsync(out[i].raw, dst, vt_size(out[i].t), cudaMemcpyDeviceToHost, kid->stream));
   }
+  if (np) OK(ripp_pairing_batch_internal(ctx, np, g1, g2, n, r));
+  for (int i = 0; i < k; i++) {
+    int a = xs[i].t, b = ys[i].t;
+    if (out[i].t == VT_GT || a == VT_NONE || b == VT_NONE) continue;
+    char* dst = r + 8 * 576 + 576 * i;
+    cudaStream_t st = kid_of[i] >= 0 ? kids[kid_of[i]]->stream : ctx->stream;
+    CU(cudaMemcpyAsync(out[i].raw, dst, vt_size(out[i].t), cudaMemcpyDeviceToHost, st));
+  }
+  for (int j = 0; j < np; j++)
+    CU(cudaMemcpyAsync(out[pair_slot[j]].raw, r + 576 * j, 576, cudaMemcpyDeviceToHost, ctx->stream));
   for (int j = 0; j < nk; j++) CU(cudaStreamSynchronize(kids[j]->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return RIPP_OK;
@@ -444,11 +455,25 @@ static int tipa_prove(ripp_ctx* ctx, int kind, const void* srs_g1, const void* s
   G2Aff open_a;
   G1Aff open_b;
   Fr shift_a = sp.w != VT_NONE ? r_shift.inv() : Fr::one();  // SSM variant opens with shift 1
-  OK(kzg_open<Fq2>(ctx, srs_g2, n_srs, tinv, shift_a, c, &open_a));
+  int st_b = RIPP_OK;
+  std::string err_b;
+  std::thread tb;
+  if (sp.w != VT_NONE) {  // the G1 opening runs on a child context from a second host thread
+    ripp_ctx* kid = ripp_child(ctx, 5);
+    if (!kid) return fail(RIPP_ERR_CUDA, "child context");
+    OK(ripp_fork(ctx, kid));
+    tb = std::thread([&, kid] {
+      st_b = kzg_open<Fq>(kid, srs_g1, n_srs, g.transcript, Fr::one(), c, &open_b);
+      if (st_b != RIPP_OK) err_b = ripp_err_slot();
+    });
+  }
+  int st_a = kzg_open<Fq2>(ctx, srs_g2, n_srs, tinv, shift_a, c, &open_a);
+  if (tb.joinable()) tb.join();
+  if (st_a != RIPP_OK) return st_a;
+  if (st_b != RIPP_OK) return fail(st_b, err_b);
   *proof = g.proof;
   put_val(*proof, g.v0);
   if (sp.w != VT_NONE) {
-    OK(kzg_open<Fq>(ctx, srs_g1, n_srs, g.transcript, Fr::one(), c, &open_b));
     put_val(*proof, g.w0);
     put_g2(*proof, open_a);
     put_g1(*proof, open_b);
@@ -532,8 +557,17 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
   // :118-131 r_vec, a_r = a * r^i, ck_1_r = ck_1 * r^-i
   k_fr_powers<<<nb, 128, 0, st>>>(r, n, (Fr*)(W + o_pw), (Fr*)(W + o_pwi), r_inv);
   LAUNCHED(ctx);
+  ripp_ctx* pk = ripp_child(ctx, 5);
+  if (!pk) return fail(RIPP_ERR_CUDA, "child context");
+  OK(ripp_fork(ctx, pk));
+  OK(ripp_g2_scale_dev(pk, ck1, W + o_pwi, n, W + o_ck1r));   // the long one (G2, 255-bit) on its own stream
   OK(ripp_g1_scale_dev(ctx, a_dev, W + o_pw, n, W + o_ar));
-  OK(ripp_g2_scale_dev(ctx, ck1, W + o_pwi, n, W + o_ck1r));
+  // :125 agg_c = MSM(c, r_vec) needs only r_vec: queue it behind the G1 scaling on a third stream
+  ripp_ctx* mk = ripp_child(ctx, 4);
+  if (!mk) return fail(RIPP_ERR_CUDA, "child context");
+  OK(ripp_fork(ctx, mk));
+  OK(ripp_msm_g1_dev(mk, c_dev, W + o_pw, n, W + o_res));
+  OK(ripp_join(ctx, pk));
   // :124 ip_ab = IP(a_r, b); :133-136 sanity com_a == IP(a_r, ck_1_r)
   Val ipv[2];
   {
@@ -547,7 +581,7 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
   Val agg_c;
   agg_c.t = VT_G1;
   memset(agg_c.raw, 0, 576);
-  OK(ripp_msm_g1_dev(ctx, c_dev, W + o_pw, n, W + o_res));
+  OK(ripp_join(ctx, mk));
   CU(cudaMemcpyAsync(agg_c.raw, W + o_res, 96, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (trace_on()) fprintf(stderr, "[trace] aggregate prologue (3 commitments, r, scalings, ip_ab, agg_c) %.2f ms\n", now_ms() - t_a0);
