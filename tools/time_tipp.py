@@ -11,3 +11,7 @@ for i in range(reps):
     l0 = ctx.launches; t0 = time.time()
     proof = ctx.tipp_aggregate_dev(inst["srs_g1"], inst["srs_g2"], inst["a"], inst["b"], inst["c"], n)
     print("aggregate n=%d: %.1f ms, %d launches, %d proof bytes" % (n, 1e3 * (time.time() - t0), ctx.launches - l0, len(proof)))
+ctx.set_timing(True); ctx.timing()
+proof = ctx.tipp_aggregate_dev(inst["srs_g1"], inst["srs_g2"], inst["a"], inst["b"], inst["c"], n)
+tm = ctx.timing()
+print({k: (round(v[0], 2), v[1], round(v[0] / max(v[1], 1), 2)) for k, v in tm.items()})
