@@ -21,14 +21,16 @@ namespace l6 {
 // ---- group scratch layout (32-bit words) ---------------------------------------------------------
 constexpr int FQ2W = 24;
 constexpr int F12W = 6 * FQ2W;
-constexpr int OFF_T = 0;                  // running point T: x, y, z
-constexpr int OFF_R = OFF_T + 3 * FQ2W;   // round results R0..R5
+constexpr int OFF_R = 0;                  // round results R0..R5
 constexpr int OFF_LINE = OFF_R + F12W;    // line coefficients d0, d1, d4
-constexpr int OFF_P = OFF_LINE + 3 * FQ2W;  // xP, yP (Fq each)
-constexpr int OFF_Q = OFF_P + FQ2W;       // xQ, yQ
-constexpr int OFF_F = OFF_Q + 2 * FQ2W;   // Fq12 registers F0..F(NREG-1)
-constexpr int NREG = 5;
-constexpr int GROUP_WORDS = OFF_F + NREG * F12W;  // 1104 words = 4416 B
+constexpr int OFF_F = OFF_LINE + 3 * FQ2W;  // Fq12 registers F0..F(nreg-1), then the per-pair blocks
+// per-pair block (a group can walk several pairs that share one accumulator, ark-ec's multi_miller_loop shape)
+constexpr int PB_T = 0;                   // running point T: x, y, z
+constexpr int PB_P = PB_T + 3 * FQ2W;     // xP, yP (Fq each)
+constexpr int PB_Q = PB_P + FQ2W;         // xQ, yQ
+constexpr int PB_VALID = PB_Q + 2 * FQ2W; // 1 = finite pair, 0 = contributes the constant line 1
+constexpr int PAIR_WORDS = PB_VALID + 8;
+RIPP_HD constexpr int group_words(int nreg, int npairs) { return OFF_F + nreg * F12W + npairs * PAIR_WORDS; }
 
 struct Ctx {
   int k;          // lane within the group, 0..5
@@ -310,8 +312,8 @@ RIPP_HD void final_exp(const Ctx& c) {
 // ---- Miller loop --------------------------------------------------------------------------------
 // smem: T = (x, y, z) at OFF_T, P = (xP, yP) at OFF_P, Q = (xQ, yQ) at OFF_Q, accumulator in register 0.
 // One doubling step: two rounds of at most six parallel Fq2 products.
-RIPP_HD void dbl_step(const Ctx& c) {
-  uint32_t* T = c.sm + OFF_T;
+RIPP_HD void dbl_step(const Ctx& c, uint32_t* pb) {
+  uint32_t* T = pb + PB_T;
   uint32_t* R = c.sm + OFF_R;
   const int k = c.k;
   Fq2 x = ld2(T), y = ld2(T + FQ2W), z = ld2(T + 2 * FQ2W);
@@ -329,7 +331,8 @@ RIPP_HD void dbl_step(const Ctx& c) {
   Fq2 j3 = f2add(f2dbl(j), j);
   sync(c);
   // round 2: R0 = a (b - f), R1 = g^2, R2 = b h, R3 = e^2, R4 = 3j * xP, R5 = -h * yP
-  Fq xp = ld2(c.sm + OFF_P).c0, yp = ld2(c.sm + OFF_P).c1;
+  Fq xp = ld2(pb + PB_P).c0, yp = ld2(pb + PB_P).c1;
+  const bool valid = pb[PB_VALID] != 0;
   Fq2 sxp = {xp, Fq::zero()}, syp = {yp, Fq::zero()};
   u = f2sel(k == 0, a, f2sel(k == 1, g, f2sel(k == 2, b, f2sel(k == 3, e, f2sel(k == 4, j3, f2neg(h))))));
   v = f2sel(k == 0, f2sub(b, f), f2sel(k == 1, g, f2sel(k == 2, h, f2sel(k == 3, e, f2sel(k == 4, sxp, syp)))));
@@ -345,21 +348,21 @@ RIPP_HD void dbl_step(const Ctx& c) {
     st2(T + FQ2W, ny);
     st2(T + 2 * FQ2W, nz);
   }
-  if (k == 1) {
-    st2(c.sm + OFF_LINE, f2sub(e, b));
-    st2(c.sm + OFF_LINE + FQ2W, d1);
-    st2(c.sm + OFF_LINE + 2 * FQ2W, d4);
+  if (k == 1) {  // masked pairs multiply the accumulator by the constant line 1
+    st2(c.sm + OFF_LINE, f2sel(valid, f2sub(e, b), Fq2::one()));
+    st2(c.sm + OFF_LINE + FQ2W, f2sel(valid, d1, Fq2::zero()));
+    st2(c.sm + OFF_LINE + 2 * FQ2W, f2sel(valid, d4, Fq2::zero()));
   }
   sync(c);
 }
 
 // One addition step T <- T + Q with the chord line.
-RIPP_HD void add_step(const Ctx& c) {
-  uint32_t* T = c.sm + OFF_T;
+RIPP_HD void add_step(const Ctx& c, uint32_t* pb) {
+  uint32_t* T = pb + PB_T;
   uint32_t* R = c.sm + OFF_R;
   const int k = c.k;
   Fq2 x = ld2(T), y = ld2(T + FQ2W), z = ld2(T + 2 * FQ2W);
-  Fq2 qx = ld2(c.sm + OFF_Q), qy = ld2(c.sm + OFF_Q + FQ2W);
+  Fq2 qx = ld2(pb + PB_Q), qy = ld2(pb + PB_Q + FQ2W);
   // round 1: R0 = qy z, R1 = qx z
   st2(R + k * FQ2W, f2mul(f2sel(k == 0, qy, qx), z));
   sync(c);
@@ -381,7 +384,8 @@ RIPP_HD void add_step(const Ctx& c) {
   Fq2 h = f2sub(f2add(e, f), f2dbl(g));
   sync(c);
   // round 4: R0 = lambda h, R1 = theta (g - h), R2 = e y, R3 = z e, R4 = -theta xP, R5 = lambda yP
-  Fq xp = ld2(c.sm + OFF_P).c0, yp = ld2(c.sm + OFF_P).c1;
+  Fq xp = ld2(pb + PB_P).c0, yp = ld2(pb + PB_P).c1;
+  const bool valid = pb[PB_VALID] != 0;
   Fq2 sxp = {xp, Fq::zero()}, syp = {yp, Fq::zero()};
   u = f2sel(k == 0, lambda, f2sel(k == 1, theta, f2sel(k == 2, e, f2sel(k == 3, z, f2sel(k == 4, f2neg(theta), lambda)))));
   v = f2sel(k == 0, h, f2sel(k == 1, f2sub(g, h), f2sel(k == 2, y, f2sel(k == 3, e, f2sel(k == 4, sxp, syp)))));
@@ -396,30 +400,40 @@ RIPP_HD void add_step(const Ctx& c) {
     st2(T + 2 * FQ2W, nz);
   }
   if (k == 1) {
-    st2(c.sm + OFF_LINE, jv);
-    st2(c.sm + OFF_LINE + FQ2W, d1);
-    st2(c.sm + OFF_LINE + 2 * FQ2W, d4);
+    st2(c.sm + OFF_LINE, f2sel(valid, jv, Fq2::one()));
+    st2(c.sm + OFF_LINE + FQ2W, f2sel(valid, d1, Fq2::zero()));
+    st2(c.sm + OFF_LINE + 2 * FQ2W, f2sel(valid, d4, Fq2::zero()));
   }
   sync(c);
 }
 
-// Register 0 <- f_{|x|,Q}(P) conjugated.  P, Q must be loaded at OFF_P / OFF_Q (finite points).
-RIPP_HD void miller(const Ctx& c) {
-  uint32_t* T = c.sm + OFF_T;
+// Register 0 <- prod_j f_{|x|,Q_j}(P_j), conjugated, over the npairs pair blocks at `pairs` (P, Q and the
+// valid flag staged by the caller; masked pairs must still hold finite points).  One accumulator squaring per
+// bit is shared by all the group's pairs.
+RIPP_HD void miller(const Ctx& c, uint32_t* pairs, int npairs) {
   if (c.k == 0) {
-    st2(T, ld2(c.sm + OFF_Q));
-    st2(T + FQ2W, ld2(c.sm + OFF_Q + FQ2W));
-    st2(T + 2 * FQ2W, Fq2::one());
+    for (int j = 0; j < npairs; j++) {
+      uint32_t* pb = pairs + j * PAIR_WORDS;
+      st2(pb + PB_T, ld2(pb + PB_Q));
+      st2(pb + PB_T + FQ2W, ld2(pb + PB_Q + FQ2W));
+      st2(pb + PB_T + 2 * FQ2W, Fq2::one());
+    }
   }
   set_one(c, 0);
 #pragma unroll 1
   for (int i = 62; i >= 0; i--) {
     sqr(c, 0, 0);
-    dbl_step(c);
-    mul_line(c, 0, 0);
-    if ((k::X_ABS >> i) & 1) {
-      add_step(c);
+#pragma unroll 1
+    for (int j = 0; j < npairs; j++) {
+      dbl_step(c, pairs + j * PAIR_WORDS);
       mul_line(c, 0, 0);
+    }
+    if ((k::X_ABS >> i) & 1) {
+#pragma unroll 1
+      for (int j = 0; j < npairs; j++) {
+        add_step(c, pairs + j * PAIR_WORDS);
+        mul_line(c, 0, 0);
+      }
     }
   }
   conj(c, 0, 0);

@@ -12,57 +12,55 @@ static __device__ __forceinline__ int tower_slot(int k) { return (k & 1) * 3 + (
 struct Miller6Batch {
   const G1Aff* p[RIPP_MAX_BATCH];
   const G2Aff* q[RIPP_MAX_BATCH];
-  uint32_t n, wps;  // pairs per segment, warps per segment (5 pairs per warp)
+  uint32_t n, wps;  // pairs per segment, warps per segment (5 * KP pairs per warp)
   int nseg;
 };
 
 constexpr int M6_NREG = 2;
-constexpr int M6_GROUP_WORDS = OFF_F + M6_NREG * F12W;
-constexpr int M6_WARP_WORDS = 6 * M6_GROUP_WORDS;  // five groups + one junk slot for lanes 30, 31
+constexpr int M6_WARPS = 4;
 
-template <int WARPS>
+// KP pairs per six-lane group share one accumulator (one Fq12 squaring per bit instead of KP):
+// KP = 1 minimises latency (late GIPA rounds), KP = 4 maximises throughput (long vectors).
+template <int WARPS, int KP>
 __global__ void __launch_bounds__(32 * WARPS) k_miller6(Miller6Batch b, Fq12* __restrict__ partials) {
   extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int GW = group_words(M6_NREG, KP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / 6;
-  uint32_t* wsm = smem + warp * M6_WARP_WORDS;
-  Ctx c{lane % 6, wsm + g * M6_GROUP_WORDS};
+  uint32_t* wsm = smem + warp * 6 * GW;  // five groups + one junk slot for lanes 30, 31
+  Ctx c{lane % 6, wsm + g * GW};
+  uint32_t* pairs = c.sm + OFF_F + M6_NREG * F12W;
   const uint32_t gw = blockIdx.x * WARPS + warp;
   const uint32_t seg = gw / b.wps, wl = gw % b.wps;
-  const uint32_t i = wl * 5 + g;
-  // lane 0 of each real group stages its pair; identities / padding run on the generators and are masked
-  int valid = 0;
+  // lane 0 of each group stages its pairs; identities / padding run on the generators and are masked
   if (c.k == 0) {
-    G1Aff P = g1_generator();
-    G2Aff Q = g2_generator();
-    if (g < 5 && seg < (uint32_t)b.nseg && i < b.n) {
-      G1Aff p = b.p[seg][i];
-      G2Aff q = b.q[seg][i];
-      if (!p.is_inf() && !q.is_inf()) {
-        P = p;
-        Q = q;
-        valid = 1;
+    for (int j = 0; j < KP; j++) {
+      const uint32_t i = (wl * 5 + g) * KP + j;
+      G1Aff P = g1_generator();
+      G2Aff Q = g2_generator();
+      uint32_t valid = 0;
+      if (g < 5 && seg < (uint32_t)b.nseg && i < b.n) {
+        G1Aff p = b.p[seg][i];
+        G2Aff q = b.q[seg][i];
+        if (!p.is_inf() && !q.is_inf()) {
+          P = p;
+          Q = q;
+          valid = 1;
+        }
       }
+      uint32_t* pb = pairs + j * PAIR_WORDS;
+      st2(pb + PB_P, Fq2{P.x, P.y});
+      st2(pb + PB_Q, Q.x);
+      st2(pb + PB_Q + FQ2W, Q.y);
+      pb[PB_VALID] = valid;
     }
-    st2(c.sm + OFF_P, Fq2{P.x, P.y});
-    st2(c.sm + OFF_Q, Q.x);
-    st2(c.sm + OFF_Q + FQ2W, Q.y);
   }
-  valid = __shfl_sync(0xffffffffu, valid, (g * 6) & 31);
   __syncwarp();
-  miller(c);
-  // masked groups contribute 1
-  {
-    Fq2 v = ld2(freg(c, 0) + c.k * FQ2W);
-    v = f2sel(valid, v, f2sel(c.k == 0, Fq2::one(), Fq2::zero()));
-    __syncwarp();
-    st2(freg(c, 0) + c.k * FQ2W, v);
-    __syncwarp();
-  }
+  miller(c, pairs, KP);
   // product of the five groups' values: (0 <- 0*1, 2 <- 2*3), 0 <- 0*2, 0 <- 0*4; idle groups write their junk register
   uint32_t* F0 = freg(c, 0);
   uint32_t* J = freg(c, 1);
-  auto other = [&](int gg) { return wsm + gg * M6_GROUP_WORDS + OFF_F; };
+  auto other = [&](int gg) { return wsm + gg * GW + OFF_F; };
   mul_p(c, (g == 0 || g == 2) ? F0 : J, F0, other(g == 0 ? 1 : (g == 2 ? 3 : g)));
   mul_p(c, g == 0 ? F0 : J, F0, other(g == 0 ? 2 : g));
   mul_p(c, g == 0 ? F0 : J, F0, other(g == 0 ? 4 : g));
@@ -73,7 +71,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_miller6(Miller6Batch b, Fq12* __
 }
 
 // out[s][j] = prod in[s][j*R .. min(T, j*R+R)) ; one group per output, five groups per warp
-constexpr int R6_GROUP_WORDS = OFF_F + 2 * F12W;
+constexpr int R6_GROUP_WORDS = group_words(2, 0);
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS) k_reduce6(const Fq12* __restrict__ in, uint32_t T, uint32_t R, uint32_t To,
                                                        Fq12* __restrict__ out, uint32_t total) {
@@ -100,7 +98,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_reduce6(const Fq12* __restrict__
 
 // out[s] = final_exponentiation(prod_j in[s][j]), j < T (T <= 8); one group per value
 constexpr int FE_NREG = 9;
-constexpr int FE_GROUP_WORDS = OFF_F + FE_NREG * F12W;
+constexpr int FE_GROUP_WORDS = group_words(FE_NREG, 0);
 __global__ void __launch_bounds__(64) k_final_exp6(const Fq12* __restrict__ in, uint32_t T, Fq12* __restrict__ out, int nseg) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -120,7 +118,23 @@ __global__ void __launch_bounds__(64) k_final_exp6(const Fq12* __restrict__ in, 
   if (live) reinterpret_cast<Fq2*>(out + s)[tower_slot(c.k)] = ld2(freg(c, 0) + c.k * FQ2W);
 }
 
-static const int M6_WARPS = 4;
+
+template <int KP>
+static int launch_miller6(ripp_ctx* ctx, Miller6Batch& b, size_t n, Fq12* dst, size_t* nwarps_out) {
+  constexpr int SM = M6_WARPS * 6 * group_words(M6_NREG, KP) * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
+    attr_done = true;
+  }
+  b.wps = (uint32_t)((n + 5 * KP - 1) / (5 * KP));
+  size_t nwarps = (size_t)b.wps * b.nseg;
+  unsigned blocks = (unsigned)((nwarps + M6_WARPS - 1) / M6_WARPS);
+  k_miller6<M6_WARPS, KP><<<blocks, 32 * M6_WARPS, SM, ctx->stream>>>(b, dst);
+  LAUNCHED(ctx);
+  *nwarps_out = nwarps;
+  return RIPP_OK;
+}
 
 int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const void* const* g2, size_t n, void* out,
                           bool with_final_exp) {
@@ -128,7 +142,6 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
   CU(cudaSetDevice(ctx->device));
   static bool attr_done = false;
   if (!attr_done) {
-    CU(cudaFuncSetAttribute(k_miller6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * M6_WARP_WORDS * 4));
     CU(cudaFuncSetAttribute(k_reduce6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * R6_GROUP_WORDS * 4));
     CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
     attr_done = true;
@@ -143,23 +156,30 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
   Miller6Batch b;
   b.nseg = nseg;
   b.n = (uint32_t)n;
-  b.wps = (uint32_t)((n + 4) / 5);
   for (int s = 0; s < nseg; s++) {
     b.p[s] = (const G1Aff*)g1[s];
     b.q[s] = (const G2Aff*)g2[s];
   }
-  size_t nwarps = (size_t)b.wps * nseg;
+  // pairs per group: the largest of {4, 2, 1} that still leaves ~one wave of groups (148 SMs x 8 warps x 5)
+  size_t total = (size_t)nseg * n;
+  int kp = total >= 4 * 5920 ? 4 : (total >= 2 * 5920 ? 2 : 1);
+  size_t max_warps = (size_t)nseg * ((n + 4) / 5);
   void *bufA, *bufB;
-  OK(scratch(ctx, 2, nwarps * sizeof(Fq12) + 4096, &bufA));
-  OK(scratch(ctx, 3, nwarps * sizeof(Fq12) / 4 + 8192, &bufB));
-  uint32_t T = b.wps;
+  OK(scratch(ctx, 2, max_warps * sizeof(Fq12) + 4096, &bufA));
+  OK(scratch(ctx, 3, max_warps * sizeof(Fq12) / 4 + 8192, &bufB));
   const uint32_t R = 8;
   Fq12 *src = (Fq12*)bufA, *dst = (Fq12*)bufB;
+  size_t nwarps = 0;
+  uint32_t T;
   {
     TimeScope ts_(ctx, RIPP_T_MILLER);
-    unsigned blocks = (unsigned)((nwarps + M6_WARPS - 1) / M6_WARPS);
-    k_miller6<M6_WARPS><<<blocks, 32 * M6_WARPS, M6_WARPS * M6_WARP_WORDS * 4, ctx->stream>>>(b, src);
-    LAUNCHED(ctx);
+    if (kp == 4)
+      OK(launch_miller6<4>(ctx, b, n, src, &nwarps));
+    else if (kp == 2)
+      OK(launch_miller6<2>(ctx, b, n, src, &nwarps));
+    else
+      OK(launch_miller6<1>(ctx, b, n, src, &nwarps));
+    T = b.wps;
     uint32_t stop = with_final_exp ? R : 1;
     while (T > stop) {
       uint32_t To = (T + R - 1) / R;

@@ -75,7 +75,7 @@ static inline int tower_slot(int k) { return (k & 1) * 3 + (k >> 1); }
 
 template <class Fn>
 static void run_group(Fn fn, int nreg = 8) {
-  std::vector<uint32_t> sm(l6::OFF_F + nreg * l6::F12W, 0);
+  std::vector<uint32_t> sm(l6::group_words(nreg, 4), 0);
   pthread_barrier_t bar;
   pthread_barrier_init(&bar, nullptr, 6);
   std::vector<std::thread> th;
@@ -124,18 +124,23 @@ void hs_l6_mul_line(const uint32_t* f, const uint32_t* d0, const uint32_t* d1, c
     l6_store_reg(c, 0, r);
   });
 }
-// Miller loop (+ optional final exponentiation) of one finite pair
-void hs_l6_miller(const uint32_t* p, const uint32_t* q, int with_final_exp, uint32_t* r) {
+// Miller loop (+ optional final exponentiation) over npairs pairs sharing one accumulator; valid[j] = 0 masks a pair
+void hs_l6_miller(const uint32_t* p, const uint32_t* q, const int* valid, int npairs, int with_final_exp, uint32_t* r) {
   run_group([&](const l6::Ctx& c) {
+    uint32_t* pairs = c.sm + l6::OFF_F + 8 * l6::F12W;
     if (c.k == 0) {
-      G1Aff P = ld<G1Aff>(p);
-      l6::st2(c.sm + l6::OFF_P, Fq2{P.x, P.y});
-      G2Aff Q = ld<G2Aff>(q);
-      l6::st2(c.sm + l6::OFF_Q, Q.x);
-      l6::st2(c.sm + l6::OFF_Q + 24, Q.y);
+      for (int j = 0; j < npairs; j++) {
+        uint32_t* pb = pairs + j * l6::PAIR_WORDS;
+        G1Aff P = ld<G1Aff>(p + 24 * j);
+        G2Aff Q = ld<G2Aff>(q + 48 * j);
+        l6::st2(pb + l6::PB_P, Fq2{P.x, P.y});
+        l6::st2(pb + l6::PB_Q, Q.x);
+        l6::st2(pb + l6::PB_Q + 24, Q.y);
+        pb[l6::PB_VALID] = valid[j];
+      }
     }
     l6::sync(c);
-    l6::miller(c);
+    l6::miller(c, pairs, npairs);
     if (with_final_exp) l6::final_exp(c);
     l6_store_reg(c, 0, r);
   });

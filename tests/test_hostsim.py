@@ -153,5 +153,14 @@ def test_l6_miller_and_final_exp(hostsim):
     f = E.miller_loop(p, q)
     ef = C.gt_enc(f)
     assert C.gt_dec(hostsim.call("hs_l6_op", 7, ef, ef, out=144)) == E.final_exponentiation(f)
-    got = hostsim.call("hs_l6_miller", C.g1_enc(p), C.g2_enc(q), 1, out=144)
+    import numpy as np
+
+    one = np.array([1], dtype=np.int32)
+    got = hostsim.call("hs_l6_miller", C.g1_enc(p), C.g2_enc(q), one.view(np.uint32), 1, 1, out=144)
     assert C.gt_dec(got) == E.pairing(p, q)
+    # three pairs sharing one accumulator, the middle one masked (contributes 1)
+    ps = [E.g1_mul(E.G1_GEN, s) for s in (5, 6, 7)]
+    qs = [E.g2_mul(E.G2_GEN, s) for s in (8, 9, 10)]
+    valid = np.array([1, 0, 1], dtype=np.int32)
+    got = hostsim.call("hs_l6_miller", C.g1_vec_enc(ps), C.g2_vec_enc(qs), valid.view(np.uint32), 3, 1, out=144)
+    assert C.gt_dec(got) == E.multi_pairing([ps[0], ps[2]], [qs[0], qs[2]])
