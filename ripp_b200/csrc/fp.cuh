@@ -63,18 +63,118 @@ RIPP_HD void mont_row(uint64_t* X, uint64_t* Y, const uint32_t* a, uint32_t bi) 
   addc_hi(Y[H - 1]);
 }
 
-// Add m*p with m chosen so the lowest limb of X cancels.
-template <class P>
+// Add m*p with m chosen so the lowest limb of X cancels.  CIN: the carry flag left by a preceding
+// add_lo_hi_cc (fold of the retired pair's high limb into X's lowest limb) enters the offset chain, whose
+// lowest position is exactly one limb above the fold.
+template <class P, bool CIN = false>
 RIPP_HD void mont_redc(uint64_t* X, uint64_t* Y) {
   constexpr int H = P::N / 2;
   uint32_t m = mul_lo((uint32_t)X[0], P::M0);
-  mw_cc(Y[0], P::p(1), m, Y[0]);
+  if (CIN)
+    mwc_cc(Y[0], P::p(1), m, Y[0]);
+  else
+    mw_cc(Y[0], P::p(1), m, Y[0]);
 #pragma unroll
   for (int k = 1; k < H; k++) mwc_cc(Y[k], P::p(2 * k + 1), m, Y[k]);
   mw_cc(X[0], P::p(0), m, X[0]);
 #pragma unroll
   for (int k = 1; k < H; k++) mwc_cc(X[k], P::p(2 * k), m, X[k]);
   addc_hi(Y[H - 1]);
+}
+
+// ---- lazy (unreduced) arithmetic for sums of products -----------------------------------------------
+// wide_mul: t[0..2N) = a * b over the integers (operands any N-limb values), same even/odd carry chains as
+// the Montgomery product minus the reduction rows.  redc_wide: T (2N limbs, T < 2^(32 N) * k p) -> T / R mod p,
+// fully reduced with up to `subs` conditional subtractions.  Summing several products before one reduction is
+// what makes schoolbook Fq12 arithmetic over six lanes as cheap as the Karatsuba tower (l6.cuh).
+template <class P>
+RIPP_HD void wide_mul(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = P::N;
+  constexpr int H = N / 2;
+  uint64_t ev[H], od[H];
+#pragma unroll
+  for (int k = 0; k < H; k++) {
+    ev[k] = mul_wide(a[2 * k], b[0]);
+    od[k] = mul_wide(a[2 * k + 1], b[0]);
+  }
+  t[0] = (uint32_t)ev[0];
+#pragma unroll
+  for (int i = 1; i < N; i += 2) {
+    mont_row<P>(od, ev, a, b[i]);
+    t[i] = (uint32_t)od[0];
+    if (i + 1 < N) {
+      mont_row<P>(ev, od, a, b[i + 1]);
+      t[i + 1] = (uint32_t)ev[0];
+    }
+  }
+  // window now starts at limb N-1 with od aligned (its lowest limb already emitted): t[N + k] = ev[k] + od[k+1]
+  uint32_t e[N], o[N];
+#pragma unroll
+  for (int k = 0; k < H; k++) {
+    e[2 * k] = (uint32_t)ev[k];
+    e[2 * k + 1] = (uint32_t)(ev[k] >> 32);
+    o[2 * k] = (uint32_t)od[k];
+    o[2 * k + 1] = (uint32_t)(od[k] >> 32);
+  }
+  add_cc(t[N], e[0], o[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) addc_cc(t[N + k], e[k], o[k + 1]);
+  addc(t[2 * N - 1], e[N - 1], 0);
+}
+template <int NW>
+RIPP_HD void wide_add(uint32_t* acc, const uint32_t* t) {
+  add_cc(acc[0], acc[0], t[0]);
+#pragma unroll
+  for (int k = 1; k < NW - 1; k++) addc_cc(acc[k], acc[k], t[k]);
+  addc(acc[NW - 1], acc[NW - 1], t[NW - 1]);
+}
+template <int NW>
+RIPP_HD void wide_sub(uint32_t* acc, const uint32_t* t) {
+  sub_cc(acc[0], acc[0], t[0]);
+#pragma unroll
+  for (int k = 1; k < NW - 1; k++) subc_cc(acc[k], acc[k], t[k]);
+  subc(acc[NW - 1], acc[NW - 1], t[NW - 1]);
+}
+template <class P>
+RIPP_HD void redc_wide(uint32_t* r, const uint32_t* t, int subs) {
+  constexpr int N = P::N;
+  constexpr int H = N / 2;
+  uint64_t X[H], Y[H];
+#pragma unroll
+  for (int k = 0; k < H; k++) {
+    X[k] = (uint64_t)t[2 * k] | ((uint64_t)t[2 * k + 1] << 32);
+    Y[k] = 0;
+  }
+  // N rounds: add m p so the lowest limb cancels, slide the window by one limb, inject the next high limb.
+  // (A aligned, B offset); after a round the roles swap.  The carry of the fold rides into the next round.
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint64_t* A = (i & 1) ? Y : X;
+    uint64_t* B = (i & 1) ? X : Y;
+    if (i == 0)
+      mont_redc<P, false>(A, B);
+    else
+      mont_redc<P, true>(A, B);
+    uint64_t a0 = A[0];
+#pragma unroll
+    for (int k = 0; k < H - 1; k++) A[k] = A[k + 1];
+    A[H - 1] = (uint64_t)t[N + i];
+    add_lo_hi_cc(B[0], a0);  // B.limb0 += a0.limb1, carry pending for the next chain
+  }
+  // N even: X aligned again; value = X + (Y << 32) + (pending carry << 32)
+  uint32_t e[N], o[N];
+#pragma unroll
+  for (int k = 0; k < H; k++) {
+    e[2 * k] = (uint32_t)X[k];
+    e[2 * k + 1] = (uint32_t)(X[k] >> 32);
+    o[2 * k] = (uint32_t)Y[k];
+    o[2 * k + 1] = (uint32_t)(Y[k] >> 32);
+  }
+  r[0] = e[0];
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) addc_cc(r[k], e[k], o[k - 1]);
+  addc(r[N - 1], e[N - 1], o[N - 2]);
+  for (int s2 = 0; s2 < subs; s2++) final_sub<P>(r);
 }
 
 #if defined(RIPP_HOSTSIM)

@@ -66,6 +66,45 @@ RIPP_HD Fq2 f2mul(const Fq2& a, const Fq2& b) {
   Fq t2 = fqmul(a.c0 + a.c1, b.c0 + b.c1);
   return {t0 - t1, t2 - t0 - t1};
 }
+// ---- lazy Fq2 multiply-accumulate: sum_i a_i b_i with ONE Montgomery reduction per output limb vector ----
+// Karatsuba in the wide (768-bit) domain: S0 += a0 b0, S1 += a1 b1, K += (a0 + a1)(b0 + b1); then
+// c0 = REDC(S0) - REDC(S1), c1 = REDC(K - S0 - S1).  Operand components must be < p; up to six products.
+struct Acc3 {
+  uint32_t s0[24], s1[24], k[24];
+};
+RIPP_HD void acc_zero(Acc3& A) {
+#pragma unroll
+  for (int i = 0; i < 24; i++) A.s0[i] = A.s1[i] = A.k[i] = 0;
+}
+RIPP_HD void f2_mac(Acc3& A, const Fq2& a, const Fq2& b) {
+  using namespace limb;
+  uint32_t t[24];
+  detail::wide_mul<FqParams>(t, a.c0.v, b.c0.v);
+  detail::wide_add<24>(A.s0, t);
+  detail::wide_mul<FqParams>(t, a.c1.v, b.c1.v);
+  detail::wide_add<24>(A.s1, t);
+  uint32_t sa[12], sb[12];  // unreduced sums (< 2p < 2^382)
+  add_cc(sa[0], a.c0.v[0], a.c1.v[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) addc_cc(sa[i], a.c0.v[i], a.c1.v[i]);
+  addc(sa[11], a.c0.v[11], a.c1.v[11]);
+  add_cc(sb[0], b.c0.v[0], b.c1.v[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) addc_cc(sb[i], b.c0.v[i], b.c1.v[i]);
+  addc(sb[11], b.c0.v[11], b.c1.v[11]);
+  detail::wide_mul<FqParams>(t, sa, sb);
+  detail::wide_add<24>(A.k, t);
+}
+RIPP_HD Fq2 f2_finish(Acc3& A) {
+  detail::wide_sub<24>(A.k, A.s0);
+  detail::wide_sub<24>(A.k, A.s1);
+  Fq r0, r1, c1;
+  detail::redc_wide<FqParams>(r0.v, A.s0, 1);  // < 6 p^2 / R + p < 1.7 p
+  detail::redc_wide<FqParams>(r1.v, A.s1, 1);
+  detail::redc_wide<FqParams>(c1.v, A.k, 2);   // < 12 p^2 / R + p < 2.3 p
+  return {r0 - r1, c1};
+}
+
 RIPP_HD Fq2 f2sel(bool c, const Fq2& a, const Fq2& b) {  // c ? a : b, branch-free
   Fq2 r;
 #pragma unroll
@@ -120,23 +159,26 @@ RIPP_HD void mul_p(const Ctx& c, uint32_t* D, const uint32_t* A, const uint32_t*
 // dst = a * b;  dst may alias a or b
 RIPP_HD void mul(const Ctx& c, int dst, int a, int b) { mul_p(c, freg(c, dst), freg(c, a), freg(c, b)); }
 RIPP_HD void mul_p(const Ctx& c, uint32_t* D, const uint32_t* A, const uint32_t* B) {
-  Fq2 acc = Fq2::zero();
+  Acc3 acc;
+  acc_zero(acc);
 #pragma unroll 1
   for (int i = 0; i < 6; i++) {
     int j = c.k - i;
     bool wrap = j < 0;
     j += wrap ? 6 : 0;
-    Fq2 t = f2mul(ld2(A + i * FQ2W), ld2(B + j * FQ2W));
-    acc = f2add(acc, f2sel(wrap, f2xi(t), t));
+    Fq2 b = ld2(B + j * FQ2W);
+    f2_mac(acc, ld2(A + i * FQ2W), f2sel(wrap, f2xi(b), b));  // xi applied to the operand: stays linear
   }
+  Fq2 out = f2_finish(acc);
   sync(c);
-  st2(D + c.k * FQ2W, acc);
+  st2(D + c.k * FQ2W, out);
   sync(c);
 }
 // dst = a^2: 21 distinct products over six lanes (cross terms doubled)
 RIPP_HD void sqr(const Ctx& c, int dst, int a) {
   const uint32_t* A = freg(c, a);
-  Fq2 acc = Fq2::zero();
+  Acc3 acc;
+  acc_zero(acc);
   // pairs (i, j), i <= j, i + j = k or k + 6:  i runs over 0..3 slots; slots beyond the lane's count are masked
 #pragma unroll 1
   for (int s = 0; s < 4; s++) {
@@ -157,13 +199,14 @@ RIPP_HD void sqr(const Ctx& c, int dst, int a) {
       found = found || take;
     }
     Fq2 x = ld2(A + ii * FQ2W), y = ld2(A + jj * FQ2W);
-    Fq2 t = f2mul(x, y);
-    t = f2sel(ii != jj, f2dbl(t), t);
-    t = f2sel(wrap, f2xi(t), t);
-    acc = f2sel(found, f2add(acc, t), acc);
+    y = f2sel(ii != jj, f2dbl(y), y);
+    y = f2sel(wrap, f2xi(y), y);
+    x = f2sel(found, x, Fq2::zero());  // lanes with only three terms add 0 in the fourth slot
+    f2_mac(acc, x, y);
   }
+  Fq2 out = f2_finish(acc);
   sync(c);
-  st2(freg(c, dst) + c.k * FQ2W, acc);
+  st2(freg(c, dst) + c.k * FQ2W, out);
   sync(c);
 }
 // dst = a * (d0 + d1 w^2 + d4 w^3), line coefficients at OFF_LINE (the ark-ec `mul_by_014` shape)
@@ -175,13 +218,16 @@ RIPP_HD void mul_line(const Ctx& c, int dst, int a) {
   bool w2 = k2 < 0, w3 = k3 < 0;
   k2 += w2 ? 6 : 0;
   k3 += w3 ? 6 : 0;
-  Fq2 acc = f2mul(ld2(A + k * FQ2W), ld2(L));
-  Fq2 t = f2mul(ld2(A + k2 * FQ2W), ld2(L + FQ2W));
-  acc = f2add(acc, f2sel(w2, f2xi(t), t));
-  t = f2mul(ld2(A + k3 * FQ2W), ld2(L + 2 * FQ2W));
-  acc = f2add(acc, f2sel(w3, f2xi(t), t));
+  Acc3 acc;
+  acc_zero(acc);
+  f2_mac(acc, ld2(A + k * FQ2W), ld2(L));
+  Fq2 d = ld2(L + FQ2W);
+  f2_mac(acc, ld2(A + k2 * FQ2W), f2sel(w2, f2xi(d), d));
+  d = ld2(L + 2 * FQ2W);
+  f2_mac(acc, ld2(A + k3 * FQ2W), f2sel(w3, f2xi(d), d));
+  Fq2 out = f2_finish(acc);
   sync(c);
-  st2(freg(c, dst) + k * FQ2W, acc);
+  st2(freg(c, dst) + k * FQ2W, out);
   sync(c);
 }
 // dst = conj(a)  (w -> -w)

@@ -55,6 +55,15 @@ void hs_g2_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { st(r, G2Jac:
 void hs_g2_add_mixed(const uint32_t* a, const uint32_t* b, uint32_t* r) { st(r, G2Jac::from_affine(ld<G2Aff>(a)).add_mixed(ld<G2Aff>(b)).to_affine()); }
 void hs_g2_dbl(const uint32_t* a, const uint32_t*, uint32_t* r) { st(r, G2Jac::from_affine(ld<G2Aff>(a)).dbl().to_affine()); }
 void hs_g2_mul(const uint32_t* a, const uint32_t* bits, int nbits, uint32_t* r) { st(r, scalar_mul(ld<G2Aff>(a), bits, nbits).to_affine()); }
+// lazy arithmetic: r = REDC(sum_i a_i * b_i) for k products
+void hs_fq_dot_redc(const uint32_t* a, const uint32_t* b, int k, int subs, uint32_t* r) {
+  uint32_t acc[24] = {0}, t[24];
+  for (int i = 0; i < k; i++) {
+    detail::wide_mul<FqParams>(t, a + 12 * i, b + 12 * i);
+    detail::wide_add<24>(acc, t);
+  }
+  detail::redc_wide<FqParams>(r, acc, subs);
+}
 uint64_t hs_mul_count(int which) { return detail::mul_count_[which]; }
 void hs_mul_count_reset() { detail::mul_count_[0] = detail::mul_count_[1] = 0; }
 void hs_g1_gen(uint32_t* r) { st(r, g1_generator()); }
