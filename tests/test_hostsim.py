@@ -164,3 +164,20 @@ def test_l6_miller_and_final_exp(hostsim):
     valid = np.array([1, 0, 1], dtype=np.int32)
     got = hostsim.call("hs_l6_miller", C.g1_vec_enc(ps), C.g2_vec_enc(qs), valid.view(np.uint32), 3, 1, out=144)
     assert C.gt_dec(got) == E.multi_pairing([ps[0], ps[2]], [qs[0], qs[2]])
+
+
+def test_lazy_sum_of_products(hostsim):
+    """wide_mul / redc_wide (fp.cuh): REDC(sum_i a_i b_i) for up to 12 products incl. the extreme operands."""
+    import ctypes
+
+    import numpy as np
+
+    rinv = pow(1 << 384, -1, E.P)
+    for k in (1, 2, 6, 12):
+        for it in range(40):
+            a = [E.P - 1 if it == 0 else rnd.randrange(E.P) for _ in range(k)]
+            b = [E.P - 1 if it == 0 else rnd.randrange(E.P) for _ in range(k)]
+            A = np.concatenate([C._words(x, 12) for x in a])
+            B = np.concatenate([C._words(x, 12) for x in b])
+            got = hostsim.call("hs_fq_dot_redc", A, B, k, 3, out=12)
+            assert C._int(got) == sum(x * y for x, y in zip(a, b)) * rinv % E.P
