@@ -5,6 +5,7 @@
 // opening MSMs (tipa/mod.rs:333-334), and the "rescale" maps of GIPA/SIPP (gipa.rs:261-291,
 // sipp/src/lib.rs:87-100; scalar-mul primitive `mul_helper`, ip_proofs/src/lib.rs:15-19).
 #include "common.cuh"
+#include "x3.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // MSM
@@ -222,6 +223,34 @@ __global__ void k_msm_horner(const Jac<F>* __restrict__ sums, int nw, int c, Aff
   *out = acc.to_affine();
 }
 
+static bool use_x3() {
+  static int v = -1;
+  if (v < 0) {
+    // "x3" selects the three-lanes-per-point kernels (x3.cuh).  Bit-exact, but measured NOT faster on B200
+    // (TIPP 2^12: 199.5 ms vs 184.5 ms; element-wise scaling 2x slower): shuffles, selects and spills eat the
+    // shorter multiplication chain.  One thread per element stays the default.
+    const char* e = getenv("RIPP_B200_FOLD");
+    v = (e && strcmp(e, "x3") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// Horner tail on one three-lane group
+template <class XF>
+__global__ void k_msm_horner_x3(const Jac<XF>* __restrict__ sums, int nw, int c, Aff<XF>* __restrict__ out) {
+  if (threadIdx.x >= 3) return;
+  Jac<XF> acc = sums[nw - 1];
+  for (int w = nw - 2; w >= 0; w--) {
+    for (int j = 0; j < c; j++) acc = x3::Ops<XF>::dbl(acc);
+    acc = acc.add(sums[w]);
+  }
+  Aff<XF> o = acc.to_affine();
+  if (threadIdx.x == 0) *out = o;
+}
+template <class F> struct X3Of;
+template <> struct X3Of<Fq> { typedef Fq type; };
+template <> struct X3Of<Fq2> { typedef x3::Fq2x3 type; };
+
 template <class F>
 static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, Aff<F>* out) {
   CU(cudaSetDevice(ctx->device));
@@ -287,7 +316,12 @@ static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, A
     pb = t;
     T = To;
   }
-  k_msm_horner<F><<<1, 32, 0, st>>>(pa, p.nw, p.c, out);
+  if (use_x3()) {
+    typedef typename X3Of<F>::type XF;
+    k_msm_horner_x3<XF><<<1, 32, 0, st>>>((const Jac<XF>*)pa, p.nw, p.c, (Aff<XF>*)out);
+  } else {
+    k_msm_horner<F><<<1, 32, 0, st>>>(pa, p.nw, p.c, out);
+  }
   LAUNCHED(ctx);
   return RIPP_OK;
 }
@@ -407,22 +441,42 @@ __global__ void __launch_bounds__(64, 4) k_fold(const Aff<F>* __restrict__ hi, c
   out[i] = acc.to_affine();
 }
 
-template <class F>
+// three lanes per element (x3.cuh): XF = Fq for G1, x3::Fq2x3 for G2 (same memory layout as Fq / Fq2)
+template <class XF>
+__global__ void __launch_bounds__(128) k_fold_x3(const Aff<XF>* __restrict__ hi, const Aff<XF>* __restrict__ lo, ScalarBits c,
+                                                 size_t n, Aff<XF>* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  if (lane >= 30) return;
+  size_t i = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 10 + lane / 3;
+  if (i >= n) return;
+  Jac<XF> acc = x3::mul_naf<XF>(hi[i], c.pos, c.neg, c.nbits);
+  acc = x3::Ops<XF>::madd(acc, lo[i]);
+  Aff<XF> o = acc.to_affine();
+  if (lane % 3 == 0) out[i] = o;
+}
+
+template <class F, class XF>
 static int fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c, size_t n, void* out) {
   if (!ctx || !c || (n && (!hi || !lo || !out))) return fail(RIPP_ERR_ARG, "null argument");
   if (n == 0) return RIPP_OK;
   CU(cudaSetDevice(ctx->device));
   TimeScope ts_(ctx, RIPP_T_FOLD);
-  k_fold<F><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const Aff<F>*)hi, (const Aff<F>*)lo, scalar_bits(c), n,
-                                                            (Aff<F>*)out);
+  if (use_x3()) {
+    size_t warps = (n + 9) / 10;
+    k_fold_x3<XF><<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>((const Aff<XF>*)hi, (const Aff<XF>*)lo, scalar_bits(c),
+                                                                       n, (Aff<XF>*)out);
+  } else {
+    k_fold<F><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const Aff<F>*)hi, (const Aff<F>*)lo, scalar_bits(c), n,
+                                                              (Aff<F>*)out);
+  }
   LAUNCHED(ctx);
   return RIPP_OK;
 }
 extern "C" int ripp_g1_fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c, size_t n, void* out) {
-  return fold_dev<Fq>(ctx, hi, lo, c, n, out);
+  return fold_dev<Fq, Fq>(ctx, hi, lo, c, n, out);
 }
 extern "C" int ripp_g2_fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c, size_t n, void* out) {
-  return fold_dev<Fq2>(ctx, hi, lo, c, n, out);
+  return fold_dev<Fq2, x3::Fq2x3>(ctx, hi, lo, c, n, out);
 }
 
 __global__ void k_fr_fold(const Fr* __restrict__ hi, const Fr* __restrict__ lo, Fr c, size_t n, Fr* __restrict__ out) {

@@ -4,6 +4,7 @@
 // CPU-only box (the carry flag is emulated, see ripp_b200/csrc/limb.cuh).  Built by tests/conftest.py.
 #define RIPP_HOSTSIM 1
 #include "../../ripp_b200/csrc/l6.cuh"
+#include "../../ripp_b200/csrc/x3.cuh"
 #include <pthread.h>
 #include <thread>
 #include <vector>
@@ -152,6 +153,55 @@ void hs_l6_miller(const uint32_t* p, const uint32_t* q, const int* valid, int np
     l6::miller(c, pairs, npairs);
     if (with_final_exp) l6::final_exp(c);
     l6_store_reg(c, 0, r);
+  });
+}
+}
+
+// ---- x3 (three lanes per point): each lane a host thread, gather3 through a shared bus -------------
+namespace {
+struct X3Bus {
+  pthread_barrier_t bar;
+  Fq slot[3];
+};
+thread_local int x3_r = 0;
+thread_local X3Bus* x3_bus = nullptr;
+}
+namespace ripp { namespace x3 {
+int lane_r() { return x3_r; }
+void gather3(const Fq& mine, Fq& t0, Fq& t1, Fq& t2) {
+  x3_bus->slot[x3_r] = mine;
+  pthread_barrier_wait(&x3_bus->bar);
+  t0 = x3_bus->slot[0];
+  t1 = x3_bus->slot[1];
+  t2 = x3_bus->slot[2];
+  pthread_barrier_wait(&x3_bus->bar);
+}
+}}
+template <class Fn>
+static void run_x3(Fn fn) {
+  X3Bus bus;
+  pthread_barrier_init(&bus.bar, nullptr, 3);
+  std::vector<std::thread> th;
+  for (int r = 0; r < 3; r++) th.emplace_back([&, r] { x3_r = r; x3_bus = &bus; fn(r); });
+  for (auto& t : th) t.join();
+  pthread_barrier_destroy(&bus.bar);
+}
+extern "C" {
+// out = k * p + lo with k given as NAF bitmaps (9 words each); group 1 = G1, 2 = G2
+void hs_x3_fold(int group, const uint32_t* p, const uint32_t* lo, const uint32_t* pos, const uint32_t* neg, int nd, uint32_t* out) {
+  run_x3([&](int r) {
+    if (group == 1) {
+      Jac<Fq> acc = x3::mul_naf<Fq>(ld<G1Aff>(p), pos, neg, nd);
+      acc = x3::g1_madd(acc, ld<G1Aff>(lo));
+      G1Aff o = acc.to_affine();
+      if (r == 0) st(out, o);
+    } else {
+      typedef x3::Fq2x3 F;
+      Jac<F> acc = x3::mul_naf<F>(ld<Aff<F>>(p), pos, neg, nd);
+      acc = acc.add_mixed_body(ld<Aff<F>>(lo));
+      Aff<F> o = acc.to_affine();
+      if (r == 0) st(out, o);
+    }
   });
 }
 }

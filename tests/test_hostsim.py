@@ -181,3 +181,41 @@ def test_lazy_sum_of_products(hostsim):
             B = np.concatenate([C._words(x, 12) for x in b])
             got = hostsim.call("hs_fq_dot_redc", A, B, k, 3, out=12)
             assert C._int(got) == sum(x * y for x, y in zip(a, b)) * rinv % E.P
+
+
+def test_x3_three_lane_point_arithmetic(hostsim):
+    """x3.cuh (three lanes per curve point, each lane a host thread): k * P + L against the oracle, incl. the
+    exceptional cases of the final mixed addition."""
+    import numpy as np
+
+    def naf(k):
+        pos = neg = 0
+        i = 0
+        while k:
+            if k & 1:
+                if k & 3 == 1:
+                    pos |= 1 << i
+                    k -= 1
+                else:
+                    neg |= 1 << i
+                    k += 1
+            k >>= 1
+            i += 1
+        return pos, neg, i
+
+    def fold(group, p, lo, k):
+        pos, neg, nd = naf(k)
+        P = np.frombuffer(pos.to_bytes(36, "little"), dtype=np.uint32).copy()
+        N = np.frombuffer(neg.to_bytes(36, "little"), dtype=np.uint32).copy()
+        enc, dec, w = (C.g1_enc, C.g1_dec, 24) if group == 1 else (C.g2_enc, C.g2_dec, 48)
+        return dec(hostsim.call("hs_x3_fold", group, enc(p), enc(lo), P, N, nd, out=w))
+
+    k = rnd.randrange(E.R)
+    p1, l1 = E.g1_mul(E.G1_GEN, 11), E.g1_mul(E.G1_GEN, 13)
+    p2, l2 = E.g2_mul(E.G2_GEN, 11), E.g2_mul(E.G2_GEN, 13)
+    assert fold(1, p1, l1, k) == E.g1_add(E.g1_mul(p1, k), l1)
+    assert fold(2, p2, l2, k) == E.g2_add(E.g2_mul(p2, k), l2)
+    k = 12345
+    assert fold(1, p1, None, k) == E.g1_mul(p1, k) and fold(1, None, p1, k) == p1
+    assert fold(1, p1, E.g1_neg(E.g1_mul(p1, k)), k) is None
+    assert fold(2, p2, E.g2_mul(p2, k), k) == E.g2_mul(p2, 2 * k)
