@@ -26,7 +26,7 @@ static MsmPlan msm_plan(size_t n) {
   // warp (at 4 per bucket a warp runs at max/mean ~ 2.5x), short enough for the small MSMs of late rounds
   p.c = lg - 5;
   if (p.c < 4) p.c = 4;
-  if (p.c > 14) p.c = 14;
+  if (p.c > 16) p.c = 16;
   p.nw = (255 + p.c - 1) / p.c;
   p.B = 1u << p.c;
   p.L = p.B / 256;  // short chunks: the running-sum chains are latency, not throughput
@@ -74,7 +74,8 @@ struct FatBucket {
 // exclusive scan of counts within each window (one block per window) -> offsets into idx[w*n ..]
 __global__ void k_msm_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
                            uint32_t* __restrict__ cursor, uint32_t B, size_t n, uint32_t* __restrict__ fat_counters,
-                           FatItem* __restrict__ items, FatBucket* __restrict__ fats, uint32_t max_items) {
+                           FatItem* __restrict__ items, FatBucket* __restrict__ fats, uint32_t max_items,
+                           uint32_t fat_threshold) {
   __shared__ uint32_t part[256];
   int w = blockIdx.x;
   uint32_t per = (B + 255) / 256;
@@ -98,7 +99,7 @@ __global__ void k_msm_scan(const uint32_t* __restrict__ counts, uint32_t* __rest
     offsets[(size_t)w * B + j] = run;
     cursor[(size_t)w * B + j] = run;
     run += cnt;
-    if (cnt > MSM_FAT) {
+    if (cnt > fat_threshold) {
       uint32_t nch = (cnt + MSM_FAT_CHUNK - 1) / MSM_FAT_CHUNK;
       uint32_t first = atomicAdd(&fat_counters[0], nch);
       uint32_t fb = atomicAdd(&fat_counters[1], 1u);
@@ -127,11 +128,11 @@ template <class F>
 __global__ void __launch_bounds__(128) k_msm_accumulate(const Aff<F>* __restrict__ bases, const uint32_t* __restrict__ idx,
                                                         const uint32_t* __restrict__ offsets,
                                                         const uint32_t* __restrict__ counts, Jac<F>* __restrict__ buckets,
-                                                        size_t total) {
+                                                        size_t total, uint32_t fat_threshold) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   uint32_t start = offsets[t], cnt = counts[t];
-  if (cnt > MSM_FAT) return;  // summed by k_msm_fat_*
+  if (cnt > fat_threshold) return;  // summed by k_msm_fat_*
   Jac<F> acc = Jac<F>::inf();
   for (uint32_t j = 0; j < cnt; j++) acc = acc.add_mixed(bases[idx[start + j]]);
   buckets[t] = acc;
@@ -284,12 +285,16 @@ static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, A
   CU(cudaMemsetAsync(counts, 0, WB * sizeof(uint32_t), st));
   k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, n, (Fr*)canon, counts, p.c, p.nw);
   LAUNCHED(ctx);
-  k_msm_scan<<<p.nw, 256, 0, st>>>(counts, offsets, cursor, p.B, n, fat_counters, fat_items, fat_buckets, max_items);
+  // "fat" = far above the mean bucket size (and never below MSM_FAT points)
+  uint32_t fat_threshold = (uint32_t)(4 * (n >> p.c));
+  if (fat_threshold < MSM_FAT) fat_threshold = MSM_FAT;
+  k_msm_scan<<<p.nw, 256, 0, st>>>(counts, offsets, cursor, p.B, n, fat_counters, fat_items, fat_buckets, max_items,
+                                   fat_threshold);
   LAUNCHED(ctx);
   k_msm_scatter<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const Fr*)canon, n, cursor, (uint32_t*)idx, p.c, p.nw);
   LAUNCHED(ctx);
   k_msm_accumulate<F><<<(unsigned)((WB + 127) / 128), 128, 0, st>>>(bases, (const uint32_t*)idx, offsets, counts,
-                                                                   (Jac<F>*)bkt, WB);
+                                                                   (Jac<F>*)bkt, WB, fat_threshold);
   LAUNCHED(ctx);
   {
     unsigned fat_grid = max_items < 1184u ? max_items : 1184u;  // grid-stride over the item list; 8 blocks per SM
