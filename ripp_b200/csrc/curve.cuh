@@ -114,6 +114,27 @@ RIPP_FN Jac<F> scalar_mul(const Aff<F>& p, const uint32_t* bits, int nbits) {
   return acc;
 }
 
+// Efficient endomorphisms (GLV / GLS).  G1: phi(x, y) = (beta x, y) = [lambda] with lambda = x^2 - 1 (128 bits).
+// G2: psi(x, y) = (conj(x) cx, conj(y) cy) = [x] (x = -|x|, 64 bits), so -psi = [|x|].
+RIPP_HD Aff<Fq> endo_map(const Aff<Fq>& p) {
+  Fq beta;
+#pragma unroll
+  for (int i = 0; i < 12; i++) beta.v[i] = k::ENDO_BETA(i);
+  return {p.x * beta, p.y};
+}
+RIPP_HD Aff<Fq2> endo_map(const Aff<Fq2>& p) {  // -psi(p) = [|x|] p
+  Fq2 cx, cy;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    cx.c0.v[i] = k::PSI_CX(i);
+    cx.c1.v[i] = k::PSI_CX(12 + i);
+    cy.c0.v[i] = k::PSI_CY(i);
+    cy.c1.v[i] = k::PSI_CY(12 + i);
+  }
+  if (p.is_inf()) return p;
+  return {p.x.conj() * cx, -(p.y.conj() * cy)};
+}
+
 using G1Aff = Aff<Fq>;
 using G1Jac = Jac<Fq>;
 using G2Aff = Aff<Fq2>;

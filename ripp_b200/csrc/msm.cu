@@ -430,6 +430,123 @@ static ScalarBits scalar_bits(const void* fr_mont_host) {
   return b;
 }
 
+// ---- endomorphism-accelerated folds -----------------------------------------------------------------
+// The shared scalar is split on the host into m short digits in base B (G1: B = lambda = x^2 - 1, two 128-bit
+// digits; G2: B = |x|, up to four 64-bit digits), c = sum_i d_i B^i, and  c P = sum_i d_i E^i(P)  with the
+// cheap map E = phi (G1) / -psi (G2): a joint double-and-add over max|d_i| bits instead of |c| bits.
+struct EndoBits {
+  uint32_t pos[4][5], neg[4][5];
+  int m, nbits;
+};
+
+static void naf_bitmaps(const uint32_t* k_in, int words, uint32_t* pos, uint32_t* neg, int* nd) {
+  uint32_t k[10] = {0};
+  for (int i = 0; i < words; i++) k[i] = k_in[i];
+  int i = 0;
+  auto is_zero = [&] { for (int j = 0; j < 10; j++) if (k[j]) return false; return true; };
+  while (!is_zero()) {
+    if (k[0] & 1) {
+      if ((k[0] & 3) == 1) {
+        pos[i >> 5] |= 1u << (i & 31);
+        k[0] -= 1;
+      } else {
+        neg[i >> 5] |= 1u << (i & 31);
+        for (int j = 0; j < 10; j++)
+          if (++k[j]) break;
+      }
+    }
+    for (int j = 0; j < 9; j++) k[j] = (k[j] >> 1) | (k[j + 1] << 31);
+    k[9] >>= 1;
+    i++;
+  }
+  *nd = i;
+}
+
+// (q, r) = divmod(k, d) on little-endian 32-bit words, bitwise restoring division (host, once per fold)
+static void divmod_words(const uint32_t* k, int kw, const uint32_t* d, int dw, uint32_t* q, uint32_t* r) {
+  uint32_t rem[10] = {0};
+  for (int i = 0; i < kw; i++) q[i] = 0;
+  for (int bit = 32 * kw - 1; bit >= 0; bit--) {
+    for (int j = 9; j > 0; j--) rem[j] = (rem[j] << 1) | (rem[j - 1] >> 31);
+    rem[0] = (rem[0] << 1) | ((k[bit >> 5] >> (bit & 31)) & 1);
+    bool ge = true;
+    for (int j = 9; j >= 0; j--) {
+      uint32_t dj = j < dw ? d[j] : 0;
+      if (rem[j] != dj) {
+        ge = rem[j] > dj;
+        break;
+      }
+    }
+    if (ge) {
+      uint64_t borrow = 0;
+      for (int j = 0; j < 10; j++) {
+        uint64_t dj = j < dw ? d[j] : 0;
+        uint64_t t = (uint64_t)rem[j] - dj - borrow;
+        rem[j] = (uint32_t)t;
+        borrow = (t >> 32) & 1;
+      }
+      q[bit >> 5] |= 1u << (bit & 31);
+    }
+  }
+  for (int j = 0; j < dw; j++) r[j] = rem[j];
+}
+
+template <class F>
+static EndoBits endo_bits(const void* fr_mont_host) {
+  Fr s;
+  memcpy(s.v, fr_mont_host, sizeof(Fr));
+  s = s.from_mont();
+  EndoBits b;
+  memset(&b, 0, sizeof(b));
+  uint32_t base[4] = {0};
+  int bw;
+  if (sizeof(F) == sizeof(Fq)) {
+    for (int i = 0; i < 4; i++) base[i] = k::ENDO_LAMBDA(i);
+    bw = 4;
+  } else {
+    base[0] = (uint32_t)k::X_ABS;
+    base[1] = (uint32_t)(k::X_ABS >> 32);
+    bw = 2;
+  }
+  uint32_t cur[8], q[8], r[4];
+  for (int i = 0; i < 8; i++) cur[i] = s.v[i];
+  b.m = 0;
+  b.nbits = 0;
+  for (int i = 0; i < 4; i++) {
+    bool zero = true;
+    for (int j = 0; j < 8; j++) zero = zero && cur[j] == 0;
+    if (zero) break;
+    memset(r, 0, sizeof(r));
+    divmod_words(cur, 8, base, bw, q, r);
+    int nd = 0;
+    naf_bitmaps(r, bw, b.pos[i], b.neg[i], &nd);
+    if (nd > b.nbits) b.nbits = nd;
+    memcpy(cur, q, sizeof(cur));
+    b.m = i + 1;
+  }
+  return b;
+}
+
+template <class F>
+__global__ void __launch_bounds__(64, 4) k_fold_endo(const Aff<F>* __restrict__ hi, const Aff<F>* __restrict__ lo, EndoBits c,
+                                                     size_t n, Aff<F>* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Aff<F> base[4];
+  base[0] = hi[i];
+  for (int t = 1; t < c.m; t++) base[t] = endo_map(base[t - 1]);
+  Jac<F> acc = Jac<F>::inf();
+  for (int j = c.nbits - 1; j >= 0; j--) {
+    acc = acc.dbl();
+    for (int t = 0; t < c.m; t++) {
+      if ((c.pos[t][j >> 5] >> (j & 31)) & 1) acc = acc.add_mixed(base[t]);
+      if ((c.neg[t][j >> 5] >> (j & 31)) & 1) acc = acc.add_mixed(base[t].neg());
+    }
+  }
+  acc = acc.add_mixed(lo[i]);
+  out[i] = acc.to_affine();
+}
+
 template <class F>
 __global__ void __launch_bounds__(64, 4) k_fold(const Aff<F>* __restrict__ hi, const Aff<F>* __restrict__ lo, ScalarBits c,
                                                 size_t n, Aff<F>* __restrict__ out) {
@@ -460,6 +577,15 @@ __global__ void __launch_bounds__(128) k_fold_x3(const Aff<XF>* __restrict__ hi,
   if (lane % 3 == 0) out[i] = o;
 }
 
+static bool use_endo() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RIPP_B200_FOLD");  // "plain" = no endomorphism (A/B runs)
+    v = (e && strcmp(e, "plain") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <class F, class XF>
 static int fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c, size_t n, void* out) {
   if (!ctx || !c || (n && (!hi || !lo || !out))) return fail(RIPP_ERR_ARG, "null argument");
@@ -470,6 +596,9 @@ static int fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c
     size_t warps = (n + 9) / 10;
     k_fold_x3<XF><<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>((const Aff<XF>*)hi, (const Aff<XF>*)lo, scalar_bits(c),
                                                                        n, (Aff<XF>*)out);
+  } else if (use_endo()) {
+    k_fold_endo<F><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const Aff<F>*)hi, (const Aff<F>*)lo, endo_bits<F>(c), n,
+                                                                   (Aff<F>*)out);
   } else {
     k_fold<F><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const Aff<F>*)hi, (const Aff<F>*)lo, scalar_bits(c), n,
                                                               (Aff<F>*)out);

@@ -67,6 +67,8 @@ void hs_fq_dot_redc(const uint32_t* a, const uint32_t* b, int k, int subs, uint3
 }
 uint64_t hs_mul_count(int which) { return detail::mul_count_[which]; }
 void hs_mul_count_reset() { detail::mul_count_[0] = detail::mul_count_[1] = 0; }
+void hs_g1_endo(const uint32_t* a, const uint32_t*, uint32_t* r) { st(r, endo_map(ld<G1Aff>(a))); }
+void hs_g2_endo(const uint32_t* a, const uint32_t*, uint32_t* r) { st(r, endo_map(ld<G2Aff>(a))); }
 void hs_g1_gen(uint32_t* r) { st(r, g1_generator()); }
 void hs_g2_gen(uint32_t* r) { st(r, g2_generator()); }
 void hs_miller(const uint32_t* p, const uint32_t* q, uint32_t* r) { st(r, miller_loop(ld<G1Aff>(p), ld<G2Aff>(q))); }

@@ -219,3 +219,11 @@ def test_x3_three_lane_point_arithmetic(hostsim):
     assert fold(1, p1, None, k) == E.g1_mul(p1, k) and fold(1, None, p1, k) == p1
     assert fold(1, p1, E.g1_neg(E.g1_mul(p1, k)), k) is None
     assert fold(2, p2, E.g2_mul(p2, k), k) == E.g2_mul(p2, 2 * k)
+
+
+def test_endomorphisms(hostsim):
+    """phi = [x^2 - 1] on G1 and -psi = [|x|] on G2 (curve.cuh endo_map, constants from tools/gen_constants.py)."""
+    p = E.g1_mul(E.G1_GEN, 4242)
+    q = E.g2_mul(E.G2_GEN, 4242)
+    assert C.g1_dec(hostsim.call("hs_g1_endo", C.g1_enc(p), C.g1_enc(p), out=24)) == E.g1_mul(p, E.X_ABS**2 - 1)
+    assert C.g2_dec(hostsim.call("hs_g2_endo", C.g2_enc(q), C.g2_enc(q), out=48)) == E.g2_mul(q, E.X_ABS)
