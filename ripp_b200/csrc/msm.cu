@@ -6,6 +6,16 @@
 // sipp/src/lib.rs:87-100; scalar-mul primitive `mul_helper`, ip_proofs/src/lib.rs:15-19).
 #include "common.cuh"
 #include "x3.cuh"
+#include "endo.cuh"
+
+static bool use_endo() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RIPP_B200_FOLD");  // "plain" = no endomorphism (A/B runs)
+    v = (e && strcmp(e, "plain") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // ------------------------------------------------------------------------------------------------
 // MSM
@@ -18,7 +28,7 @@ struct MsmPlan {
   uint32_t T;  // chunks per window
 };
 
-static MsmPlan msm_plan(size_t n) {
+static MsmPlan msm_plan(size_t n, int bits = 255) {
   int lg = 0;
   while (((size_t)2 << lg) <= n) lg++;
   MsmPlan p;
@@ -27,7 +37,7 @@ static MsmPlan msm_plan(size_t n) {
   p.c = lg - 5;
   if (p.c < 4) p.c = 4;
   if (p.c > 16) p.c = 16;
-  p.nw = (255 + p.c - 1) / p.c;
+  p.nw = (bits + p.c - 1) / p.c;
   p.B = 1u << p.c;
   p.L = p.B / 256;  // short chunks: the running-sum chains are latency, not throughput
   if (p.L < 2) p.L = 2;
@@ -46,10 +56,10 @@ __device__ __forceinline__ uint32_t msm_digit(const uint32_t* s, int w, int c) {
 
 // canonical scalars + per-(window, bucket) histogram
 __global__ void k_msm_prepare(const Fr* __restrict__ sc, size_t n, Fr* __restrict__ canon, uint32_t* __restrict__ counts,
-                              int c, int nw) {
+                              int c, int nw, int is_mont) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fr s = sc[i].from_mont();
+  Fr s = is_mont ? sc[i].from_mont() : sc[i];
   canon[i] = s;
   uint32_t B = 1u << c;
   for (int w = 0; w < nw; w++) {
@@ -252,6 +262,30 @@ template <class F> struct X3Of;
 template <> struct X3Of<Fq> { typedef Fq type; };
 template <> struct X3Of<Fq2> { typedef x3::Fq2x3 type; };
 
+// sum_i s_i P_i = sum_i sum_t d_{i,t} E^t(P_i): m n points with short (128- / 64-bit) scalars, which cuts the
+// Horner tail (the latency floor of every MSM) from 255 to 128 / 64 doublings at the same bucket work
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_endo_expand(const Aff<F>* __restrict__ bases, const Fr* __restrict__ sc, size_t n,
+                                                         Aff<F>* __restrict__ bases2, Fr* __restrict__ canon2, int m) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = sc[i].from_mont();
+  uint32_t digits[4][4];
+  int mm;
+  endo_digits<sizeof(F) == sizeof(Fq) ? 1 : 2>(s.v, digits, &mm);
+  Aff<F> p = bases[i];
+  for (int t = 0; t < m; t++) {
+    Fr d = Fr::zero();
+    for (int j = 0; j < 4; j++) d.v[j] = digits[t][j];
+    bases2[(size_t)t * n + i] = p;
+    canon2[(size_t)t * n + i] = d;
+    if (t + 1 < m) p = endo_map(p);
+  }
+}
+
+template <class F>
+static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, Aff<F>* out, int bits, int is_mont);
+
 template <class F>
 static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, Aff<F>* out) {
   CU(cudaSetDevice(ctx->device));
@@ -260,7 +294,21 @@ static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, A
     return RIPP_OK;
   }
   TimeScope ts_(ctx, RIPP_T_MSM);
-  MsmPlan p = msm_plan(n);
+  if (!use_endo()) return msm_core<F>(ctx, bases, sc, n, out, 255, 1);
+  const int m = sizeof(F) == sizeof(Fq) ? 2 : 4;
+  void* ex;
+  size_t pts_bytes = ((size_t)m * n * sizeof(Aff<F>) + 255) & ~(size_t)255;
+  OK(scratch(ctx, 16, pts_bytes + (size_t)m * n * sizeof(Fr) + 256, &ex));
+  Aff<F>* bases2 = (Aff<F>*)ex;
+  Fr* canon2 = (Fr*)((char*)ex + pts_bytes);
+  k_msm_endo_expand<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(bases, sc, n, bases2, canon2, m);
+  LAUNCHED(ctx);
+  return msm_core<F>(ctx, bases2, canon2, (size_t)m * n, out, m == 2 ? 128 : 64, 0);
+}
+
+template <class F>
+static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, Aff<F>* out, int bits, int is_mont) {
+  MsmPlan p = msm_plan(n, bits);
   size_t WB = (size_t)p.nw * p.B;
   void *canon, *cnt, *idx, *bkt, *parts;
   OK(scratch(ctx, 4, n * sizeof(Fr), &canon));
@@ -283,7 +331,7 @@ static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, A
   FatBucket* fat_buckets = (FatBucket*)(fat_items + max_items);
   CU(cudaMemsetAsync(fat_counters, 0, 64, st));
   CU(cudaMemsetAsync(counts, 0, WB * sizeof(uint32_t), st));
-  k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, n, (Fr*)canon, counts, p.c, p.nw);
+  k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, n, (Fr*)canon, counts, p.c, p.nw, is_mont);
   LAUNCHED(ctx);
   // "fat" = far above the mean bucket size (and never below MSM_FAT points)
   uint32_t fat_threshold = (uint32_t)(4 * (n >> p.c));
@@ -434,96 +482,13 @@ static ScalarBits scalar_bits(const void* fr_mont_host) {
 // The shared scalar is split on the host into m short digits in base B (G1: B = lambda = x^2 - 1, two 128-bit
 // digits; G2: B = |x|, up to four 64-bit digits), c = sum_i d_i B^i, and  c P = sum_i d_i E^i(P)  with the
 // cheap map E = phi (G1) / -psi (G2): a joint double-and-add over max|d_i| bits instead of |c| bits.
-struct EndoBits {
-  uint32_t pos[4][5], neg[4][5];
-  int m, nbits;
-};
-
-static void naf_bitmaps(const uint32_t* k_in, int words, uint32_t* pos, uint32_t* neg, int* nd) {
-  uint32_t k[10] = {0};
-  for (int i = 0; i < words; i++) k[i] = k_in[i];
-  int i = 0;
-  auto is_zero = [&] { for (int j = 0; j < 10; j++) if (k[j]) return false; return true; };
-  while (!is_zero()) {
-    if (k[0] & 1) {
-      if ((k[0] & 3) == 1) {
-        pos[i >> 5] |= 1u << (i & 31);
-        k[0] -= 1;
-      } else {
-        neg[i >> 5] |= 1u << (i & 31);
-        for (int j = 0; j < 10; j++)
-          if (++k[j]) break;
-      }
-    }
-    for (int j = 0; j < 9; j++) k[j] = (k[j] >> 1) | (k[j + 1] << 31);
-    k[9] >>= 1;
-    i++;
-  }
-  *nd = i;
-}
-
-// (q, r) = divmod(k, d) on little-endian 32-bit words, bitwise restoring division (host, once per fold)
-static void divmod_words(const uint32_t* k, int kw, const uint32_t* d, int dw, uint32_t* q, uint32_t* r) {
-  uint32_t rem[10] = {0};
-  for (int i = 0; i < kw; i++) q[i] = 0;
-  for (int bit = 32 * kw - 1; bit >= 0; bit--) {
-    for (int j = 9; j > 0; j--) rem[j] = (rem[j] << 1) | (rem[j - 1] >> 31);
-    rem[0] = (rem[0] << 1) | ((k[bit >> 5] >> (bit & 31)) & 1);
-    bool ge = true;
-    for (int j = 9; j >= 0; j--) {
-      uint32_t dj = j < dw ? d[j] : 0;
-      if (rem[j] != dj) {
-        ge = rem[j] > dj;
-        break;
-      }
-    }
-    if (ge) {
-      uint64_t borrow = 0;
-      for (int j = 0; j < 10; j++) {
-        uint64_t dj = j < dw ? d[j] : 0;
-        uint64_t t = (uint64_t)rem[j] - dj - borrow;
-        rem[j] = (uint32_t)t;
-        borrow = (t >> 32) & 1;
-      }
-      q[bit >> 5] |= 1u << (bit & 31);
-    }
-  }
-  for (int j = 0; j < dw; j++) r[j] = rem[j];
-}
-
 template <class F>
 static EndoBits endo_bits(const void* fr_mont_host) {
   Fr s;
   memcpy(s.v, fr_mont_host, sizeof(Fr));
   s = s.from_mont();
   EndoBits b;
-  memset(&b, 0, sizeof(b));
-  uint32_t base[4] = {0};
-  int bw;
-  if (sizeof(F) == sizeof(Fq)) {
-    for (int i = 0; i < 4; i++) base[i] = k::ENDO_LAMBDA(i);
-    bw = 4;
-  } else {
-    base[0] = (uint32_t)k::X_ABS;
-    base[1] = (uint32_t)(k::X_ABS >> 32);
-    bw = 2;
-  }
-  uint32_t cur[8], q[8], r[4];
-  for (int i = 0; i < 8; i++) cur[i] = s.v[i];
-  b.m = 0;
-  b.nbits = 0;
-  for (int i = 0; i < 4; i++) {
-    bool zero = true;
-    for (int j = 0; j < 8; j++) zero = zero && cur[j] == 0;
-    if (zero) break;
-    memset(r, 0, sizeof(r));
-    divmod_words(cur, 8, base, bw, q, r);
-    int nd = 0;
-    naf_bitmaps(r, bw, b.pos[i], b.neg[i], &nd);
-    if (nd > b.nbits) b.nbits = nd;
-    memcpy(cur, q, sizeof(cur));
-    b.m = i + 1;
-  }
+  endo_decompose<sizeof(F) == sizeof(Fq) ? 1 : 2>(s.v, b);
   return b;
 }
 
@@ -532,17 +497,7 @@ __global__ void __launch_bounds__(64, 4) k_fold_endo(const Aff<F>* __restrict__ 
                                                      size_t n, Aff<F>* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Aff<F> base[4];
-  base[0] = hi[i];
-  for (int t = 1; t < c.m; t++) base[t] = endo_map(base[t - 1]);
-  Jac<F> acc = Jac<F>::inf();
-  for (int j = c.nbits - 1; j >= 0; j--) {
-    acc = acc.dbl();
-    for (int t = 0; t < c.m; t++) {
-      if ((c.pos[t][j >> 5] >> (j & 31)) & 1) acc = acc.add_mixed(base[t]);
-      if ((c.neg[t][j >> 5] >> (j & 31)) & 1) acc = acc.add_mixed(base[t].neg());
-    }
-  }
+  Jac<F> acc = endo_mul<F>(hi[i], c);
   acc = acc.add_mixed(lo[i]);
   out[i] = acc.to_affine();
 }
@@ -575,15 +530,6 @@ __global__ void __launch_bounds__(128) k_fold_x3(const Aff<XF>* __restrict__ hi,
   acc = x3::Ops<XF>::madd(acc, lo[i]);
   Aff<XF> o = acc.to_affine();
   if (lane % 3 == 0) out[i] = o;
-}
-
-static bool use_endo() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RIPP_B200_FOLD");  // "plain" = no endomorphism (A/B runs)
-    v = (e && strcmp(e, "plain") == 0) ? 0 : 1;
-  }
-  return v == 1;
 }
 
 template <class F, class XF>

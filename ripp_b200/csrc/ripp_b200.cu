@@ -1,6 +1,7 @@
 // ripp_b200: CUDA kernels (sm_100a) + C ABI (include/ripp_b200.h).
 #include "common.cuh"
 #include "x3.cuh"
+#include "endo.cuh"
 
 static thread_local std::string g_err;
 std::string& ripp_err_slot() { return g_err; }
@@ -209,7 +210,15 @@ __global__ void __launch_bounds__(64, 4) k_scale(const Aff<F>* __restrict__ pts,
   if (i >= n) return;
   Fr s = sc[i].from_mont();
   Aff<F> p = GEN ? gen : pts[i];
-  out[i] = scalar_mul(p, s.v, 255).to_affine();
+  EndoBits eb;  // GLV / GLS decomposition of this element's scalar (endo.cuh)
+  endo_decompose<sizeof(F) == sizeof(Fq) ? 1 : 2>(s.v, eb);
+  // warp-uniform trip counts (every lane walks the longest digit of the warp)
+  int nb = eb.nbits, mm = eb.m;
+  for (int o = 16; o >= 1; o >>= 1) {
+    nb = max(nb, __shfl_xor_sync(__activemask(), nb, o));
+    mm = max(mm, __shfl_xor_sync(__activemask(), mm, o));
+  }
+  out[i] = endo_mul_simt<F>(p, eb, mm, nb).to_affine();
 }
 
 // three lanes per element (x3.cuh); the scalar is NAF-recoded by the group itself

@@ -5,6 +5,7 @@
 #define RIPP_HOSTSIM 1
 #include "../../ripp_b200/csrc/l6.cuh"
 #include "../../ripp_b200/csrc/x3.cuh"
+#include "../../ripp_b200/csrc/endo.cuh"
 #include <pthread.h>
 #include <thread>
 #include <vector>
@@ -67,6 +68,9 @@ void hs_fq_dot_redc(const uint32_t* a, const uint32_t* b, int k, int subs, uint3
 }
 uint64_t hs_mul_count(int which) { return detail::mul_count_[which]; }
 void hs_mul_count_reset() { detail::mul_count_[0] = detail::mul_count_[1] = 0; }
+// k * P through the GLV / GLS decomposition (endo.cuh); k = 8 canonical words
+void hs_g1_endo_mul(const uint32_t* p, const uint32_t* k, uint32_t* r) { EndoBits b; endo_decompose<1>(k, b); st(r, endo_mul<Fq>(ld<G1Aff>(p), b).to_affine()); }
+void hs_g2_endo_mul(const uint32_t* p, const uint32_t* k, uint32_t* r) { EndoBits b; endo_decompose<2>(k, b); st(r, endo_mul<Fq2>(ld<G2Aff>(p), b).to_affine()); }
 void hs_g1_endo(const uint32_t* a, const uint32_t*, uint32_t* r) { st(r, endo_map(ld<G1Aff>(a))); }
 void hs_g2_endo(const uint32_t* a, const uint32_t*, uint32_t* r) { st(r, endo_map(ld<G2Aff>(a))); }
 void hs_g1_gen(uint32_t* r) { st(r, g1_generator()); }

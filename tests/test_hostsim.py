@@ -227,3 +227,14 @@ def test_endomorphisms(hostsim):
     q = E.g2_mul(E.G2_GEN, 4242)
     assert C.g1_dec(hostsim.call("hs_g1_endo", C.g1_enc(p), C.g1_enc(p), out=24)) == E.g1_mul(p, E.X_ABS**2 - 1)
     assert C.g2_dec(hostsim.call("hs_g2_endo", C.g2_enc(q), C.g2_enc(q), out=48)) == E.g2_mul(q, E.X_ABS)
+
+
+def test_endo_scalar_multiplication(hostsim):
+    """GLV / GLS decomposition + joint double-and-add (endo.cuh) against the oracle, incl. edge scalars."""
+    p = E.g1_mul(E.G1_GEN, 99)
+    q = E.g2_mul(E.G2_GEN, 99)
+    lam = E.X_ABS**2 - 1
+    for k in (0, 1, 2, lam - 1, lam, lam + 1, E.X_ABS, E.X_ABS**2, E.X_ABS**3 + 5, E.R - 1, rnd.randrange(E.R), rnd.randrange(1 << 128)):
+        kw = C.scalar_words(k)
+        assert C.g1_dec(hostsim.call("hs_g1_endo_mul", C.g1_enc(p), kw, out=24)) == E.g1_mul(p, k), k
+        assert C.g2_dec(hostsim.call("hs_g2_endo_mul", C.g2_enc(q), kw, out=48)) == E.g2_mul(q, k), k
