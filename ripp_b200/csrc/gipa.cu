@@ -568,46 +568,53 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
   OK(ripp_fork(ctx, mk));
   OK(ripp_msm_g1_dev(mk, c_dev, W + o_pw, n, W + o_res));
   OK(ripp_join(ctx, pk));
-  // :124 ip_ab = IP(a_r, b); :133-136 sanity com_a == IP(a_r, ck_1_r)
+  // :124 ip_ab = IP(a_r, b) and the :133-136 sanity product IP(a_r, ck_1_r) are not inputs of the two TIPA
+  // proofs: they run from a third host thread on their own child context, overlapping the first GIPA rounds.
   Val ipv[2];
-  {
-    Slice xs[2] = {Slice{VT_G1, W + o_ar}, Slice{VT_G1, W + o_ar}};
-    Slice ys[2] = {Slice{VT_G2, (const char*)b_dev}, Slice{VT_G2, W + o_ck1r}};
-    OK(eval_products(ctx, 2, xs, ys, n, ipv));
-  }
-  if (memcmp(ipv[1].raw, com[0].raw, 576) != 0)
-    return fail(RIPP_ERR_INNER_PRODUCT, "com_a != IP(a_r, ck_1_r) (groth16_aggregation.rs:133-136)");
-  // :125 agg_c = MSM(c, r_vec)
   Val agg_c;
   agg_c.t = VT_G1;
   memset(agg_c.raw, 0, 576);
-  OK(ripp_join(ctx, mk));
-  CU(cudaMemcpyAsync(agg_c.raw, W + o_res, 96, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  if (trace_on()) fprintf(stderr, "[trace] aggregate prologue (3 commitments, r, scalings, ip_ab, agg_c) %.2f ms\n", now_ms() - t_a0);
-  // :138-149 the two TIPA proofs
-  // ... which are independent: run them from two host threads on two child contexts so their
-  // (latency-bound) rounds overlap on the GPU
+  int st_ip = RIPP_OK, st_c = RIPP_OK, st_a = RIPP_OK;
+  std::string err_ip, err_c;
+  // :138-149 the two TIPA proofs are independent as well: three host threads on three child contexts, so the
+  // (latency-bound) rounds of both recursions and the two big products overlap on the GPU.  All children are
+  // created and forked before any thread starts; after that, failures are reported through the status words.
+  ripp_ctx* ik = ripp_child(ctx, 3);
+  ripp_ctx* ka = ripp_child(ctx, 6);
+  ripp_ctx* kc = ripp_child(ctx, 7);
+  if (!ik || !ka || !kc) return fail(RIPP_ERR_CUDA, "child context");
+  OK(ripp_fork(ctx, ik));
+  OK(ripp_fork(ctx, ka));
+  OK(ripp_fork(ctx, kc));
+  if (trace_on()) fprintf(stderr, "[trace] aggregate prologue (3 commitments, r, scalings queued) %.2f ms\n", now_ms() - t_a0);
   Bytes proof_ab, proof_c;
   {
-    ripp_ctx* ka = ripp_child(ctx, 6);
-    ripp_ctx* kc = ripp_child(ctx, 7);
-    if (!ka || !kc) return fail(RIPP_ERR_CUDA, "child context");
-    OK(ripp_fork(ctx, ka));
-    OK(ripp_fork(ctx, kc));
-    int st_c = RIPP_OK;
-    std::string err_c;
+    std::thread tip([&] {
+      Slice xs[2] = {Slice{VT_G1, W + o_ar}, Slice{VT_G1, W + o_ar}};
+      Slice ys[2] = {Slice{VT_G2, (const char*)b_dev}, Slice{VT_G2, W + o_ck1r}};
+      st_ip = eval_products(ik, 2, xs, ys, n, ipv);
+      if (st_ip != RIPP_OK) err_ip = ripp_err_slot();
+    });
     std::thread tc([&] {
       st_c = tipa_prove(kc, RIPP_GIPA_MULTIEXP_SSM, srs_g1_dev, srs_g2_dev, c_dev, W + o_pw, ck1, nullptr, n, Fr::one(), &proof_c);
       if (st_c != RIPP_OK) err_c = ripp_err_slot();
     });
-    int st_a = tipa_prove(ka, RIPP_GIPA_PAIRING, srs_g1_dev, srs_g2_dev, W + o_ar, b_dev, W + o_ck1r, ck2, n, r, &proof_ab);
+    st_a = tipa_prove(ka, RIPP_GIPA_PAIRING, srs_g1_dev, srs_g2_dev, W + o_ar, b_dev, W + o_ck1r, ck2, n, r, &proof_ab);
     tc.join();
-    if (st_a != RIPP_OK) return st_a;
-    if (st_c != RIPP_OK) return fail(st_c, err_c);
-    OK(ripp_join(ctx, ka));
-    OK(ripp_join(ctx, kc));
+    tip.join();
   }
+  if (st_a != RIPP_OK) return st_a;
+  if (st_c != RIPP_OK) return fail(st_c, err_c);
+  if (st_ip != RIPP_OK) return fail(st_ip, err_ip);
+  OK(ripp_join(ctx, ka));
+  OK(ripp_join(ctx, kc));
+  OK(ripp_join(ctx, ik));
+  if (memcmp(ipv[1].raw, com[0].raw, 576) != 0)
+    return fail(RIPP_ERR_INNER_PRODUCT, "com_a != IP(a_r, ck_1_r) (groth16_aggregation.rs:133-136)");
+  // :125 agg_c = MSM(c, r_vec), queued in the prologue on its own stream
+  OK(ripp_join(ctx, mk));
+  CU(cudaMemcpyAsync(agg_c.raw, W + o_res, 96, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   // AggregateProof { com_a, com_b, com_c, ip_ab, agg_c, tipa_proof_ab, tipa_proof_c } (:58-66)
   Bytes out;
   for (int i = 0; i < 3; i++) put_val(out, com[i]);
