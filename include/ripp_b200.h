@@ -190,6 +190,49 @@ int ripp_sipp_product_with_coeffs(ripp_ctx* ctx, const void* a_aff, const void* 
 int ripp_sipp_prove(ripp_ctx* ctx, const void* a_aff, const void* b_aff, const void* r, size_t n,
                     const void* value_gt, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 
+/* ---- verifiers ----------------------------------------- */
+/* All arithmetic of the verifiers runs on the GPU (GT multi-exponentiation, MSMs, pairings); the host
+ * recomputes the Fiat-Shamir chain from the proof bytes.  Inputs are arkworks serialize_uncompressed
+ * bytes as the provers above emit them.  *accept = 1 / 0 is the reference's Ok(true) / Ok(false);
+ * bytes that do not decode (non-canonical field element, point off the curve, wrong length) fail with
+ * RIPP_ERR_ARG, as ark-serialize would before the reference's verify is ever called.
+ *
+ * `com`: the statement, serialised commitment by commitment --
+ *     com_a || com_b || com_t          (com_t = IdentityOutput: u64 LE length 1, then the value)
+ *     com_a || com_t                   for the *_SSM kinds (the right commitment is the placeholder). */
+
+/* prod_i g_i^(s_i) in GT, device pointers (g: n x 576 B, s: n Fr Montgomery): `PairingOutput * Fr`
+ * (mul_helper with T = GT, ip_proofs/src/lib.rs:15-19), the primitive of gipa.rs:355-357 and
+ * sipp/src/lib.rs:152-160.  Generic Fq12 squarings: inputs need not lie in the cyclotomic subgroup. */
+int ripp_gt_multiexp_dev(ripp_ctx* ctx, const void* gt_dev, const void* fr_dev, size_t n, void* gt_out_dev);
+
+/* GIPA::verify (gipa.rs:135-160: _compute_recursive_challenges :322-363, _compute_final_commitment_keys
+ * :365-399 as one MSM per key vector, _verify_base_commitment :401-415); for the *_SSM kinds
+ * GIPAWithSSM::verify_with_structured_scalar_message (structured_scalar_message.rs:86-127) with
+ * scalar_b = one Fr (host, Montgomery), w_dev NULL.  v_dev / w_dev: the n commitment keys (device, affine). */
+int ripp_gipa_verify_dev(ripp_ctx* ctx, int kind, const void* v_dev, const void* w_dev, size_t n, const uint8_t* com,
+                         size_t com_len, const void* scalar_b, const uint8_t* proof, size_t proof_len, int* accept);
+
+/* VerifierSRS (tipa/mod.rs:88-94), host, Montgomery affine, packed: g (96 B) | h (192 B) | g_beta (96 B) |
+ * h_alpha (192 B).
+ * TIPA::verify_with_srs_shift (tipa/mod.rs:242-301; `shift` = r_shift, NULL for TIPA::verify) for kinds with a
+ * G1 right key; TIPAWithSSM::verify_with_structured_scalar_message (structured_scalar_message.rs:270-331;
+ * `shift` = scalar_b, required) for the *_SSM kinds.  The KZG checks are verify_commitment_key_g{1,2}_kzg_opening
+ * (tipa/mod.rs:340-370). */
+int ripp_tipa_verify(ripp_ctx* ctx, int kind, const void* vsrs, const uint8_t* com, size_t com_len, const void* shift,
+                     const uint8_t* proof, size_t proof_len, int* accept);
+
+/* verify_aggregate_proof (applications/groth16_aggregation.rs:162-231).
+ * vk (ark-groth16 VerifyingKey), host, Montgomery affine, packed: alpha_g1 (96 B) | beta_g2 (192 B) |
+ * gamma_g2 (192 B) | delta_g2 (192 B) | gamma_abc_g1[m + 1] (96 B each); public_inputs: n x m Fr (host,
+ * Montgomery, row = one proof's inputs); proof: the bytes ripp_tipp_aggregate emits. */
+int ripp_tipp_verify_aggregate(ripp_ctx* ctx, const void* vsrs, const void* vk, size_t m, const void* public_inputs,
+                               size_t n, const uint8_t* proof, size_t proof_len, int* accept);
+
+/* SIPP::verify (sipp/src/lib.rs:109-180): inputs as ripp_sipp_prove, proof = its output. */
+int ripp_sipp_verify(ripp_ctx* ctx, const void* a_aff, const void* b_aff, const void* r, size_t n, const void* value_gt,
+                     const uint8_t* proof, size_t proof_len, int* accept);
+
 /* ---- diagnostics --------------------------------------------------------------------------- */
 /* Element-wise primitive ops on device, used by the GPU parity tests to pin the PTX limb layer:
  * op in ripp_test_op; a, b, r are HOST arrays of n elements of the op's operand size. */

@@ -281,6 +281,46 @@ class Context:
                                     ctypes.c_size_t(cap), ctypes.byref(plen)))
         return proof[: plen.value].tobytes()
 
+    # ---- verifiers --------------------------------------------------------------------------------
+    def gt_multiexp_dev(self, gt_dev, fr_dev, n, out_dev):
+        check(lib().ripp_gt_multiexp_dev(self.handle, _p(gt_dev), _p(fr_dev), ctypes.c_size_t(n), _p(out_dev)))
+
+    @staticmethod
+    def _bytes(b):
+        return np.frombuffer(bytes(b), dtype=np.uint8).copy() if len(b) else np.zeros(1, dtype=np.uint8)
+
+    def gipa_verify_dev(self, kind, v, w, n, com, proof, scalar_b=None):
+        """-> bool.  com / proof: serialize_uncompressed bytes."""
+        acc = ctypes.c_int(0)
+        cb, pb = self._bytes(com), self._bytes(proof)
+        check(lib().ripp_gipa_verify_dev(self.handle, int(kind), _p(v), _p(w), ctypes.c_size_t(n), _p(cb),
+                                         ctypes.c_size_t(len(com)), _p(scalar_b), _p(pb), ctypes.c_size_t(len(proof)),
+                                         ctypes.byref(acc)))
+        return bool(acc.value)
+
+    def tipa_verify(self, kind, vsrs, com, proof, shift=None):
+        acc = ctypes.c_int(0)
+        cb, pb = self._bytes(com), self._bytes(proof)
+        check(lib().ripp_tipa_verify(self.handle, int(kind), _p(vsrs), _p(cb), ctypes.c_size_t(len(com)), _p(shift), _p(pb),
+                                     ctypes.c_size_t(len(proof)), ctypes.byref(acc)))
+        return bool(acc.value)
+
+    def tipp_verify_aggregate(self, vsrs, vk, public_inputs, proof):
+        """public_inputs: (n, m, 8) uint32 Montgomery Fr."""
+        acc = ctypes.c_int(0)
+        pb = self._bytes(proof)
+        n, m = public_inputs.shape[0], public_inputs.shape[1]
+        check(lib().ripp_tipp_verify_aggregate(self.handle, _p(vsrs), _p(vk), ctypes.c_size_t(m), _p(public_inputs),
+                                               ctypes.c_size_t(n), _p(pb), ctypes.c_size_t(len(proof)), ctypes.byref(acc)))
+        return bool(acc.value)
+
+    def sipp_verify(self, a, b, r, value, proof):
+        acc = ctypes.c_int(0)
+        pb = self._bytes(proof)
+        check(lib().ripp_sipp_verify(self.handle, _p(a), _p(b), _p(r), ctypes.c_size_t(len(a)), _p(value), _p(pb),
+                                     ctypes.c_size_t(len(proof)), ctypes.byref(acc)))
+        return bool(acc.value)
+
     # ---- diagnostics ----------------------------------------------------------------------
     def test_elementwise(self, op, a, b, out_words):
         a = np.ascontiguousarray(a, dtype=np.uint32)

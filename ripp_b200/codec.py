@@ -157,3 +157,44 @@ def gt_dec(a):
 def scalar_words(s, n=8):
     """Canonical (non-Montgomery) little-endian words of an integer scalar."""
     return _words(s, n)
+
+
+# ---- arkworks `serialize_uncompressed` of statement values (what the verifier entry points take) ----
+def ser_fr(v):
+    return (v % R).to_bytes(32, "little")
+
+
+def ser_gt(f):
+    """Fq12 in struct order c0.c0 .. c1.c2, each Fq little-endian canonical (PairingOutput)."""
+    return b"".join((c % P).to_bytes(48, "little") for k in _TOWER_ORDER for c in f[k])
+
+
+def ser_g1(pt):
+    """ark-bls12-381 uncompressed G1: big-endian x || y; identity = 0x40 then zeros."""
+    if pt is None:
+        return b"\x40" + bytes(95)
+    return pt[0].to_bytes(48, "big") + pt[1].to_bytes(48, "big")
+
+
+def ser_g2(pt):
+    if pt is None:
+        return b"\x40" + bytes(191)
+    (x0, x1), (y0, y1) = pt
+    return b"".join(v.to_bytes(48, "big") for v in (x1, x0, y1, y0))
+
+
+def ser_identity_output(item_bytes):
+    """IdentityOutput<T>(vec![t]) (dh_commitments/src/identity/mod.rs:33-62): u64 LE length, then the item."""
+    return (1).to_bytes(8, "little") + item_bytes
+
+
+def ser_value(v):
+    """Serialise a commitment / inner-product value by its Python shape: int = Fr, 6-tuple = GT,
+    None or a pair of ints = G1, a pair of pairs = G2."""
+    if isinstance(v, int):
+        return ser_fr(v)
+    if v is not None and len(v) == 6:
+        return ser_gt(v)
+    if v is None:
+        raise ValueError("ambiguous identity point: serialise with ser_g1 / ser_g2")
+    return ser_g1(v) if isinstance(v[0], int) else ser_g2(v)

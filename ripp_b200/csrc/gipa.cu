@@ -208,6 +208,27 @@ static int eval_products(ripp_ctx* ctx, int k, const Slice* xs, const Slice* ys,
   return RIPP_OK;
 }
 
+// gipa.rs:235-258 (prover) == :330-353 (verifier): Blake2b-512 over nonce_be(8) || previous c || the six
+// commitments of the round; x = u128_be(digest[0..16]); returns (c, c_inv) = (x^-1, x) -- swapped as gipa.rs:253-255.
+static void gipa_challenge(const Fr& prev, const Val* com, Fr* c, Fr* c_inv) {
+  for (uint64_t nonce = 0;; nonce++) {
+    Bytes h;
+    put_u64_be(h, nonce);
+    put_fr(h, prev);
+    for (int i = 0; i < 6; i++) {
+      if (i % 3 == 2) put_u64_le(h, 1);  // IdentityOutput<T>(Vec<T>) of length 1
+      put_val(h, com[i]);
+    }
+    uint8_t d[64];
+    ripp_hash::blake2b512(h.data(), h.size(), d);
+    *c_inv = fr_from_u128_be(d);
+    if (!c_inv->is_zero()) {
+      *c = c_inv->inv();
+      return;
+    }
+  }
+}
+
 static int fold_typed(ripp_ctx* ctx, int t, char* base, size_t split, const Fr& c) {
   if (t == VT_NONE || !base) return RIPP_OK;  // HomomorphicPlaceholderValue: no-op (identity/mod.rs:18-30)
   char* hi = base + split * vt_size(t);
@@ -274,22 +295,7 @@ static int gipa_prove(ripp_ctx* ctx, const GipaSpec& sp, const void* a_in, const
     if (trace_on()) fprintf(stderr, "[trace] gipa(a=%d,b=%d) n'=%zu products+prev folds %.2f ms\n", sp.a, sp.b, split, now_ms() - t_r0);
     // gipa.rs:235-258 -- Fiat-Shamir challenge
     Fr c, c_inv;
-    for (uint64_t nonce = 0;; nonce++) {
-      Bytes h;
-      put_u64_be(h, nonce);
-      put_fr(h, transcript.empty() ? Fr::zero() : transcript.back());
-      for (int i = 0; i < 6; i++) {
-        if (i % 3 == 2) put_u64_le(h, 1);  // IdentityOutput<T>(Vec<T>) of length 1
-        put_val(h, com[i]);
-      }
-      uint8_t d[64];
-      ripp_hash::blake2b512(h.data(), h.size(), d);
-      c_inv = fr_from_u128_be(d);
-      if (!c_inv.is_zero()) {
-        c = c_inv.inv();  // (c, c_inv) swapped as in gipa.rs:253-255
-        break;
-      }
-    }
+    gipa_challenge(transcript.empty() ? Fr::zero() : transcript.back(), com.data(), &c, &c_inv);
     // gipa.rs:261-291 -- rescale
     {
       ripp_ctx* k1 = ripp_child(ctx, 0);
@@ -746,3 +752,5 @@ extern "C" int ripp_sipp_prove(ripp_ctx* ctx, const void* a_aff, const void* b_a
   CU(cudaStreamSynchronize(ctx->stream));
   return copy_out(proof, proof_out, proof_cap, proof_len);
 }
+
+#include "verify.cuh"

@@ -327,6 +327,26 @@ RIPP_HD void exp_by_x(const Ctx& c, int dst, int a) {
   conj(c, dst, dst);
 }
 
+// acc = a^e for ANY a in Fq12 (generic squarings: verifier inputs are not trusted to be cyclotomic) and a
+// 256-bit canonical exponent e (8 words in the group's scratch).  `PairingOutput *= Fr` of the verifiers
+// (mul_helper on GT, gipa.rs:355-357; sipp/src/lib.rs:148-156).  Fixed 2-bit windows; the window digit
+// selects an operand ADDRESS (1, a, a^2, a^3), so groups with different exponents share one instruction stream.
+// a in register t1; clobbers t2, t3, one.
+RIPP_HD void pow_fr(const Ctx& c, int acc, int t1, int t2, int t3, int one, const uint32_t* e) {
+  set_one(c, one);
+  set_one(c, acc);
+  sqr(c, t2, t1);
+  mul(c, t3, t2, t1);
+#pragma unroll 1
+  for (int i = 127; i >= 0; i--) {
+    sqr(c, acc, acc);
+    sqr(c, acc, acc);
+    uint32_t w = (e[i >> 4] >> ((i & 15) * 2)) & 3u;
+    int src = w == 0 ? one : (w == 1 ? t1 : (w == 2 ? t2 : t3));
+    mul(c, acc, acc, src);
+  }
+}
+
 // Register 0 <- final_exponentiation(register 0) (ark-ec convention, see pairing.cuh); needs 8 registers.
 RIPP_HD void final_exp(const Ctx& c) {
   enum { F = 0, R = 1, Y0 = 2, Y1 = 3, Y2 = 4, T0 = 5, T1 = 6, T2 = 7 };

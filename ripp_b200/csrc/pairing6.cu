@@ -119,6 +119,69 @@ __global__ void __launch_bounds__(64) k_final_exp6(const Fq12* __restrict__ in, 
 }
 
 
+// out[i] = in[i]^sc[i] (GT exponentiation by an Fr scalar in Montgomery form); one group per element.
+// The verifiers' `mul_helper` on PairingOutput (ip_proofs/src/lib.rs:15-19 with T = GT; gipa.rs:355-357,
+// sipp/src/lib.rs:148-156).
+constexpr int GP_NREG = 5;
+constexpr int GP_GROUP_WORDS = group_words(GP_NREG, 0);
+__global__ void __launch_bounds__(32) k_gt_pow6(const Fq12* __restrict__ in, const Fr* __restrict__ sc, uint32_t n,
+                                                Fq12* __restrict__ out) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int g = lane / 6;
+  Ctx c{lane % 6, smem + g * GP_GROUP_WORDS};
+  uint32_t t = blockIdx.x * 5 + g;
+  bool live = g < 5 && t < n;
+  const Fq2* src = reinterpret_cast<const Fq2*>(in + (live ? t : 0));
+  st2(freg(c, 1) + c.k * FQ2W, src[tower_slot(c.k)]);
+  uint32_t* e = c.sm + OFF_LINE;  // the line slot is free here: holds the canonical exponent
+  if (c.k == 0) {
+    Fr s = live ? sc[t].from_mont() : Fr::zero();
+    for (int i = 0; i < 8; i++) e[i] = s.v[i];
+  }
+  __syncwarp();
+  pow_fr(c, 0, 1, 2, 3, 4, e);
+  if (live) reinterpret_cast<Fq2*>(out + t)[tower_slot(c.k)] = ld2(freg(c, 0) + c.k * FQ2W);
+}
+
+// out = prod_i in[i]^sc[i]  (device memory; in: n Fq12, sc: n Fr Montgomery)
+int ripp_gt_multiexp_l6(ripp_ctx* ctx, const void* in, const void* sc, size_t n, void* out) {
+  CU(cudaSetDevice(ctx->device));
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(k_reduce6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * R6_GROUP_WORDS * 4));
+    attr_done = true;
+  }
+  if (n == 0) {
+    Fq12 one = Fq12::one();
+    CU(cudaMemcpyAsync(out, &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RIPP_OK;
+  }
+  void *bufA, *bufB;
+  OK(scratch(ctx, 17, n * sizeof(Fq12) + 4096, &bufA));
+  OK(scratch(ctx, 18, n * sizeof(Fq12) / 4 + 8192, &bufB));
+  TimeScope ts_(ctx, RIPP_T_OTHER);
+  k_gt_pow6<<<(unsigned)((n + 4) / 5), 32, 6 * GP_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, (const Fr*)sc, (uint32_t)n,
+                                                                                  n == 1 ? (Fq12*)out : (Fq12*)bufA);
+  LAUNCHED(ctx);
+  const uint32_t R = 8;
+  Fq12 *src = (Fq12*)bufA, *dst = (Fq12*)bufB;
+  uint32_t T = (uint32_t)n;
+  while (T > 1) {
+    uint32_t To = (T + R - 1) / R;
+    Fq12* o = To == 1 ? (Fq12*)out : dst;
+    unsigned blk = (To + 5 * M6_WARPS - 1) / (5 * M6_WARPS);
+    k_reduce6<M6_WARPS><<<blk, 32 * M6_WARPS, M6_WARPS * 6 * R6_GROUP_WORDS * 4, ctx->stream>>>(src, T, R, To, o, To);
+    LAUNCHED(ctx);
+    Fq12* t = src;
+    src = dst;
+    dst = t;
+    T = To;
+  }
+  return RIPP_OK;
+}
+
 template <int KP>
 static int launch_miller6(ripp_ctx* ctx, Miller6Batch& b, size_t n, Fq12* dst, size_t* nwarps_out) {
   constexpr int SM = M6_WARPS * 6 * group_words(M6_NREG, KP) * 4;

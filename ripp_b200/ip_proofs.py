@@ -30,6 +30,26 @@ def _upload(ctx, kind, vecs):
     return out
 
 
+def _ser_com(com):
+    """(com_a, [com_b,] com_t) -> the byte string of include/ripp_b200.h: the last value is framed as IdentityOutput."""
+    *heads, com_t = com
+    if isinstance(com_t, (list,)):  # already an IdentityOutput-style one-element list
+        (com_t,) = com_t
+    return b"".join(codec.ser_value(c) for c in heads) + codec.ser_identity_output(codec.ser_value(com_t))
+
+
+def vsrs_enc(v_srs):
+    """VerifierSRS (tipa/mod.rs:88-94) -> packed g | h | g_beta | h_alpha (144 words)."""
+    return np.concatenate([codec.g1_enc(v_srs["g"]), codec.g2_enc(v_srs["h"]), codec.g1_enc(v_srs["g_beta"]),
+                           codec.g2_enc(v_srs["h_alpha"])])
+
+
+def vk_enc(vk):
+    """ark-groth16 VerifyingKey dict(alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1) -> packed words."""
+    return np.concatenate([codec.g1_enc(vk["alpha_g1"]), codec.g2_enc(vk["beta_g2"]), codec.g2_enc(vk["gamma_g2"]),
+                           codec.g2_enc(vk["delta_g2"])] + [codec.g1_enc(p) for p in vk["gamma_abc_g1"]])
+
+
 class GIPA:
     """GIPA<IP, LMC, RMC, IPC, Blake2b> for one of the instantiations in include/ripp_b200.h."""
 
@@ -45,6 +65,20 @@ class GIPA:
         a, b, v, w = _upload(self.ctx, self.kind, (m_a, m_b, ck[0], ck[1]))
         proof, tr, ckb = self.ctx.gipa_prove_dev(self.kind, a, b, v, w, n)
         return proof, codec.fr_vec_dec(tr), ckb
+
+    def verify(self, ck, com, proof, scalar_b=None):
+        """gipa.rs:135-160 (ck = (ck_a, ck_b), com = (com_a, com_b, com_t)); for the *_SSM kinds
+        structured_scalar_message.rs:86-127 (ck = (ck_a, None), com = (com_a, com_t), scalar_b).
+        com_t is the bare inner-product value; the IdentityOutput framing is added here.  -> bool"""
+        ck_a, ck_b = ck
+        n = len(ck_a)
+        _, _, tv, tw = _KIND_TYPES[self.kind]
+        if n == 0 or n & (n - 1) or (tw is not None and len(ck_b) != n):
+            raise InnerProductArgumentError("left length, right length: %d, %d" % (n, 0 if ck_b is None else len(ck_b)))
+        v = self.ctx.to_device(_ENC[tv](ck_a))
+        w = None if tw is None else self.ctx.to_device(_ENC[tw](ck_b))
+        sb = None if scalar_b is None else codec.fr_enc(scalar_b).copy()
+        return self.ctx.gipa_verify_dev(self.kind, v, w, n, _ser_com(com), proof, sb)
 
 
 class TIPA:
@@ -67,6 +101,17 @@ class TIPA:
     def prove(self, srs, values, ck):
         return self.prove_with_srs_shift(srs, values, ck, 1)
 
+    def verify_with_srs_shift(self, v_srs, com, proof, r_shift=1):
+        """tipa/mod.rs:242-301.  v_srs = dict(g, h, g_beta, h_alpha); com = (com_a, com_b, com_t).  -> bool"""
+        return self.ctx.tipa_verify(self.kind, vsrs_enc(v_srs), _ser_com(com), proof, codec.fr_enc(r_shift).copy())
+
+    def verify(self, v_srs, com, proof):
+        return self.verify_with_srs_shift(v_srs, com, proof, 1)
+
+    def verify_with_structured_scalar_message(self, v_srs, com, scalar_b, proof):
+        """structured_scalar_message.rs:270-331 (the *_SSM kinds).  com = (com_a, com_t).  -> bool"""
+        return self.ctx.tipa_verify(self.kind, vsrs_enc(v_srs), _ser_com(com), proof, codec.fr_enc(scalar_b).copy())
+
 
 def aggregate_proofs(srs, proofs, ctx=None):
     """groth16_aggregation.rs:77-160.  srs = (g_alpha_powers, h_beta_powers); proofs = [(A, B, C)]."""
@@ -78,3 +123,12 @@ def aggregate_proofs(srs, proofs, ctx=None):
     s1 = ctx.to_device(codec.g1_vec_enc(srs[0]))
     s2 = ctx.to_device(codec.g2_vec_enc(srs[1]))
     return ctx.tipp_aggregate_dev(s1, s2, a, b, c, n)
+
+
+def verify_aggregate_proof(v_srs, vk, public_inputs, proof, ctx=None):
+    """groth16_aggregation.rs:162-231.  public_inputs: one list of Fr per proof; proof: aggregate_proofs' bytes.  -> bool"""
+    ctx = ctx or default_context()
+    n, m = len(public_inputs), len(public_inputs[0])
+    assert len(vk["gamma_abc_g1"]) == m + 1  # :214
+    inp = np.ascontiguousarray(np.stack([codec.fr_vec_enc(row) for row in public_inputs]).reshape(n, m, 8))
+    return ctx.tipp_verify_aggregate(vsrs_enc(v_srs), np.ascontiguousarray(vk_enc(vk)), inp, proof)

@@ -24,3 +24,11 @@ class SIPP:
         ctx = ctx or default_context()
         ea, eb, er = _enc(a, b, r)
         return ctx.sipp_prove(ea, eb, er, np.ascontiguousarray(codec.gt_enc(value)))
+
+    @staticmethod
+    def verify(a, b, r, claimed_value, proof, ctx=None):
+        """sipp/src/lib.rs:109-180 -> bool."""
+        assert len(a) == len(b) and len(a) >= 2 and bin(len(a)).count("1") == 1  # lib.rs:117-120
+        ctx = ctx or default_context()
+        ea, eb, er = _enc(a, b, r)
+        return ctx.sipp_verify(ea, eb, er, np.ascontiguousarray(codec.gt_enc(claimed_value)), proof)

@@ -123,6 +123,13 @@ void hs_l6_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
       case 6: l6::exp_by_x(c, 2, 0); break;
       case 7: l6::final_exp(c); l6::copy(c, 2, 0); break;
       case 8: l6::cyc_sqr(c, 2, 0); break;
+      case 9: {  // pow_fr: exponent = first 8 words of b (canonical)
+        if (c.k == 0) for (int i = 0; i < 8; i++) c.sm[l6::OFF_LINE + i] = b[i];
+        l6::sync(c);
+        l6::copy(c, 1, 0);
+        l6::pow_fr(c, 2, 1, 3, 4, 5, c.sm + l6::OFF_LINE);
+        break;
+      }
     }
     l6_store_reg(c, 2, r);
   });

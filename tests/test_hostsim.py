@@ -146,6 +146,13 @@ def test_l6_six_lane_fq12(hostsim):
     ec = C.gt_enc(c)
     assert op(8, ec, ec) == E.f12_sqr(c)  # Granger-Scott squaring in the flat basis
     assert op(6, ec, ec) == E.f12_cyc_pow(c, E.X)
+    # pow_fr: generic a^e with a 256-bit canonical exponent (the verifiers' GT scalar multiplication)
+    import numpy as np
+
+    for e in (0, 1, 2, 3, rnd.randrange(E.R), E.R - 1):
+        ew = np.zeros(144, dtype=np.uint32)
+        ew[:8] = C.scalar_words(e)
+        assert op(9, ea, ew) == E.f12_pow(a, e)
 
 
 def test_l6_miller_and_final_exp(hostsim):
