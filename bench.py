@@ -10,7 +10,8 @@ opening MSMs, Fiat-Shamir hashing on the host.  Metric: prove seconds (lower is 
   value        device-resident inputs, CUDA events on the library's stream, L2 flushed between steps
   e2e          the same aggregation through the host-pointer C-ABI call (ripp_tipp_aggregate): Groth16
                proofs in pinned host memory, H2D + kernels + D2H of the proof bytes, wall clock
-  sub_metrics  the two leaf throughputs the metric string also names, measured in the same run:
+  sub_metrics  verify_aggregate_proof of the emitted proof on the GPU (must accept), and
+               the two leaf throughputs the metric string also names, measured in the same run:
                multi-Miller pairs/s (configs[1], 2^16 pairs per GPU) and G1 MSM points/s (configs[2] leaf,
                2^18 points per GPU), sharded by input slices with an NCCL all-gather of the per-rank
                partials when N > 1
@@ -44,6 +45,8 @@ MAC32_PER_FQ_MUL = 300
 LOG_PROOFS = 12
 LOG_PAIRS = 16
 LOG_MSM = 18
+# per-launch DRAM traffic of the kernel classes measured once with `ncu --set full` (profiles/README.md)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"fold": 82176, "miller": 19165440, "msm": 109165824}
 METRIC = "tipp_groth16_aggregate_prove_seconds_at_2^12_proofs"
 DTYPE = "u32-limb Montgomery (BLS12-381 Fq 381-bit / Fr 255-bit)"
 
@@ -209,8 +212,17 @@ def main():
         host_proof = ctx.tipp_aggregate(inst["srs_g1"], inst["srs_g2"], a_np, b_np, c_np)
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
 
-    # ---- leaf throughputs (sharded by input slices; one partial per rank all-gathered) -------------
+    # ---- the verifier of the same statement on the GPU (groth16_aggregation.rs:162-231) -------------
     sub = {}
+    assert ctx.tipp_verify_aggregate(inst["vsrs"], inst["vk"], inst["inputs"], host_proof), "aggregate proof rejected"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.tipp_verify_aggregate(inst["vsrs"], inst["vk"], inst["inputs"], host_proof)
+    sub["verify_aggregate_s"] = {"value": max_over_ranks((time.perf_counter() - t0) / e2e_steps), "proofs_per_gpu": n,
+                                 "accepted": True, "timing": "wall clock through the host-pointer C ABI"}
+
+    # ---- leaf throughputs (sharded by input slices; one partial per rank all-gathered) -------------
     miller_k_ms = None
     if not args.no_sub_metrics:
         npairs = 1 << LOG_PAIRS
@@ -284,7 +296,10 @@ def main():
         "bound": "int32 multiply pipe (IMAD.WIDE.U32: one 32x32+64 MAC per lane-instruction)",
         "kernel": "%s kernels of one aggregation (%d timed scopes)" % (dom, dom_launches),
         "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TMAC32/s", "frac": achieved / imad_peak,
-        "traffic": None, "kernel_ms": dom_ms,
+        # dram__bytes_read + write per launch of the dominant class from the committed `ncu --set full` capture
+        # (profiles/r1c_ncu_fold_raw.csv: 63 KB G1 / 101 KB G2 per late-round fold launch; Miller 2^16: 19 MB)
+        "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(dom), "traffic_source": "profiles/r1c_ncu_*_raw.csv (static, from the committed ncu capture)",
+        "kernel_ms": dom_ms,
         "peak_source": "ripp_bench_imad in this run: independent IMAD.WIDE.U32 chains, all SMs",
         "peak_imad32_tmacs": imad32_peak / 1e12, "peak_carry_chain_tmacs": chain_peak / 1e12,
         "step_breakdown_ms": {c: round(breakdown[c][0], 3) for c in breakdown},

@@ -432,6 +432,52 @@ __global__ void __launch_bounds__(256) k_imad(uint32_t* out, int iters, uint32_t
 #pragma unroll
     for (int j = 0; j < 8; j++) s ^= acc[j];
     if (s == 0x1234567) out[0] = s;
+  } else if (KIND == 3) {
+    // carry OUT only: independent 64-bit accumulators, the carry of every product counted by an ALU-pipe addc
+    uint64_t acc[8];
+    uint32_t cnt[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      acc[j] = a + j;
+      cnt[j] = 0;
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          limb::mw_cc(acc[j], a + u, b + j, acc[j]);
+          limb::addc(cnt[j], cnt[j], 0);
+        }
+      }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= acc[j] + cnt[j];
+    if (s == 0x1234567) out[0] = (uint32_t)s;
+  } else if (KIND == 4) {
+    // carry IN only: an ALU-pipe add.cc produces the carry each IMAD.WIDE.X consumes; no carry out
+    uint64_t acc[8];
+    uint32_t src[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      acc[j] = a + j;
+      src[j] = b + j;
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          limb::add_cc(src[j], src[j], a);
+          limb::mwc(acc[j], a + u, b + j, acc[j]);
+        }
+      }
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= acc[j] + src[j];
+    if (s == 0x1234567) out[0] = (uint32_t)s;
   } else {
     // carry-chained pairs exactly as mont_row issues them: 2 independent chains of 8 limbs
     uint32_t x[8], y[8];
@@ -486,6 +532,10 @@ extern "C" int ripp_bench_imad(ripp_ctx* ctx, int kind, int iters, double* macs_
       k_imad<0><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, 12345u + rep);
     else if (kind == 1)
       k_imad<1><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, 12345u + rep);
+    else if (kind == 3)
+      k_imad<3><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, 12345u + rep);
+    else if (kind == 4)
+      k_imad<4><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, 12345u + rep);
     else
       k_imad<2><<<blocks, threads, 0, ctx->stream>>>((uint32_t*)out, iters, 12345u + rep);
     LAUNCHED(ctx);

@@ -82,9 +82,21 @@ def tipp_instance_dev(ctx, n, seed=0):
     for _ in range(m - 1):
         pa.append(pa[-1] * alpha % R)
         pb.append(pb[-1] * beta % R)
-    _, _, proofs, _ = groth16_scalars(n, seed=seed)
+    vk, ic, proofs, inputs = groth16_scalars(n, seed=seed)
+    # verifier material (tipa/mod.rs:120-127 VerifierSRS; ark-groth16 VerifyingKey), packed as include/ripp_b200.h
+    # lays it out: g | h | g_beta | h_alpha and alpha_g1 | beta_g2 | gamma_g2 | delta_g2 | gamma_abc_g1[]
+    g1s = _gen_dev(ctx, 1, [1, beta, vk["alpha"]] + ic)
+    g2s = _gen_dev(ctx, 2, [1, alpha, vk["beta"], vk["gamma"], vk["delta"]])
+    h1 = g1s.download((3 + len(ic), 24))
+    h2 = g2s.download((5, 48))
+    g1s.free()
+    g2s.free()
+    vsrs = np.concatenate([h1[0], h2[0], h1[1], h2[1]])
+    vk_words = np.concatenate([h1[2], h2[2], h2[3], h2[4]] + [h1[3 + j] for j in range(len(ic))])
     return {
         "srs_g1": _gen_dev(ctx, 1, pa), "srs_g2": _gen_dev(ctx, 2, pb),
         "a": _gen_dev(ctx, 1, [p[0] for p in proofs]), "b": _gen_dev(ctx, 2, [p[1] for p in proofs]),
         "c": _gen_dev(ctx, 1, [p[2] for p in proofs]),
+        "vsrs": np.ascontiguousarray(vsrs), "vk": np.ascontiguousarray(vk_words),
+        "inputs": np.ascontiguousarray(np.stack([codec.fr_vec_enc(x) for x in inputs])),
     }

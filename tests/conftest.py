@@ -40,11 +40,12 @@ class HostSim:
 @pytest.fixture(scope="session")
 def hostsim():
     src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
-    so = os.path.join(ROOT, "tests", "hostsim", "_hostsim.so")
+    flags = os.environ.get("RIPP_HOSTSIM_FLAGS", "").split()  # e.g. -DRIPP_L6_SHARED_CODE=0 to test the inlined engine
+    so = os.path.join(ROOT, "tests", "hostsim", "_hostsim%s.so" % ("_" + str(abs(hash(tuple(flags))) % 10**6) if flags else ""))
     csrc = os.path.join(ROOT, "ripp_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-o", so, src], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC"] + flags + ["-o", so, src], check=True)
     return HostSim(ctypes.CDLL(so))
 
 
