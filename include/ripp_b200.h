@@ -92,6 +92,16 @@ int ripp_miller_partial_dev(ripp_ctx* ctx, const void* g1_aff_dev, const void* g
  * apply the single shared final exponentiation (lib.rs:115). */
 int ripp_gt_combine_dev(ripp_ctx* ctx, const void* fq12_partials_dev, size_t count, void* gt_out_dev);
 
+/* Batch forms for the sharded provers (SURVEY.md §8e "GIPA rounds"): the six products of a GIPA
+ * round (gipa.rs:220-231) over this rank's share in ONE Miller launch, no final exponentiation ... */
+int ripp_miller_partial_batch_dev(ripp_ctx* ctx, int nseg, const void* const* g1_aff_dev, const void* const* g2_aff_dev,
+                                  size_t n, void* fq12_out_dev);
+/* ... and out[s] = final_exponentiation(prod_r partials[s * count + r]) for the gathered per-rank partials. */
+int ripp_gt_combine_batch_dev(ripp_ctx* ctx, const void* fq12_partials_dev, size_t count, int nseg, void* gt_out_dev);
+/* out[s] = sum_r in[s * count + r]: per-rank MSM / scalar partials added in rank order.
+ * type: 1 = G1 affine, 2 = G2 affine, 3 = Fr. */
+int ripp_seg_sum_dev(ripp_ctx* ctx, int type, const void* in_dev, size_t count, int nseg, void* out_dev);
+
 /* MultiexponentiationInnerProduct::inner_product (lib.rs:123-142) == G::msm(normalize_batch(left), right),
  * also PedersenCommitment::commit (dh_commitments/src/pedersen/mod.rs:24-26).  Host pointers:
  * bases Jacobian, scalars Fr (Montgomery), result Jacobian (Z = 1, or Z = 0 for the identity). */
@@ -155,6 +165,11 @@ int ripp_kzg_open_g1_dev(ripp_ctx* ctx, const void* srs_g1_dev, size_t n_srs, co
                          const void* r_shift, const void* z, void* g1_aff_out);
 int ripp_kzg_open_g2_dev(ripp_ctx* ctx, const void* srs_g2_dev, size_t n_srs, const void* transcript, size_t k,
                          const void* r_shift, const void* z, void* g2_aff_out);
+
+/* The quotient coefficients q = (f - f(z)) / (X - z) of the opening above (tipa/mod.rs:313-332), host in / host
+ * out (n_srs Fr, Montgomery, zero padded): with them every rank of a sharded prover runs the opening MSM over its
+ * own slice of the SRS powers and the partial points are summed (SURVEY.md §8e "KZG openings"). */
+int ripp_kzg_quotient(const void* transcript, size_t k, const void* r_shift, const void* z, size_t n_srs, void* fr_out);
 
 /* TIPA::prove_with_srs_shift (tipa/mod.rs:176-231) for kinds with a G1 right key, and
  * TIPAWithSSM::prove_with_structured_scalar_message (structured_scalar_message.rs:211-268) for the

@@ -281,6 +281,31 @@ class Context:
                                     ctypes.c_size_t(cap), ctypes.byref(plen)))
         return proof[: plen.value].tobytes()
 
+    # ---- batch primitives of the sharded provers (parallel.py) ---------------------------------------
+    def miller_partial_batch_dev(self, g1_ptrs, g2_ptrs, n, out_dev):
+        k = len(g1_ptrs)
+        a1 = (ctypes.c_void_p * k)(*[int(_p(x).value or 0) for x in g1_ptrs])
+        a2 = (ctypes.c_void_p * k)(*[int(_p(x).value or 0) for x in g2_ptrs])
+        check(lib().ripp_miller_partial_batch_dev(self.handle, k, a1, a2, ctypes.c_size_t(n), _p(out_dev)))
+
+    def gt_combine_batch_dev(self, partials_dev, count, nseg, out_dev):
+        check(lib().ripp_gt_combine_batch_dev(self.handle, _p(partials_dev), ctypes.c_size_t(count), int(nseg), _p(out_dev)))
+
+    def seg_sum_dev(self, type_id, in_dev, count, nseg, out_dev):
+        """type_id: 1 = G1 affine, 2 = G2 affine, 3 = Fr."""
+        check(lib().ripp_seg_sum_dev(self.handle, int(type_id), _p(in_dev), ctypes.c_size_t(count), int(nseg), _p(out_dev)))
+
+    def scalar_ip_dev(self, a_dev, b_dev, n, out_dev):
+        check(lib().ripp_scalar_ip_dev(self.handle, _p(a_dev), _p(b_dev), ctypes.c_size_t(n), _p(out_dev)))
+
+    def kzg_quotient(self, transcript, r_shift, z, n_srs):
+        """-> (n_srs, 8) uint32 Montgomery Fr: coefficients of (f - f(z)) / (X - z), zero padded (tipa/mod.rs:313-332)."""
+        transcript = np.ascontiguousarray(transcript, dtype=np.uint32)
+        out = np.zeros((n_srs, 8), dtype=np.uint32)
+        check(lib().ripp_kzg_quotient(_p(transcript), ctypes.c_size_t(len(transcript)), _p(r_shift), _p(z),
+                                      ctypes.c_size_t(n_srs), _p(out)))
+        return out
+
     # ---- verifiers --------------------------------------------------------------------------------
     def gt_multiexp_dev(self, gt_dev, fr_dev, n, out_dev):
         check(lib().ripp_gt_multiexp_dev(self.handle, _p(gt_dev), _p(fr_dev), ctypes.c_size_t(n), _p(out_dev)))

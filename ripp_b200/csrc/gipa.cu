@@ -396,6 +396,22 @@ static std::vector<Fr> kzg_quotient(const std::vector<Fr>& transcript, const Fr&
   return q;
 }
 
+// The quotient coefficients alone (host in, host out): the sharded KZG opening lets every rank run the MSM over
+// its slice of the SRS powers (SURVEY.md §8e "KZG openings").
+extern "C" int ripp_kzg_quotient(const void* transcript, size_t k, const void* r_shift, const void* z, size_t n_srs,
+                                 void* fr_out) {
+  if (!transcript || !r_shift || !z || !fr_out) return fail(RIPP_ERR_ARG, "null argument");
+  if (n_srs != 2 * ((size_t)1 << k) - 1) return fail(RIPP_ERR_ARG, "SRS length must be 2*2^k - 1");
+  std::vector<Fr> t(k);
+  memcpy(t.data(), transcript, k * sizeof(Fr));
+  Fr rs, zz;
+  memcpy(rs.v, r_shift, 32);
+  memcpy(zz.v, z, 32);
+  std::vector<Fr> q = kzg_quotient(t, rs, zz, n_srs);
+  memcpy(fr_out, q.data(), n_srs * sizeof(Fr));
+  return RIPP_OK;
+}
+
 template <class F>
 static int kzg_open(ripp_ctx* ctx, const void* srs_dev, size_t n_srs, const std::vector<Fr>& transcript, const Fr& r_shift,
                     const Fr& z, Aff<F>* out_host) {

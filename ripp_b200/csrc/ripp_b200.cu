@@ -719,6 +719,50 @@ extern "C" int ripp_gt_combine_dev(ripp_ctx* ctx, const void* partials, size_t c
   return RIPP_OK;
 }
 
+// ---- batch primitives of the sharded (multi-GPU) provers: DESIGN.md §5 ---------------------------------------
+// nseg Miller partials (no final exponentiation) of equal-length vector pairs in one launch
+extern "C" int ripp_miller_partial_batch_dev(ripp_ctx* ctx, int nseg, const void* const* g1_aff_dev,
+                                             const void* const* g2_aff_dev, size_t n, void* fq12_out_dev) {
+  if (!ctx || !fq12_out_dev || !g1_aff_dev || !g2_aff_dev) return fail(RIPP_ERR_ARG, "null argument");
+  return ripp_pairing_batch_l6(ctx, nseg, g1_aff_dev, g2_aff_dev, n, fq12_out_dev, false);
+}
+// out[s] = final_exponentiation(prod_r partials[s * count + r]), s < nseg
+extern "C" int ripp_gt_combine_batch_dev(ripp_ctx* ctx, const void* partials, size_t count, int nseg, void* out) {
+  if (!ctx || !out || !partials || count == 0 || nseg <= 0) return fail(RIPP_ERR_ARG, "bad argument");
+  return ripp_final_exp_l6(ctx, partials, (uint32_t)count, out, nseg);
+}
+// out[s] = sum_r in[s * count + r] (G1 / G2 affine points or Fr), one thread per segment
+template <class F>
+__global__ void k_aff_seg_sum(const Aff<F>* __restrict__ in, uint32_t count, int nseg, Aff<F>* __restrict__ out) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  Jac<F> acc = Jac<F>::inf();
+  for (uint32_t r = 0; r < count; r++) acc = acc.add_mixed(in[(size_t)s * count + r]);
+  out[s] = acc.is_inf() ? Aff<F>::inf() : acc.to_affine();
+}
+__global__ void k_fr_seg_sum(const Fr* __restrict__ in, uint32_t count, int nseg, Fr* __restrict__ out) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  Fr acc = Fr::zero();
+  for (uint32_t r = 0; r < count; r++) acc = acc + in[(size_t)s * count + r];
+  out[s] = acc;
+}
+extern "C" int ripp_seg_sum_dev(ripp_ctx* ctx, int type, const void* in, size_t count, int nseg, void* out) {
+  if (!ctx || !in || !out || count == 0 || nseg <= 0) return fail(RIPP_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(ctx->device));
+  unsigned blk = (unsigned)((nseg + 31) / 32);
+  if (type == 1)
+    k_aff_seg_sum<Fq><<<blk, 32, 0, ctx->stream>>>((const G1Aff*)in, (uint32_t)count, nseg, (G1Aff*)out);
+  else if (type == 2)
+    k_aff_seg_sum<Fq2><<<blk, 32, 0, ctx->stream>>>((const G2Aff*)in, (uint32_t)count, nseg, (G2Aff*)out);
+  else if (type == 3)
+    k_fr_seg_sum<<<blk, 32, 0, ctx->stream>>>((const Fr*)in, (uint32_t)count, nseg, (Fr*)out);
+  else
+    return fail(RIPP_ERR_ARG, "type must be 1 (G1), 2 (G2) or 3 (Fr)");
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}
+
 extern "C" int ripp_pairing_ip_dev(ripp_ctx* ctx, const void* g1, const void* g2, size_t n, void* out) {
   if (!ctx || !out || (n && (!g1 || !g2))) return fail(RIPP_ERR_ARG, "null argument");
   CU(cudaSetDevice(ctx->device));

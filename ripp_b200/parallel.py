@@ -24,3 +24,265 @@ def sharded_pairing_ip(ctx, g1_dev, g2_dev, n_local, out_ptr, scratch):
     ctx.miller_partial_dev(g1_dev, g2_dev, n_local, partial.data_ptr())
     dist.all_gather_into_tensor(gathered, partial)
     ctx.gt_combine_dev(gathered.data_ptr(), world, out_ptr)
+
+
+# =====================================================================================================
+# Sharded GIPA / TIPA provers (SURVEY.md §8e "GIPA rounds", "KZG openings")
+# =====================================================================================================
+# Cyclic partition: with g ranks, rank k holds the elements with global index i = j g + k (local index j) of
+# all four vectors.  A round pairs global index i of the left half with i + n' of the right half
+# (gipa.rs:209-217); while g divides n', both live on the same rank and at local indices j and j + n'/g, so the
+# six products of the round are products over LOCAL halves, the four folds are local, and the folded element i
+# stays on rank i mod g: the only exchange per round is one all-gather of six fixed-size partials (<= 576 B
+# each), combined on every rank in rank order (GT: product of Miller values, then ONE final exponentiation per
+# commitment; points / scalars: sum).  When one element per rank is left the vectors (g elements) are
+# all-gathered once and every rank finishes the last log2(g) rounds redundantly.  The Fiat-Shamir hash is
+# computed identically on every rank from the combined values, so all ranks emit the same proof bytes -- the
+# bytes ripp_gipa_prove_dev emits on one GPU.
+#
+# Host side (this file): transcript, serialisation, hashing, torch.distributed.  Every group / field operation
+# on vectors runs in the CUDA library through the C ABI (no CPU fallback; the context fails without a GPU).
+import hashlib
+
+from . import codec
+
+_KIND_TYPES = {0: ("G1", "G2", "G2", "G1"), 1: ("G1", "Fr", "G2", "G1"), 2: ("G1", "Fr", "G2", None),
+               3: ("Fr", "Fr", "G2", "G2"), 4: ("Fr", "Fr", "G2", "G1"), 5: ("Fr", "Fr", "G2", None)}
+_WORDS = {"G1": 24, "G2": 48, "Fr": 8, "GT": 144}
+_SUM_ID = {"G1": 1, "G2": 2, "Fr": 3}
+_DEC = {"G1": codec.g1_dec, "G2": codec.g2_dec, "Fr": codec.fr_dec, "GT": codec.gt_dec}
+_SER = {"G1": codec.ser_g1, "G2": codec.ser_g2, "Fr": codec.ser_fr, "GT": codec.ser_gt}
+
+
+def ip_out_type(x, y):
+    """Output type of IP(x, y): pairing -> GT, placeholder -> Fr (zero), scalar x scalar -> Fr, else the point type."""
+    if {x, y} == {"G1", "G2"}:
+        return "GT"
+    if x is None or y is None or (x == "Fr" and y == "Fr"):
+        return "Fr"
+    return y if x == "Fr" else x
+
+
+def cyclic_share(vec, rank, world):
+    """Rank's share of a global vector under the cyclic partition (elements rank, rank + world, ...)."""
+    return vec[rank::world]
+
+
+def gipa_challenge(prev_c, com_bytes):
+    """gipa.rs:235-258: Blake2b-512(nonce_be || prev c || six commitments); x = u128_be(digest[..16]);
+    returns (c, c_inv) = (x^-1, x) -- swapped as gipa.rs:253-255."""
+    nonce = 0
+    while True:
+        d = hashlib.blake2b(nonce.to_bytes(8, "big") + codec.ser_fr(prev_c) + com_bytes, digest_size=64).digest()
+        x = int.from_bytes(d[:16], "big")
+        if x % codec.R:
+            return pow(x, -1, codec.R), x
+        nonce += 1
+
+
+def challenge_from_random_bytes(parts):
+    """tipa/mod.rs:195-209: hash(nonce_be || parts) until Fp::from_random_bytes accepts (32 bytes LE, top bit cleared, < r)."""
+    nonce = 0
+    while True:
+        d = hashlib.blake2b(nonce.to_bytes(8, "big") + parts, digest_size=64).digest()
+        v = int.from_bytes(d[:32], "little") & ((1 << 255) - 1)
+        if v < codec.R:
+            return v
+        nonce += 1
+
+
+class Comm:
+    """All-gather of one fixed-size device blob per rank.  NCCL: device tensors straight over NVLink.  Any other
+    backend (gloo in the single-GPU tests): staged through the host."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist, self.group = dist, group
+        self.on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if self.on else 1
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.device_native = self.on and dist.get_backend(group) == "nccl"
+
+    def all_gather(self, t):
+        """t: contiguous device tensor -> (world, *t.shape) device tensor, rank order."""
+        import torch
+
+        if self.world == 1:
+            return t.unsqueeze(0)
+        if self.device_native:
+            out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+            self.dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group)
+            return out
+        torch.cuda.current_stream().synchronize()
+        host = t.cpu()
+        outs = [torch.empty_like(host) for _ in range(self.world)]
+        self.dist.all_gather(outs, host, group=self.group)
+        return torch.stack(outs).to(t.device)
+
+
+class ShardedGIPA:
+    """GIPA::prove_with_aux (gipa.rs:162-312) over vectors partitioned cyclically across the ranks of `comm`.
+    Vectors are torch int32 CUDA tensors (n_local, words) in the C ABI's packed layout (affine points / Fr,
+    Montgomery); the context must run on torch's current stream (ctx.set_stream)."""
+
+    def __init__(self, kind, ctx, comm=None):
+        self.kind, self.ctx, self.comm = kind, ctx, comm or Comm()
+        self.ta, self.tb, self.tv, self.tw = _KIND_TYPES[kind]
+        # (x type, y type) of the three products of a commitment triple: IP(A, v), IP(w, B), IP(A, B)
+        self.prod_types = [(self.ta, self.tv), (self.tw, self.tb), (self.ta, self.tb)]
+        self.out_types = [ip_out_type(x, y) for x, y in self.prod_types]
+
+    # -- six partial products over local halves -> combined values on every rank ------------------------
+    def _round_products(self, A, B, V, W, split, count_ranks):
+        import torch
+
+        ctx = self.ctx
+        dev = A.device
+        parts = torch.zeros((6, 144), dtype=torch.int32, device=dev)
+        lo = lambda t: None if t is None else t[:split]
+        hi = lambda t: None if t is None else t[split:2 * split]
+        # gipa.rs:220-231: com_1 = (IP(A_R, v_L), IP(w_R, B_L), IP(A_R, B_L)); com_2 = (IP(A_L, v_R), IP(w_L, B_R), IP(A_L, B_R))
+        xs = [hi(A), hi(W), hi(A), lo(A), lo(W), lo(A)]
+        ys = [lo(V), lo(B), lo(B), hi(V), hi(B), hi(B)]
+        types = self.prod_types * 2
+        outs = self.out_types * 2
+        gt_slots = [i for i in range(6) if outs[i] == "GT"]
+        if gt_slots:
+            g1p, g2p = [], []
+            for i in gt_slots:
+                x_is_g1 = types[i][0] == "G1"
+                g1p.append((xs[i] if x_is_g1 else ys[i]).data_ptr())
+                g2p.append((ys[i] if x_is_g1 else xs[i]).data_ptr())
+            tmp = torch.zeros((len(gt_slots), 144), dtype=torch.int32, device=dev)
+            ctx.miller_partial_batch_dev(g1p, g2p, split, tmp.data_ptr())
+            parts[gt_slots] = tmp
+        for i in range(6):
+            tx, ty = types[i]
+            if outs[i] == "GT" or tx is None or ty is None:
+                continue  # placeholder commitment: Fr zero
+            if tx == "Fr" and ty == "Fr":
+                ctx.scalar_ip_dev(xs[i].data_ptr(), ys[i].data_ptr(), split, parts[i].data_ptr())
+            else:
+                pts, sc = (ys[i], xs[i]) if tx == "Fr" else (xs[i], ys[i])
+                fn = ctx.msm_g1_dev if outs[i] == "G1" else ctx.msm_g2_dev
+                fn(pts.data_ptr(), sc.data_ptr(), split, parts[i].data_ptr())
+        if count_ranks > 1:
+            gathered = self.comm.all_gather(parts).permute(1, 0, 2).contiguous()  # (6, world, 144)
+        else:
+            gathered = parts.unsqueeze(1).contiguous()
+        combined = torch.zeros((6, 144), dtype=torch.int32, device=dev)
+        cnt = gathered.shape[1]
+        if gt_slots:
+            src = gathered[gt_slots].contiguous()
+            dst = torch.zeros((len(gt_slots), 144), dtype=torch.int32, device=dev)
+            ctx.gt_combine_batch_dev(src.data_ptr(), cnt, len(gt_slots), dst.data_ptr())
+            combined[gt_slots] = dst
+        for t in ("G1", "G2", "Fr"):
+            slots = [i for i in range(6) if outs[i] == t and types[i][0] is not None and types[i][1] is not None]
+            if not slots:
+                continue
+            w = _WORDS[t]
+            src = gathered[slots][:, :, :w].contiguous()
+            dst = torch.zeros((len(slots), w), dtype=torch.int32, device=dev)
+            ctx.seg_sum_dev(_SUM_ID[t], src.data_ptr(), cnt, len(slots), dst.data_ptr())
+            combined[slots, :w] = dst
+        torch.cuda.current_stream().synchronize()
+        host = combined.cpu().numpy().view(np.uint32)
+        return [_DEC[outs[i]](host[i, :_WORDS[outs[i]]]) for i in range(6)], outs
+
+    def _ser_triples(self, vals, outs):
+        b = b""
+        for i in range(6):
+            s = _SER[outs[i]](vals[i])
+            b += codec.ser_identity_output(s) if i % 3 == 2 else s
+        return b
+
+    def _fold(self, t, typ, split, c):
+        if t is None:
+            return
+        cw = codec.fr_enc(c).copy()
+        fn = {"G1": self.ctx.g1_fold_dev, "G2": self.ctx.g2_fold_dev, "Fr": self.ctx.fr_fold_dev}[typ]
+        fn(t[split:2 * split].data_ptr(), t[:split].data_ptr(), cw, split, t[:split].data_ptr())
+
+    def prove_with_aux_dev(self, a, b, v, w=None):
+        """-> (GIPAProof bytes, r_transcript ints (reversed, as GIPAAux), ck_base bytes, (a0, b0, v0, w0) values)."""
+        import torch
+
+        world = self.comm.world
+        m = a.shape[0]
+        if m == 0 or m & (m - 1) or world & (world - 1):
+            raise ValueError("local length and world size must be powers of two (gipa.rs:116-122)")
+        A, B, V = a.clone(), b.clone(), v.clone()  # gipa.rs:175-176 clones all four vectors
+        W = None if self.tw is None else w.clone()
+        replicated = world == 1
+        steps, transcript = [], []
+        while True:
+            if not replicated and m == 1:
+                # one element per rank left: all-gather the vectors (global order = rank order) and finish everywhere
+                A, B, V = (self.comm.all_gather(t[0]).contiguous() for t in (A, B, V))
+                W = None if W is None else self.comm.all_gather(W[0]).contiguous()
+                m, replicated = world, True
+            if m == 1:
+                break
+            split = m // 2
+            vals, outs = self._round_products(A, B, V, W, split, 1 if replicated else world)
+            com_bytes = self._ser_triples(vals, outs)
+            c, c_inv = gipa_challenge(transcript[-1] if transcript else 0, com_bytes)
+            # gipa.rs:261-291: A <- A_R c + A_L, B <- B_R c^-1 + B_L, v <- v_R c^-1 + v_L, w <- w_R c + w_L
+            self._fold(A, self.ta, split, c)
+            self._fold(B, self.tb, split, c_inv)
+            self._fold(V, self.tv, split, c_inv)
+            self._fold(W, self.tw, split, c)
+            steps.append(com_bytes)
+            transcript.append(c)
+            m = split
+        torch.cuda.current_stream().synchronize()
+        base = []
+        for t, typ in ((A, self.ta), (B, self.tb), (V, self.tv), (W, self.tw)):
+            base.append(None if t is None else _DEC[typ](t[0].cpu().numpy().view(np.uint32)))
+        a0, b0, v0, w0 = base
+        proof = len(steps).to_bytes(8, "little") + b"".join(reversed(steps)) + _SER[self.ta](a0) + _SER[self.tb](b0)
+        ck_base = _SER[self.tv](v0) + (b"" if self.tw is None else _SER[self.tw](w0))
+        return proof, transcript[::-1], ck_base, (a0, b0, v0, w0)
+
+
+class ShardedTIPA:
+    """TIPA::prove_with_srs_shift (tipa/mod.rs:176-231) / TIPAWithSSM::prove_with_structured_scalar_message
+    (structured_scalar_message.rs:211-268) with the GIPA state partitioned cyclically and the two KZG opening MSMs
+    (tipa/mod.rs:304-337) sharded by contiguous slices of the SRS powers."""
+
+    def __init__(self, kind, ctx, comm=None):
+        self.gipa = ShardedGIPA(kind, ctx, comm)
+        self.ctx, self.comm = ctx, self.gipa.comm
+
+    def _open(self, group, srs_slice, lo, n_srs, transcript, r_shift, z):
+        import torch
+
+        q = self.ctx.kzg_quotient(codec.fr_vec_enc(transcript), codec.fr_enc(r_shift).copy(), codec.fr_enc(z).copy(), n_srs)
+        n_loc = srs_slice.shape[0]
+        w = 24 if group == 1 else 48
+        part = torch.zeros(w, dtype=torch.int32, device=srs_slice.device)
+        if n_loc:
+            qd = torch.from_numpy(q[lo:lo + n_loc].view(np.int32).copy()).to(srs_slice.device)
+            (self.ctx.msm_g1_dev if group == 1 else self.ctx.msm_g2_dev)(srs_slice.data_ptr(), qd.data_ptr(), n_loc, part.data_ptr())
+        gathered = self.comm.all_gather(part).contiguous()
+        out = torch.zeros(w, dtype=torch.int32, device=srs_slice.device)
+        self.ctx.seg_sum_dev(group, gathered.data_ptr(), gathered.shape[0], 1, out.data_ptr())
+        torch.cuda.current_stream().synchronize()
+        return (codec.g1_dec if group == 1 else codec.g2_dec)(out.cpu().numpy().view(np.uint32))
+
+    def prove_with_srs_shift(self, srs_g1_slice, srs_g2_slice, slice_lo, n_srs, a, b, v, w=None, r_shift=1):
+        """srs_g{1,2}_slice: this rank's CONTIGUOUS slice [slice_lo, slice_lo + len) of g^(alpha^i) / h^(beta^i),
+        i < n_srs = 2 n - 1; a, b, v, w: this rank's cyclic shares.  -> TIPAProof / TIPAWithSSMProof bytes."""
+        g = self.gipa
+        proof, transcript, ck_base, (_, _, v0, w0) = g.prove_with_aux_dev(a, b, v, w)
+        ssm = g.tw is None
+        tinv = [pow(x, -1, codec.R) for x in transcript]
+        z = challenge_from_random_bytes(codec.ser_fr(transcript[0]) + ck_base)
+        shift_a = 1 if ssm else pow(r_shift, -1, codec.R)
+        open_a = self._open(2, srs_g2_slice, slice_lo, n_srs, tinv, shift_a, z)
+        if ssm:
+            return proof + ck_base + codec.ser_g2(open_a)
+        open_b = self._open(1, srs_g1_slice, slice_lo, n_srs, transcript, 1, z)
+        return proof + ck_base + codec.ser_g2(open_a) + codec.ser_g1(open_b)
