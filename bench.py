@@ -14,7 +14,8 @@ opening MSMs, Fiat-Shamir hashing on the host.  Metric: prove seconds (lower is 
                the two leaf throughputs the metric string also names, measured in the same run:
                multi-Miller pairs/s (configs[1], 2^16 pairs per GPU) and G1 MSM points/s (configs[2] leaf,
                2^18 points per GPU), sharded by input slices with an NCCL all-gather of the per-rank
-               partials when N > 1
+               partials when N > 1; and GIPA prove of ONE 2^18-element multiexponentiation instance
+               (configs[2]) partitioned cyclically over the N ranks (strong scaling, same proof bytes at every N)
   roofline     integer-pipe (IMAD.WIDE) roofline of the dominant kernel class of the step, plus the
                Miller kernel at 2^16; peak = ripp_bench_imad measured live in this run
   cpu_baseline the compiled CPU restatement of the reference path (oracle/cpu, OpenMP on all host
@@ -45,6 +46,7 @@ MAC32_PER_FQ_MUL = 300
 LOG_PROOFS = 12
 LOG_PAIRS = 16
 LOG_MSM = 18
+LOG_GIPA = 18
 # per-launch DRAM traffic of the kernel classes measured once with `ncu --set full` (profiles/README.md)
 NCU_TRAFFIC_BYTES_PER_LAUNCH = {"fold": 82176, "miller": 19165440, "msm": 109165824}
 METRIC = "tipp_groth16_aggregate_prove_seconds_at_2^12_proofs"
@@ -280,6 +282,42 @@ def main():
         sub["msm_g1_points_per_s"] = {"value": world * nmsm / (ms * 1e-3), "points_per_gpu": nmsm, "ms_per_step": ms}
         bases.free()
         sc.free()
+
+        # ---- BASELINE configs[2] (ii): GIPA prove, multiexponentiation instantiation (benches/benches/gipa.rs:86-94),
+        # ONE global instance of 2^18 elements partitioned cyclically over the ranks (strong scaling: the same proof
+        # bytes at every N; parallel.py).  Wall clock, max over ranks: the round loop includes the host's hashing.
+        import hashlib
+
+        from ripp_b200.parallel import Comm, ShardedGIPA
+
+        ng = 1 << LOG_GIPA
+        nl = ng // world
+
+        def share(tag, group):
+            sc_h = synth.scalars_mont(tag, ng)[rank::world]
+            if group == 0:
+                return torch.from_numpy(np.ascontiguousarray(sc_h).view(np.int32)).cuda()
+            d = ctx.to_device(np.ascontiguousarray(sc_h))
+            t = torch.empty((nl, 24 if group == 1 else 48), dtype=torch.int32, device="cuda")
+            (ctx.g1_scale_dev if group == 1 else ctx.g2_scale_dev)(None, d, nl, t.data_ptr())
+            ctx.sync()
+            d.free()
+            return t
+
+        ga, gb, gv, gw = share("cfg3-a", 1), share("cfg3-b", 0), share("cfg3-v", 2), share("cfg3-w", 1)
+        sg = ShardedGIPA(_lib.GIPA_MULTIEXP_PEDERSEN, ctx, Comm())
+        gproof = sg.prove_with_aux_dev(ga, gb, gv, gw)[0]  # warm-up
+        g_reps = 2
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(g_reps):
+            gproof = sg.prove_with_aux_dev(ga, gb, gv, gw)[0]
+        torch.cuda.synchronize()
+        g_s = max_over_ranks((time.perf_counter() - t0) / g_reps)
+        sub["gipa_multiexp_prove_s"] = {"value": g_s, "elements_total": ng, "elements_per_gpu": nl, "scaling": "strong",
+                                        "proof_blake2b": hashlib.blake2b(gproof, digest_size=16).hexdigest(),
+                                        "proof_bytes": len(gproof)}
+        del ga, gb, gv, gw
 
     stop.set()
     th.join(timeout=2)

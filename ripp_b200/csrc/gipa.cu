@@ -148,6 +148,7 @@ static int ip_out_type(int a, int b) {
 
 // Up to 8 inner products of equal length evaluated together; pairing-type ones share one launch.
 static int eval_products(ripp_ctx* ctx, int k, const Slice* xs, const Slice* ys, size_t n, Val* out) {
+  CU(cudaSetDevice(ctx->device));  // the current device is per host thread: worker threads start on device 0
   void* res;
   OK(scratch(ctx, 10, 8 * 576 + 8 * 576, &res));
   char* r = (char*)res;
@@ -415,6 +416,7 @@ extern "C" int ripp_kzg_quotient(const void* transcript, size_t k, const void* r
 template <class F>
 static int kzg_open(ripp_ctx* ctx, const void* srs_dev, size_t n_srs, const std::vector<Fr>& transcript, const Fr& r_shift,
                     const Fr& z, Aff<F>* out_host) {
+  CU(cudaSetDevice(ctx->device));  // may run on a worker thread (tipa_prove)
   std::vector<Fr> q = kzg_quotient(transcript, r_shift, z, n_srs);
   void* d;
   OK(scratch(ctx, 12, n_srs * sizeof(Fr) + 1024, &d));
