@@ -158,6 +158,16 @@ int ripp_gipa_prove_dev(ripp_ctx* ctx, int kind, const void* a_dev, const void* 
                         const void* w_dev, size_t n, uint8_t* proof_out, size_t proof_cap, size_t* proof_len,
                         void* transcript_out, uint8_t* ck_base_out, size_t ck_cap, size_t* ck_len);
 
+/* The same prover continuing a transcript: prev_challenge (one Fr, host, Montgomery) is the challenge of the round
+ * before the first one proved here (NULL = fresh transcript, i.e. ripp_gipa_prove_dev).  A sharded prover
+ * (ripp_b200/parallel.py) runs its long rounds partitioned over the GPUs, all-gathers the short remaining vectors
+ * and hands this tail -- latency-bound, replicated on every rank -- to the resident single-GPU prover.  The proof
+ * bytes cover the rounds proved here: u64 count, their steps (last round first), then r_base. */
+int ripp_gipa_prove_resume_dev(ripp_ctx* ctx, int kind, const void* a_dev, const void* b_dev, const void* v_dev,
+                               const void* w_dev, size_t n, const void* prev_challenge, uint8_t* proof_out,
+                               size_t proof_cap, size_t* proof_len, void* transcript_out, uint8_t* ck_base_out,
+                               size_t ck_cap, size_t* ck_len);
+
 /* prove_commitment_key_kzg_opening (tipa/mod.rs:304-337): opening of the product-form polynomial
  * f(X) = prod_j (1 + x_j r^(2^j) X^(2^(j+1))) at z over n_srs = 2*2^k - 1 SRS powers (device).
  * transcript (k Fr), r_shift, z: host, Montgomery.  Result: one affine point (host). */

@@ -231,6 +231,19 @@ class Context:
                                         ctypes.byref(cklen)))
         return proof[: plen.value].tobytes(), tr, ck[: cklen.value].tobytes()
 
+    def gipa_prove_resume_dev(self, kind, a, b, v, w, n, prev_challenge):
+        """As gipa_prove_dev, continuing a transcript whose last challenge is prev_challenge ((8,) uint32 Montgomery)."""
+        k = max(n.bit_length() - 1, 0)
+        cap = 64 + k * 6 * 600 + 2 * 600
+        proof = np.empty(cap, dtype=np.uint8)
+        plen, cklen = ctypes.c_size_t(), ctypes.c_size_t()
+        tr = np.zeros((k, 8), dtype=np.uint32)
+        ck = np.empty(1024, dtype=np.uint8)
+        check(lib().ripp_gipa_prove_resume_dev(self.handle, int(kind), _p(a), _p(b), _p(v), _p(w), ctypes.c_size_t(n),
+                                               _p(prev_challenge), _p(proof), ctypes.c_size_t(cap), ctypes.byref(plen), _p(tr),
+                                               _p(ck), ctypes.c_size_t(1024), ctypes.byref(cklen)))
+        return proof[: plen.value].tobytes(), tr, ck[: cklen.value].tobytes()
+
     def tipa_prove_dev(self, kind, srs_g1, srs_g2, a, b, v, w, n, r_shift=None):
         k = max(n.bit_length() - 1, 0)
         cap = 64 + k * 6 * 600 + 8 * 600

@@ -262,8 +262,10 @@ struct GipaOut {
   Val a0, b0, v0, w0;          // r_base and ck_base
 };
 
+// prev0: challenge of the round BEFORE the first one proved here (a sharded prover hands its tail over after its
+// own rounds, parallel.py); NULL = a fresh transcript (the default value of gipa.rs:237-238).
 static int gipa_prove(ripp_ctx* ctx, const GipaSpec& sp, const void* a_in, const void* b_in, const void* v_in,
-                      const void* w_in, size_t n, GipaOut* out) {
+                      const void* w_in, size_t n, GipaOut* out, const Fr* prev0 = nullptr) {
   if (n == 0 || (n & (n - 1)))
     return fail(RIPP_ERR_NOT_POW2, "left length, right length: " + std::to_string(n) + ", " + std::to_string(n));
   CU(cudaSetDevice(ctx->device));
@@ -296,7 +298,7 @@ static int gipa_prove(ripp_ctx* ctx, const GipaSpec& sp, const void* a_in, const
     if (trace_on()) fprintf(stderr, "[trace] gipa(a=%d,b=%d) n'=%zu products+prev folds %.2f ms\n", sp.a, sp.b, split, now_ms() - t_r0);
     // gipa.rs:235-258 -- Fiat-Shamir challenge
     Fr c, c_inv;
-    gipa_challenge(transcript.empty() ? Fr::zero() : transcript.back(), com.data(), &c, &c_inv);
+    gipa_challenge(transcript.empty() ? (prev0 ? *prev0 : Fr::zero()) : transcript.back(), com.data(), &c, &c_inv);
     // gipa.rs:261-291 -- rescale
     {
       ripp_ctx* k1 = ripp_child(ctx, 0);
@@ -352,6 +354,25 @@ static int copy_out(const Bytes& b, uint8_t* dst, size_t cap, size_t* len) {
   if (!dst || cap < b.size()) return fail(RIPP_ERR_ARG, "output buffer too small: need " + std::to_string(b.size()));
   memcpy(dst, b.data(), b.size());
   return RIPP_OK;
+}
+
+extern "C" int ripp_gipa_prove_resume_dev(ripp_ctx* ctx, int kind, const void* a_dev, const void* b_dev, const void* v_dev,
+                                          const void* w_dev, size_t n, const void* prev_challenge, uint8_t* proof_out,
+                                          size_t proof_cap, size_t* proof_len, void* transcript_out, uint8_t* ck_base_out,
+                                          size_t ck_cap, size_t* ck_len) {
+  GipaSpec sp;
+  if (!ctx || !gipa_spec(kind, &sp)) return fail(RIPP_ERR_ARG, "bad context or GIPA kind");
+  if (!a_dev || !b_dev || !v_dev || (sp.w != VT_NONE && !w_dev)) return fail(RIPP_ERR_ARG, "null vector");
+  GipaOut g;
+  Fr prev;
+  if (prev_challenge) memcpy(prev.v, prev_challenge, 32);
+  OK(gipa_prove(ctx, sp, a_dev, b_dev, v_dev, w_dev, n, &g, prev_challenge ? &prev : nullptr));
+  OK(copy_out(g.proof, proof_out, proof_cap, proof_len));
+  if (transcript_out) memcpy(transcript_out, g.transcript.data(), g.transcript.size() * sizeof(Fr));
+  Bytes ck;
+  put_val(ck, g.v0);
+  if (sp.w != VT_NONE) put_val(ck, g.w0);
+  return copy_out(ck, ck_base_out, ck_cap, ck_len);
 }
 
 extern "C" int ripp_gipa_prove_dev(ripp_ctx* ctx, int kind, const void* a_dev, const void* b_dev, const void* v_dev,

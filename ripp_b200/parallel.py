@@ -132,6 +132,35 @@ class ShardedGIPA:
         # (x type, y type) of the three products of a commitment triple: IP(A, v), IP(w, B), IP(A, B)
         self.prod_types = [(self.ta, self.tv), (self.tw, self.tb), (self.ta, self.tb)]
         self.out_types = [ip_out_type(x, y) for x, y in self.prod_types]
+        self.tail_len = 1 << 12
+        self._helpers = None  # extra contexts (own stream + scratch) so MSM-type products and folds overlap
+
+    # -- stream fork / join between the main context's stream (torch's current stream) and helper contexts ----
+    def _helper(self, i):
+        import torch
+
+        if self._helpers is None:
+            self._helpers = []
+            for _ in range(3):
+                c = type(self.ctx)(self.ctx.device)
+                st = torch.cuda.Stream()
+                c.set_stream(st.cuda_stream)
+                self._helpers.append((c, st))
+        return self._helpers[i % 3]
+
+    def _fork(self, st):
+        import torch
+
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        st.wait_event(ev)
+
+    def _join(self, st):
+        import torch
+
+        ev = torch.cuda.Event()
+        ev.record(st)
+        torch.cuda.current_stream().wait_event(ev)
 
     # -- six partial products over local halves -> combined values on every rank ------------------------
     def _round_products(self, A, B, V, W, split, count_ranks):
@@ -148,6 +177,24 @@ class ShardedGIPA:
         types = self.prod_types * 2
         outs = self.out_types * 2
         gt_slots = [i for i in range(6) if outs[i] == "GT"]
+        # MSM-type products first, each on a helper stream; then the pairing batch on the main stream (they overlap)
+        used, nh = [], 0
+        for i in range(6):
+            tx, ty = types[i]
+            if outs[i] == "GT" or tx is None or ty is None:
+                continue  # placeholder commitment: Fr zero
+            if tx == "Fr" and ty == "Fr":
+                ctx.scalar_ip_dev(xs[i].data_ptr(), ys[i].data_ptr(), split, parts[i].data_ptr())
+                continue
+            hc, hst = self._helper(nh)
+            nh += 1
+            if hst not in used:
+                self._fork(hst)
+                used.append(hst)
+            pts, sc = (ys[i], xs[i]) if tx == "Fr" else (xs[i], ys[i])
+            fn = hc.msm_g1_dev if outs[i] == "G1" else hc.msm_g2_dev
+            fn(pts.data_ptr(), sc.data_ptr(), split, parts[i].data_ptr())
+        tmp = None
         if gt_slots:
             g1p, g2p = [], []
             for i in gt_slots:
@@ -156,17 +203,10 @@ class ShardedGIPA:
                 g2p.append((ys[i] if x_is_g1 else xs[i]).data_ptr())
             tmp = torch.zeros((len(gt_slots), 144), dtype=torch.int32, device=dev)
             ctx.miller_partial_batch_dev(g1p, g2p, split, tmp.data_ptr())
+        for hst in used:
+            self._join(hst)
+        if tmp is not None:
             parts[gt_slots] = tmp
-        for i in range(6):
-            tx, ty = types[i]
-            if outs[i] == "GT" or tx is None or ty is None:
-                continue  # placeholder commitment: Fr zero
-            if tx == "Fr" and ty == "Fr":
-                ctx.scalar_ip_dev(xs[i].data_ptr(), ys[i].data_ptr(), split, parts[i].data_ptr())
-            else:
-                pts, sc = (ys[i], xs[i]) if tx == "Fr" else (xs[i], ys[i])
-                fn = ctx.msm_g1_dev if outs[i] == "G1" else ctx.msm_g2_dev
-                fn(pts.data_ptr(), sc.data_ptr(), split, parts[i].data_ptr())
         if count_ranks > 1:
             gathered = self.comm.all_gather(parts).permute(1, 0, 2).contiguous()  # (6, world, 144)
         else:
@@ -198,53 +238,70 @@ class ShardedGIPA:
             b += codec.ser_identity_output(s) if i % 3 == 2 else s
         return b
 
-    def _fold(self, t, typ, split, c):
+    def _fold(self, t, typ, split, c, ctx=None):
         if t is None:
             return
+        ctx = ctx or self.ctx
         cw = codec.fr_enc(c).copy()
-        fn = {"G1": self.ctx.g1_fold_dev, "G2": self.ctx.g2_fold_dev, "Fr": self.ctx.fr_fold_dev}[typ]
+        fn = {"G1": ctx.g1_fold_dev, "G2": ctx.g2_fold_dev, "Fr": ctx.fr_fold_dev}[typ]
         fn(t[split:2 * split].data_ptr(), t[:split].data_ptr(), cw, split, t[:split].data_ptr())
 
-    def prove_with_aux_dev(self, a, b, v, w=None):
-        """-> (GIPAProof bytes, r_transcript ints (reversed, as GIPAAux), ck_base bytes, (a0, b0, v0, w0) values)."""
+    def prove_with_aux_dev(self, a, b, v, w=None, tail_len=None):
+        """-> (GIPAProof bytes, r_transcript ints (reversed, as GIPAAux), ck_base bytes).
+
+        Rounds run partitioned while the GLOBAL vector is longer than tail_len (default 2^12: below that every kernel
+        of a round is a latency chain of a few warps and partitioning buys nothing); then the remaining vectors are
+        all-gathered once and every rank finishes with the resident single-GPU prover continuing the same
+        transcript (ripp_gipa_prove_resume_dev), which overlaps its MSMs, folds and pairing batches on child streams."""
         import torch
 
         world = self.comm.world
         m = a.shape[0]
         if m == 0 or m & (m - 1) or world & (world - 1):
             raise ValueError("local length and world size must be powers of two (gipa.rs:116-122)")
+        tail_len = self.tail_len if tail_len is None else tail_len
         A, B, V = a.clone(), b.clone(), v.clone()  # gipa.rs:175-176 clones all four vectors
         W = None if self.tw is None else w.clone()
-        replicated = world == 1
         steps, transcript = [], []
-        while True:
-            if not replicated and m == 1:
-                # one element per rank left: all-gather the vectors (global order = rank order) and finish everywhere
-                A, B, V = (self.comm.all_gather(t[0]).contiguous() for t in (A, B, V))
-                W = None if W is None else self.comm.all_gather(W[0]).contiguous()
-                m, replicated = world, True
-            if m == 1:
-                break
+        while m > 1 and m * world > max(tail_len, world):
             split = m // 2
-            vals, outs = self._round_products(A, B, V, W, split, 1 if replicated else world)
+            vals, outs = self._round_products(A, B, V, W, split, world)
             com_bytes = self._ser_triples(vals, outs)
             c, c_inv = gipa_challenge(transcript[-1] if transcript else 0, com_bytes)
             # gipa.rs:261-291: A <- A_R c + A_L, B <- B_R c^-1 + B_L, v <- v_R c^-1 + v_L, w <- w_R c + w_L
-            self._fold(A, self.ta, split, c)
-            self._fold(B, self.tb, split, c_inv)
-            self._fold(V, self.tv, split, c_inv)
-            self._fold(W, self.tw, split, c)
+            for i, (t, typ, sc) in enumerate(((A, self.ta, c), (B, self.tb, c_inv), (V, self.tv, c_inv), (W, self.tw, c))):
+                if i == 0 or t is None:
+                    self._fold(t, typ, split, sc)          # main stream
+                else:
+                    hc, hst = self._helper(i - 1)
+                    self._fork(hst)
+                    self._fold(t, typ, split, sc, hc)
+            for i in range(3):
+                self._join(self._helper(i)[1])
             steps.append(com_bytes)
             transcript.append(c)
             m = split
+
+        # all-gather what is left into global order (global index j g + k = local index j of rank k) ...
+        def whole(t):
+            if t is None:
+                return None
+            t = t[:m].contiguous()
+            return t if world == 1 else self.comm.all_gather(t).permute(1, 0, 2).reshape(m * world, t.shape[1]).contiguous()
+
+        A, B, V, W = whole(A), whole(B), whole(V), whole(W)
         torch.cuda.current_stream().synchronize()
-        base = []
-        for t, typ in ((A, self.ta), (B, self.tb), (V, self.tv), (W, self.tw)):
-            base.append(None if t is None else _DEC[typ](t[0].cpu().numpy().view(np.uint32)))
-        a0, b0, v0, w0 = base
-        proof = len(steps).to_bytes(8, "little") + b"".join(reversed(steps)) + _SER[self.ta](a0) + _SER[self.tb](b0)
-        ck_base = _SER[self.tv](v0) + (b"" if self.tw is None else _SER[self.tw](w0))
-        return proof, transcript[::-1], ck_base, (a0, b0, v0, w0)
+        # ... and finish on every rank with the resident prover, continuing the transcript
+        prev = codec.fr_enc(transcript[-1]).copy() if transcript else None
+        tail, tail_tr, ck_base = self.ctx.gipa_prove_resume_dev(self.kind, A.data_ptr(), B.data_ptr(), V.data_ptr(),
+                                                                None if W is None else W.data_ptr(), m * world, prev)
+        k_tail = int.from_bytes(tail[:8], "little")
+        base_len = len(tail) - 8 - (len(steps[0]) * k_tail if steps else 0)
+        if not steps:  # everything was proved by the resident prover
+            return tail, codec.fr_vec_dec(tail_tr), ck_base
+        tail_steps, r_base = tail[8:len(tail) - base_len], tail[len(tail) - base_len:]
+        proof = (k_tail + len(steps)).to_bytes(8, "little") + tail_steps + b"".join(reversed(steps)) + r_base
+        return proof, codec.fr_vec_dec(tail_tr) + transcript[::-1], ck_base
 
 
 class ShardedTIPA:
@@ -276,7 +333,7 @@ class ShardedTIPA:
         """srs_g{1,2}_slice: this rank's CONTIGUOUS slice [slice_lo, slice_lo + len) of g^(alpha^i) / h^(beta^i),
         i < n_srs = 2 n - 1; a, b, v, w: this rank's cyclic shares.  -> TIPAProof / TIPAWithSSMProof bytes."""
         g = self.gipa
-        proof, transcript, ck_base, (_, _, v0, w0) = g.prove_with_aux_dev(a, b, v, w)
+        proof, transcript, ck_base = g.prove_with_aux_dev(a, b, v, w)
         ssm = g.tw is None
         tinv = [pow(x, -1, codec.R) for x in transcript]
         z = challenge_from_random_bytes(codec.ser_fr(transcript[0]) + ck_base)

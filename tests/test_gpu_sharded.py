@@ -62,7 +62,9 @@ def test_host_driven_gipa_matches_device_prover(ctx, kind):
     want_proof, want_tr, want_ck = _single_gpu_proof(ctx, kind, vecs, n)
     _with_stream(ctx)
     try:
-        proof, tr, ck, _ = ShardedGIPA(kind, ctx).prove_with_aux_dev(*[_cuda(v) for v in vecs])
+        sg = ShardedGIPA(kind, ctx)
+        proof, tr, ck = sg.prove_with_aux_dev(*[_cuda(v) for v in vecs], tail_len=2)  # two host-driven rounds + tail
+        whole = sg.prove_with_aux_dev(*[_cuda(v) for v in vecs])                     # default: all in the resident prover
     finally:
         torch.cuda.synchronize()
         ctx.set_stream(None)
@@ -70,6 +72,7 @@ def test_host_driven_gipa_matches_device_prover(ctx, kind):
     assert proof == want_proof
     assert tr == codec.fr_vec_dec(want_tr)
     assert ck == want_ck
+    assert whole == (proof, tr, ck)
 
 
 def _srs(ctx, n):
@@ -113,8 +116,9 @@ def test_host_driven_tipa_matches_device_prover(ctx, kind):
     vecs, s1, s2, r_shift, want = _tipa_case(ctx, kind, n)
     _with_stream(ctx)
     try:
-        got = ShardedTIPA(kind, ctx).prove_with_srs_shift(_cuda(s1), _cuda(s2), 0, 2 * n - 1, *[_cuda(v) for v in vecs],
-                                                          r_shift=r_shift)
+        st = ShardedTIPA(kind, ctx)
+        st.gipa.tail_len = 2
+        got = st.prove_with_srs_shift(_cuda(s1), _cuda(s2), 0, 2 * n - 1, *[_cuda(v) for v in vecs], r_shift=r_shift)
     finally:
         torch.cuda.synchronize()
         ctx.set_stream(None)
@@ -140,8 +144,9 @@ def _worker(rank, world, port, kind, n, q):
         _with_stream(ctx)
         lo, hi = shard_bounds(2 * n - 1, rank, world)
         shares = [None if v is None else _cuda(np.ascontiguousarray(cyclic_share(v, rank, world))) for v in vecs]
-        got = ShardedTIPA(kind, ctx, Comm()).prove_with_srs_shift(_cuda(s1[lo:hi]), _cuda(s2[lo:hi]), lo, 2 * n - 1, *shares,
-                                                                  r_shift=r_shift)
+        st = ShardedTIPA(kind, ctx, Comm())
+        st.gipa.tail_len = 2  # partitioned rounds down to one element per rank, then the gathered tail
+        got = st.prove_with_srs_shift(_cuda(s1[lo:hi]), _cuda(s2[lo:hi]), lo, 2 * n - 1, *shares, r_shift=r_shift)
         torch.cuda.synchronize()
         q.put((rank, got == want, len(got)))
     except Exception as e:  # surface the failure in the parent
