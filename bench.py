@@ -142,7 +142,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    # rank 0 prints exactly ONE JSON line on stdout: NCCL's version banner / debug output (it writes to stdout at
+    # NCCL_DEBUG >= VERSION) goes to a file instead
+    os.environ["NCCL_DEBUG_FILE"] = "/tmp/ripp_b200_nccl_%h_%p.log"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)

@@ -18,7 +18,7 @@ logn = int(sys.argv[2]) if len(sys.argv) > 2 else 18
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr)
-os.environ["NCCL_DEBUG"] = "WARN"
+os.environ["NCCL_DEBUG_FILE"] = "/tmp/ripp_b200_nccl_%h_%p.log"
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 ctx = _lib.Context(lr)
