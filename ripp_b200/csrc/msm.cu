@@ -6,7 +6,6 @@
 // sipp/src/lib.rs:87-100; scalar-mul primitive `mul_helper`, ip_proofs/src/lib.rs:15-19).
 #include "common.cuh"
 #include "x3.cuh"
-#include "endo.cuh"
 
 static bool use_endo() {
   static int v = -1;
@@ -234,28 +233,35 @@ __global__ void k_msm_horner(const Jac<F>* __restrict__ sums, int nw, int c, Aff
   *out = acc.to_affine();
 }
 
-static bool use_x3() {
+// RIPP_B200_FOLD = "w3" / "endo" / "plain" forces a fold kernel (A/B runs); default: three-warp teams (x3.cuh) while the
+// vector is short enough that the GPU is otherwise empty, one thread per element with the endomorphism above that.
+static int fold_mode() {
   static int v = -1;
   if (v < 0) {
-    // "x3" selects the three-lanes-per-point kernels (x3.cuh).  Bit-exact, but measured NOT faster on B200
-    // (TIPP 2^12: 199.5 ms vs 184.5 ms; element-wise scaling 2x slower): shuffles, selects and spills eat the
-    // shorter multiplication chain.  One thread per element stays the default.
     const char* e = getenv("RIPP_B200_FOLD");
-    v = (e && strcmp(e, "x3") == 0) ? 1 : 0;
+    v = !e ? 0 : (strcmp(e, "w3") == 0 ? 1 : (strcmp(e, "endo") == 0 ? 2 : (strcmp(e, "plain") == 0 ? 3 : 0)));
   }
-  return v == 1;
+  return v;
+}
+// 3 warps per 32 elements: the team kernels pay off while the GPU is otherwise empty (RIPP_B200_W3_MAX overrides)
+static size_t w3_max_n() {
+  static long v = -1;
+  if (v < 0) {
+    const char* e = getenv("RIPP_B200_W3_MAX");
+    v = e ? atol(e) : 512;  // TIPP 2^12: 148.5 ms without teams, 143.1 at 512, 146.2 at 4096 (the early rounds already fill the GPU)
+  }
+  return (size_t)v;
 }
 
-// Horner tail on one three-lane group
+// Horner tail on one three-warp team (<<<1, 96>>>; all lanes hold the same values)
 template <class XF>
-__global__ void k_msm_horner_x3(const Jac<XF>* __restrict__ sums, int nw, int c, Aff<XF>* __restrict__ out) {
-  if (threadIdx.x >= 3) return;
+__global__ void __maxnreg__(255) k_msm_horner_x3(const Jac<XF>* __restrict__ sums, int nw, int c, Aff<XF>* __restrict__ out) {
   Jac<XF> acc = sums[nw - 1];
   for (int w = nw - 2; w >= 0; w--) {
     for (int j = 0; j < c; j++) acc = x3::Ops<XF>::dbl(acc);
-    acc = acc.add(sums[w]);
+    acc = acc.add(sums[w]);  // uniform data: every thread takes the same branch of the complete addition
   }
-  Aff<XF> o = acc.to_affine();
+  Aff<XF> o = x3::to_affine(acc);
   if (threadIdx.x == 0) *out = o;
 }
 template <class F> struct X3Of;
@@ -369,9 +375,9 @@ static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, 
     pb = t;
     T = To;
   }
-  if (use_x3()) {
+  if (fold_mode() <= 1) {
     typedef typename X3Of<F>::type XF;
-    k_msm_horner_x3<XF><<<1, 32, 0, st>>>((const Jac<XF>*)pa, p.nw, p.c, (Aff<XF>*)out);
+    k_msm_horner_x3<XF><<<1, 96, 0, st>>>((const Jac<XF>*)pa, p.nw, p.c, (Aff<XF>*)out);
   } else {
     k_msm_horner<F><<<1, 32, 0, st>>>(pa, p.nw, p.c, out);
   }
@@ -518,18 +524,18 @@ __global__ void __launch_bounds__(64, 4) k_fold(const Aff<F>* __restrict__ hi, c
   out[i] = acc.to_affine();
 }
 
-// three lanes per element (x3.cuh): XF = Fq for G1, x3::Fq2x3 for G2 (same memory layout as Fq / Fq2)
+// one three-warp team per 32 elements (x3.cuh): XF = Fq for G1, x3::Fq2x3 for G2 (same memory layout as Fq / Fq2).
+// Every thread stays to the end (the exchanges are CTA barriers): lanes past n work on element n - 1 and do not store.
 template <class XF>
-__global__ void __launch_bounds__(128) k_fold_x3(const Aff<XF>* __restrict__ hi, const Aff<XF>* __restrict__ lo, ScalarBits c,
-                                                 size_t n, Aff<XF>* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  if (lane >= 30) return;
-  size_t i = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 10 + lane / 3;
-  if (i >= n) return;
-  Jac<XF> acc = x3::mul_naf<XF>(hi[i], c.pos, c.neg, c.nbits);
+__global__ void __maxnreg__(255) k_fold_w3(const Aff<XF>* __restrict__ hi, const Aff<XF>* __restrict__ lo, EndoBits c,
+                                                size_t n, Aff<XF>* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  const bool live = i < n;
+  if (!live) i = n - 1;
+  Jac<XF> acc = x3::endo_mul<XF>(hi[i], c);
   acc = x3::Ops<XF>::madd(acc, lo[i]);
-  Aff<XF> o = acc.to_affine();
-  if (lane % 3 == 0) out[i] = o;
+  Aff<XF> o = x3::to_affine(acc);
+  if (live && threadIdx.x < 32) out[i] = o;
 }
 
 template <class F, class XF>
@@ -538,11 +544,11 @@ static int fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c
   if (n == 0) return RIPP_OK;
   CU(cudaSetDevice(ctx->device));
   TimeScope ts_(ctx, RIPP_T_FOLD);
-  if (use_x3()) {
-    size_t warps = (n + 9) / 10;
-    k_fold_x3<XF><<<(unsigned)((warps + 3) / 4), 128, 0, ctx->stream>>>((const Aff<XF>*)hi, (const Aff<XF>*)lo, scalar_bits(c),
-                                                                       n, (Aff<XF>*)out);
-  } else if (use_endo()) {
+  const int mode = fold_mode();
+  if (mode == 1 || (mode == 0 && n <= w3_max_n())) {
+    k_fold_w3<XF><<<(unsigned)((n + 31) / 32), 96, 0, ctx->stream>>>((const Aff<XF>*)hi, (const Aff<XF>*)lo, endo_bits<F>(c), n,
+                                                                   (Aff<XF>*)out);
+  } else if (mode != 3) {
     k_fold_endo<F><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const Aff<F>*)hi, (const Aff<F>*)lo, endo_bits<F>(c), n,
                                                                    (Aff<F>*)out);
   } else {

@@ -221,78 +221,12 @@ __global__ void __launch_bounds__(64, 4) k_scale(const Aff<F>* __restrict__ pts,
   out[i] = endo_mul_simt<F>(p, eb, mm, nb).to_affine();
 }
 
-// three lanes per element (x3.cuh); the scalar is NAF-recoded by the group itself
-template <class XF, bool GEN>
-__global__ void __launch_bounds__(128) k_scale_x3(const Aff<XF>* __restrict__ pts, const Fr* __restrict__ sc, size_t n,
-                                                  Aff<XF>* __restrict__ out, Aff<XF> gen) {
-  const int lane = threadIdx.x & 31;
-  if (lane >= 30) return;
-  size_t i = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 10 + lane / 3;
-  if (i >= n) return;
-  Fr s = sc[i].from_mont();
-  uint32_t k[10], pos[9], neg[9];
-#pragma unroll
-  for (int j = 0; j < 10; j++) k[j] = j < 8 ? s.v[j] : 0u;
-#pragma unroll
-  for (int j = 0; j < 9; j++) pos[j] = neg[j] = 0;
-  int nd = 0;
-  for (int d = 0; d < 257; d++) {
-    uint32_t any = 0;
-#pragma unroll
-    for (int j = 0; j < 10; j++) any |= k[j];
-    if (!any) break;
-    if (k[0] & 1) {
-      if ((k[0] & 3) == 1) {
-        pos[d >> 5] |= 1u << (d & 31);
-        k[0] -= 1;
-      } else {
-        neg[d >> 5] |= 1u << (d & 31);
-        uint32_t carry = 1;
-#pragma unroll
-        for (int j = 0; j < 10; j++) {
-          uint32_t t = k[j] + carry;
-          carry = (t < carry) ? 1u : 0u;
-          k[j] = t;
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 9; j++) k[j] = (k[j] >> 1) | (k[j + 1] << 31);
-    k[9] >>= 1;
-    nd = d + 1;
-  }
-  Aff<XF> p = GEN ? gen : pts[i];
-  Aff<XF> o = x3::mul_naf<XF>(p, pos, neg, nd).to_affine();
-  if (lane % 3 == 0) out[i] = o;
-}
-
-static bool scale_use_x3() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RIPP_B200_FOLD");  // see msm.cu: "x3" = three lanes per point (not faster)
-    v = (e && strcmp(e, "x3") == 0) ? 1 : 0;
-  }
-  return v == 1;
-}
-
 template <class F, class XF>
 static int scale_dev(ripp_ctx* ctx, const void* pts, const void* sc, size_t n, void* out, const Aff<F>& gen) {
   if (!ctx || (n && (!sc || !out))) return fail(RIPP_ERR_ARG, "null argument");
   if (n == 0) return RIPP_OK;
   CU(cudaSetDevice(ctx->device));
   TimeScope ts_(ctx, RIPP_T_SCALE);
-  if (scale_use_x3()) {
-    size_t warps = (n + 9) / 10;
-    unsigned blocks = (unsigned)((warps + 3) / 4);
-    Aff<XF> xgen;
-    memcpy(&xgen, &gen, sizeof(gen));
-    if (pts)
-      k_scale_x3<XF, false><<<blocks, 128, 0, ctx->stream>>>((const Aff<XF>*)pts, (const Fr*)sc, n, (Aff<XF>*)out, xgen);
-    else
-      k_scale_x3<XF, true><<<blocks, 128, 0, ctx->stream>>>(nullptr, (const Fr*)sc, n, (Aff<XF>*)out, xgen);
-    LAUNCHED(ctx);
-    return RIPP_OK;
-  }
   unsigned blocks = (unsigned)((n + 63) / 64);
   if (pts)
     k_scale<F, false><<<blocks, 64, 0, ctx->stream>>>((const Aff<F>*)pts, (const Fr*)sc, n, (Aff<F>*)out, gen);

@@ -1,37 +1,40 @@
-// "x3": one curve point handled by three lanes.  State (coordinates) is replicated in the three lanes'
-// registers; every field multiplication level is split three ways and the results are exchanged with
-// warp shuffles, so the three lanes always hold identical values and take identical branches.
+// "x3": one vector of curve points handled by a TEAM OF THREE WARPS.  Lane l of each of the three warps works on
+// element l; the point state (coordinates) is replicated in the three warps' registers; every field
+// multiplication level is split three ways, each warp computes one product, and the results are exchanged
+// through shared memory, so the three warps always hold identical values and take identical branches.
 //   * G2 (Fq2 coordinates): the three Karatsuba sub-products of every Fq2 product / squaring go to the
-//     three lanes (Fq2x3 below has the interface of Fq2, so the Jacobian formulas of curve.cuh are
-//     reused unchanged);
+//     three warps (Fq2x3 below has the interface of Fq2, so the Jacobian formulas of curve.cuh are reused);
 //   * G1 (Fq coordinates): the independent Fq products of each level of dbl-2009-l / madd-2007-bl.
-// Purpose: the folds / element-wise scalings / Horner tails of a GIPA round are latency chains of ~3000
-// dependent field products per element; three lanes cut that chain ~2x at the vector lengths where the
-// GPU is otherwise empty.  Ten groups (30 lanes) per warp; lanes 30 and 31 idle.
+// Why warps and not lanes: a carry-chain Montgomery product is ~300 IMAD.WIDE.U32.X, each holding the heavy pipe
+// of ITS sub-partition for 4 cycles per warp instruction (profiles/README.md), so a lone warp runs at the speed of
+// one sub-partition's multiplier however many of its lanes are active.  The first version of this file put the
+// three roles in three LANES of one warp (shuffles): same pipe, no gain -- measured.  Three warps of a CTA sit on
+// three different sub-partitions: three multipliers per element, for the folds / Horner tails of the late GIPA
+// rounds, which are latency chains of ~2000-4000 dependent field products on an otherwise empty GPU.
+// A CTA is ONE team (blockDim.x == 96); every thread must reach every exchange, so the point formulas below run
+// their cooperative levels unconditionally and patch exceptional lanes afterwards with non-cooperative code.
 #pragma once
-#include "curve.cuh"
+#include "endo.cuh"
 
 namespace ripp {
 namespace x3 {
 
 #if defined(__CUDA_ARCH__)
-// Lanes 30 and 31 of a warp must have exited before any of this is called (kernels return early for them).
-__device__ __forceinline__ int lane_r() { return (threadIdx.x & 31) % 3; }
-__device__ __forceinline__ int lane_base() {
-  int l = threadIdx.x & 31;
-  return l - l % 3;
-}
-// every lane contributes `mine`; returns the three lanes' values.  The shuffle mask names only the group's
-// own lanes, so different groups of a warp may diverge (different scalars, exceptional cases).
+__device__ __forceinline__ int lane_r() { return (threadIdx.x >> 5) % 3; }
+// every warp contributes `mine` (per lane); returns the three warps' values.  [role][limb][lane]: conflict-free.
 __device__ __forceinline__ void gather3(const Fq& mine, Fq& t0, Fq& t1, Fq& t2) {
-  const int b = lane_base();
-  const unsigned m = 7u << b;
+  __shared__ uint32_t bus[3 * 12 * 32];
+  const int r = lane_r(), l = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 12; i++) bus[(r * 12 + i) * 32 + l] = mine.v[i];
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < 12; i++) {
-    t0.v[i] = __shfl_sync(m, mine.v[i], b);
-    t1.v[i] = __shfl_sync(m, mine.v[i], b + 1);
-    t2.v[i] = __shfl_sync(m, mine.v[i], b + 2);
+    t0.v[i] = bus[i * 32 + l];
+    t1.v[i] = bus[(12 + i) * 32 + l];
+    t2.v[i] = bus[(24 + i) * 32 + l];
   }
+  __syncthreads();
 }
 #else
 int lane_r();                                             // provided by the host-simulation harness
@@ -103,18 +106,15 @@ static RIPP_FN Jac<Fq> g1_dbl(Jac<Fq> p) {
   r.y = M - C.dbl().dbl().dbl();
   return r;
 }
-// madd-2007-bl in five levels; exceptional cases (either operand the identity, P = +-Q) fall back to the
-// complete single-lane formulas, executed redundantly (identically) by the three lanes
+// madd-2007-bl in five levels, executed unconditionally (every thread reaches every exchange); lanes in an
+// exceptional case (either operand the identity, P = +-Q) then recompute with the complete single-thread formulas
 static RIPP_FN Jac<Fq> g1_madd(Jac<Fq> p, Aff<Fq> q) {
-  if (q.is_inf() || p.is_inf()) return p.add_mixed_body(q);
   Fq Z1Z1, d0, d1, U2, ZZZ, S2, HH, ZH2, RR, J, V, YJ, M;
   mul3(p.z, p.z, p.z, p.z, p.z, p.z, Z1Z1, d0, d1);
   mul3(q.x, Z1Z1, p.z, Z1Z1, p.z, Z1Z1, U2, ZZZ, d0);
   Fq H = U2 - p.x;
   mul3(q.y, ZZZ, H, H, p.z + H, p.z + H, S2, HH, ZH2);
-  Fq rr = S2 - p.y;
-  if (H.is_zero()) return p.add_mixed_body(q);  // doubling or the identity
-  rr = rr.dbl();
+  Fq rr = (S2 - p.y).dbl();
   Fq I = HH.dbl().dbl();
   mul3(H, I, p.x, I, rr, rr, J, V, RR);
   Jac<Fq> r;
@@ -122,6 +122,35 @@ static RIPP_FN Jac<Fq> g1_madd(Jac<Fq> p, Aff<Fq> q) {
   r.z = ZH2 - Z1Z1 - HH;
   mul3(rr, V - r.x, p.y, J, p.y, J, M, YJ, d0);
   r.y = M - YJ.dbl();
+  if (q.is_inf() || p.is_inf() || H.is_zero()) return p.add_mixed_body(q);
+  return r;
+}
+
+// Fq2x3 <-> Fq2 (same layout): the non-cooperative fallbacks and the endomorphism use the plain tower
+RIPP_HD Fq2 plain(const Fq2x3& a) { return {a.c0, a.c1}; }
+RIPP_HD Fq2x3 coop(const Fq2& a) { return {a.c0, a.c1}; }
+RIPP_HD Aff<Fq2> plain(const Aff<Fq2x3>& a) { return {plain(a.x), plain(a.y)}; }
+RIPP_HD Aff<Fq2x3> coop(const Aff<Fq2>& a) { return {coop(a.x), coop(a.y)}; }
+RIPP_HD Jac<Fq2> plain(const Jac<Fq2x3>& a) { return {plain(a.x), plain(a.y), plain(a.z)}; }
+RIPP_HD Jac<Fq2x3> coop(const Jac<Fq2>& a) { return {coop(a.x), coop(a.y), coop(a.z)}; }
+
+// the same for G2: madd-2007-bl over the cooperative Fq2 (11 exchanges instead of 29 Fq products in a row)
+static RIPP_FN Jac<Fq2x3> g2_madd(Jac<Fq2x3> p, Aff<Fq2x3> q) {
+  typedef Fq2x3 F;
+  F Z1Z1 = p.z.sqr();
+  F U2 = q.x * Z1Z1;
+  F S2 = q.y * p.z * Z1Z1;
+  F H = U2 - p.x;
+  F rr = (S2 - p.y).dbl();
+  F HH = H.sqr();
+  F I = HH.dbl().dbl();
+  F J = H * I;
+  F V = p.x * I;
+  Jac<F> r;
+  r.x = rr.sqr() - J - V.dbl();
+  r.y = rr * (V - r.x) - (p.y * J).dbl();
+  r.z = (p.z + H).sqr() - Z1Z1 - HH;
+  if (q.is_inf() || p.is_inf() || H.is_zero()) return coop(plain(p).add_mixed_body(plain(q)));
   return r;
 }
 
@@ -138,8 +167,34 @@ template <>
 struct Ops<Fq2x3> {
   typedef Fq2x3 Field;
   RIPP_HD static Jac<Fq2x3> dbl(const Jac<Fq2x3>& a) { return a.dbl_body(); }
-  RIPP_HD static Jac<Fq2x3> madd(const Jac<Fq2x3>& a, const Aff<Fq2x3>& q) { return a.add_mixed_body(q); }
+  RIPP_HD static Jac<Fq2x3> madd(const Jac<Fq2x3>& a, const Aff<Fq2x3>& q) { return g2_madd(a, q); }
 };
+
+RIPP_HD Aff<Fq> endo_map_x(const Aff<Fq>& p) { return endo_map(p); }
+RIPP_HD Aff<Fq2x3> endo_map_x(const Aff<Fq2x3>& p) { return coop(endo_map(plain(p))); }
+
+// affine form without the identity's early exit (Z = 0 inverts to 0, which gives (0, 0) = the packed identity)
+template <class F>
+RIPP_HD Aff<F> to_affine(const Jac<F>& a) {
+  return a.to_affine_with(a.z.inv());
+}
+
+// sum_i d_i E^i(p) (endo.cuh) with the team's formulas; control flow depends only on the SHARED scalar
+template <class F>
+RIPP_FN Jac<F> endo_mul(const Aff<F>& p, const EndoBits& c) {
+  Aff<F> base[4];
+  base[0] = p;
+  for (int t = 1; t < c.m; t++) base[t] = endo_map_x(base[t - 1]);
+  Jac<F> acc = Jac<F>::inf();
+  for (int j = c.nbits - 1; j >= 0; j--) {
+    acc = Ops<F>::dbl(acc);
+    for (int t = 0; t < c.m; t++) {
+      if ((c.pos[t][j >> 5] >> (j & 31)) & 1) acc = Ops<F>::madd(acc, base[t]);
+      if ((c.neg[t][j >> 5] >> (j & 31)) & 1) acc = Ops<F>::madd(acc, base[t].neg());
+    }
+  }
+  return acc;
+}
 
 template <class F>
 RIPP_FN Jac<F> mul_naf(const Aff<F>& p, const uint32_t* pos, const uint32_t* neg, int ndigits) {

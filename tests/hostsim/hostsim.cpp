@@ -201,18 +201,38 @@ static void run_x3(Fn fn) {
 }
 extern "C" {
 // out = k * p + lo with k given as NAF bitmaps (9 words each); group 1 = G1, 2 = G2
+// out = k * p + lo exactly as k_fold_w3 computes it: endomorphism digits of the canonical scalar k (8 words),
+// joint double-and-add with the team formulas, barrier-safe mixed additions, branch-free normalisation
+void hs_x3_endo_fold(int group, const uint32_t* p, const uint32_t* lo, const uint32_t* k, uint32_t* out) {
+  EndoBits c;
+  if (group == 1) endo_decompose<1>(k, c); else endo_decompose<2>(k, c);
+  run_x3([&](int r) {
+    if (group == 1) {
+      Jac<Fq> acc = x3::endo_mul<Fq>(ld<G1Aff>(p), c);
+      acc = x3::Ops<Fq>::madd(acc, ld<G1Aff>(lo));
+      G1Aff o = x3::to_affine(acc);
+      if (r == 0) st(out, o);
+    } else {
+      typedef x3::Fq2x3 F;
+      Jac<F> acc = x3::endo_mul<F>(ld<Aff<F>>(p), c);
+      acc = x3::Ops<F>::madd(acc, ld<Aff<F>>(lo));
+      Aff<F> o = x3::to_affine(acc);
+      if (r == 0) st(out, o);
+    }
+  });
+}
 void hs_x3_fold(int group, const uint32_t* p, const uint32_t* lo, const uint32_t* pos, const uint32_t* neg, int nd, uint32_t* out) {
   run_x3([&](int r) {
     if (group == 1) {
       Jac<Fq> acc = x3::mul_naf<Fq>(ld<G1Aff>(p), pos, neg, nd);
       acc = x3::g1_madd(acc, ld<G1Aff>(lo));
-      G1Aff o = acc.to_affine();
+      G1Aff o = x3::to_affine(acc);
       if (r == 0) st(out, o);
     } else {
       typedef x3::Fq2x3 F;
       Jac<F> acc = x3::mul_naf<F>(ld<Aff<F>>(p), pos, neg, nd);
-      acc = acc.add_mixed_body(ld<Aff<F>>(lo));
-      Aff<F> o = acc.to_affine();
+      acc = x3::g2_madd(acc, ld<Aff<F>>(lo));
+      Aff<F> o = x3::to_affine(acc);
       if (r == 0) st(out, o);
     }
   });

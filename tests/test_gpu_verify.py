@@ -169,3 +169,31 @@ def test_sipp_verify(ctx, n):
     assert not SIPP.verify(a, b, r, E.f12_sqr(z), proof, ctx)  # wrong claimed value
     assert not SIPP.verify(a, b, r[::-1], z, proof, ctx)
     assert _rejects(lambda: SIPP.verify(a, b, r, z, _flip(proof, 0), ctx))
+
+
+def test_full_size_round_trips(ctx):
+    """BASELINE.json's full sizes through the size-independent property the domain offers: prove -> verify accepts,
+    verify of an altered statement rejects.  TIPP aggregation of 2^12 proofs (configs[3]) and SIPP over 2^10 pairs
+    (configs[0]); inputs generated on the GPU from the synthetic scalar streams."""
+    from ripp_b200 import synth
+
+    n = 1 << 12
+    inst = synth.tipp_instance_dev(ctx, n)
+    proof = ctx.tipp_aggregate_dev(inst["srs_g1"], inst["srs_g2"], inst["a"], inst["b"], inst["c"], n)
+    assert len(proof) == 62544
+    assert ctx.tipp_verify_aggregate(inst["vsrs"], inst["vk"], inst["inputs"], proof)
+    bad = inst["inputs"].copy()
+    bad[n - 1, 0] = C.fr_enc((C.fr_dec(bad[n - 1, 0]) + 1) % E.R)
+    assert not ctx.tipp_verify_aggregate(inst["vsrs"], inst["vk"], bad, proof)
+
+    m = 1 << 10
+    a = synth.g1_points_dev(ctx, "sipp-a", m).download((m, 24))
+    b = synth.g2_points_dev(ctx, "sipp-b", m).download((m, 48))
+    r = synth.scalars_mont("sipp-r", m)
+    z = ctx.sipp_product_with_coeffs(a, b, r)
+    sp = ctx.sipp_prove(a, b, r, z)
+    assert len(sp) == 10 * 1152
+    assert ctx.sipp_verify(a, b, r, z, sp)
+    r2 = r.copy()
+    r2[5] = r[6]
+    assert not ctx.sipp_verify(a, b, r2, z, sp)

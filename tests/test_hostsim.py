@@ -190,9 +190,9 @@ def test_lazy_sum_of_products(hostsim):
             assert C._int(got) == sum(x * y for x, y in zip(a, b)) * rinv % E.P
 
 
-def test_x3_three_lane_point_arithmetic(hostsim):
-    """x3.cuh (three lanes per curve point, each lane a host thread): k * P + L against the oracle, incl. the
-    exceptional cases of the final mixed addition."""
+def test_x3_three_warp_team_point_arithmetic(hostsim):
+    """x3.cuh (a team of three warps per vector of curve points; here each role is a host thread and the exchange a
+    barrier-protected bus): k * P + L against the oracle, incl. the exceptional cases of the mixed addition."""
     import numpy as np
 
     def naf(k):
@@ -226,6 +226,21 @@ def test_x3_three_lane_point_arithmetic(hostsim):
     assert fold(1, p1, None, k) == E.g1_mul(p1, k) and fold(1, None, p1, k) == p1
     assert fold(1, p1, E.g1_neg(E.g1_mul(p1, k)), k) is None
     assert fold(2, p2, E.g2_mul(p2, k), k) == E.g2_mul(p2, 2 * k)
+    assert fold(2, p2, E.g2_neg(E.g2_mul(p2, k)), k) is None and fold(2, None, p2, k) == p2 and fold(2, p2, None, k) == E.g2_mul(p2, k)
+
+    # the shape k_fold_w3 runs: endomorphism digits + team formulas + barrier-safe additions + branch-free to_affine
+    def efold(group, p, lo, k):
+        enc, dec, w = (C.g1_enc, C.g1_dec, 24) if group == 1 else (C.g2_enc, C.g2_dec, 48)
+        return dec(hostsim.call("hs_x3_endo_fold", group, enc(p), enc(lo), C.scalar_words(k), out=w))
+
+    for k in (rnd.randrange(E.R), rnd.randrange(1 << 128), 1, 0, E.R - 1):
+        assert efold(1, p1, l1, k) == E.g1_add(E.g1_mul(p1, k), l1), k
+        assert efold(2, p2, l2, k) == E.g2_add(E.g2_mul(p2, k), l2), k
+    k = rnd.randrange(1 << 128)
+    assert efold(1, p1, E.g1_neg(E.g1_mul(p1, k)), k) is None and efold(2, p2, E.g2_neg(E.g2_mul(p2, k)), k) is None
+    assert efold(1, p1, E.g1_mul(p1, k), k) == E.g1_mul(p1, 2 * k) and efold(2, p2, E.g2_mul(p2, k), k) == E.g2_mul(p2, 2 * k)
+    assert efold(1, None, l1, k) == l1 and efold(2, None, l2, k) == l2
+    assert efold(1, p1, None, k) == E.g1_mul(p1, k) and efold(2, p2, None, k) == E.g2_mul(p2, k)
 
 
 def test_endomorphisms(hostsim):
