@@ -352,6 +352,13 @@ def main():
                                    "achieved": m / 1e12, "frac": m / imad_peak,
                                    "mac32_per_pair": FQ_MUL_PER_MILLER_PAIR * MAC32_PER_FQ_MUL}
 
+    if "msm_g1_points_per_s" in sub:
+        mm = sub["msm_g1_points_per_s"]
+        m = world * mm["points_per_gpu"] * FQ_MUL_PER_G1_MSM_POINT * MAC32_PER_FQ_MUL / (mm["ms_per_step"] * 1e-3) / world
+        roofline["msm_2^18"] = {"kernel": "whole G1 MSM (13 launches: expand, prepare, scan, scatter, accumulate, fat buckets, reductions, Horner)",
+                                "kernel_ms": mm["ms_per_step"], "achieved": m / 1e12, "frac": m / imad_peak,
+                                "mac32_per_point": FQ_MUL_PER_G1_MSM_POINT * MAC32_PER_FQ_MUL}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value_s, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
