@@ -144,8 +144,10 @@ typedef enum ripp_gipa_kind {
                                           structured_scalar_message.rs:130-136, groth16_aggregation.rs:42-48 */
   RIPP_GIPA_SCALAR_PEDERSEN_G2_G2 = 3, /* Scalar, Pedersen<G2>, Pedersen<G2>, Identity<Fr>: (Fr, Fr, G2, G2)  gipa.rs:531-536 */
   RIPP_GIPA_SCALAR_PEDERSEN_G2_G1 = 4, /* Scalar, Pedersen<G2>, Pedersen<G1>, Identity<Fr>: (Fr, Fr, G2, G1)  tipa/mod.rs:501-506 */
-  RIPP_GIPA_SCALAR_SSM = 5             /* Scalar, Pedersen<G2>, SSMPlaceholder, Identity<Fr>: (Fr, Fr, G2, -)
+  RIPP_GIPA_SCALAR_SSM = 5,            /* Scalar, Pedersen<G2>, SSMPlaceholder, Identity<Fr>: (Fr, Fr, G2, -)
                                           structured_scalar_message.rs:392-423 */
+  RIPP_GIPA_SCALAR_SSM_G1 = 6          /* Scalar, Pedersen<G1>, SSMPlaceholder, Identity<Fr>: (Fr, Fr, G1, -)
+                                          the first-tier argument of applications/poly_commit/transparent.rs:44-49 */
 } ripp_gipa_kind;
 
 /* GIPA::prove_with_aux (gipa.rs:162-178 -> _prove :181-312).  Vectors are device resident (affine

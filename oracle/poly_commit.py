@@ -184,3 +184,94 @@ class UnivariatePolynomialCommitment:
     def verify(cls, v_srs, max_degree, com, point, evaluation, proof):
         _, yd = cls.bivariate_degrees(max_degree)
         return BivariatePolynomialCommitment.verify(v_srs, com, (pow(point, yd + 1, R), point), evaluation, proof)
+
+
+# ------------------------------------------------------------------------------------------------
+# Transparent variant (/root/reference/ip_proofs/src/applications/poly_commit/transparent.rs): no trusted setup;
+# first tier = Pedersen<G1> commitments to the Y polynomials, opened with a scalar GIPA with structured message
+# (:44-56), second tier = AFGHO over those commitments, opened with the multiexponentiation GIPA with structured
+# message (:28-42).  The verifier recomputes the final commitment keys itself (O(n), gipa.rs:365-399).
+# ------------------------------------------------------------------------------------------------
+def _second_tier():
+    return O.GIPAWithSSM(O.MultiexponentiationInnerProduct(O.G1T), O.AFGHOCommitmentG1, O.IdentityCommitment(O.G1T))
+
+
+def _first_tier():
+    return O.GIPAWithSSM(O.ScalarInnerProduct, O.PedersenCommitment(O.G1T), O.IdentityCommitment(O.FrT))
+
+
+class TransparentBivariatePolynomialCommitment:
+    """transparent.rs:85-213.  ck = (first_tier_ck: y_degree + 1 G1 points, second_tier_ck: x_degree + 1 G2 points)."""
+
+    @staticmethod
+    def commit(ck, y_polynomials):
+        first, second = ck
+        assert len(second) >= len(y_polynomials)  # :106
+        padded = list(y_polynomials) + [[]] * (len(second) - len(y_polynomials))
+        coms = []
+        for yp in padded:
+            assert len(first) >= len(yp)  # :116
+            coms.append(E.msm(first, list(yp) + [0] * (len(first) - len(yp)), E.g1_add, E.g1_mul))
+        return O.AFGHOCommitmentG1.commit(second, coms), coms
+
+    @staticmethod
+    def open(ck, y_polynomials, y_polynomial_comms, point):
+        x, y = point
+        first, second = ck
+        assert len(second) >= len(y_polynomials)  # :137
+        powers_of_x = O.structured_scalar_power(len(second), x)
+        y_eval_coeffs = [0] * len(first)
+        for i, yp in enumerate(y_polynomials):
+            for j, c in enumerate(yp):
+                y_eval_coeffs[j] = (y_eval_coeffs[j] + powers_of_x[i] * c) % R
+        y_eval_comm = E.msm(first, y_eval_coeffs, E.g1_add, E.g1_mul)
+        second_proof = _second_tier().prove_with_structured_scalar_message((y_polynomial_comms, powers_of_x), (second, None))
+        powers_of_y = O.structured_scalar_power(len(first), y)
+        first_proof = _first_tier().prove_with_structured_scalar_message((y_eval_coeffs, powers_of_y), (first, None))
+        return {"second_tier_ip_proof": second_proof, "y_eval_comm": y_eval_comm, "first_tier_ip_proof": first_proof}
+
+    @staticmethod
+    def verify(ck, com, point, evaluation, proof):
+        first, second = ck
+        x, y = point
+        ok2 = _second_tier().verify_with_structured_scalar_message((second, None), (com, [proof["y_eval_comm"]]), x,
+                                                                  proof["second_tier_ip_proof"])
+        ok1 = _first_tier().verify_with_structured_scalar_message((first, None), (proof["y_eval_comm"], [evaluation]), y,
+                                                                 proof["first_tier_ip_proof"])
+        return ok2 and ok1
+
+
+def ser_transparent_opening_proof(proof):
+    """Field order of transparent.rs:79-83."""
+    return (_second_tier().gipa.ser_proof(proof["second_tier_ip_proof"]) + ser_g1(proof["y_eval_comm"])
+            + _first_tier().gipa.ser_proof(proof["first_tier_ip_proof"]))
+
+
+class TransparentUnivariatePolynomialCommitment:
+    """transparent.rs:215-318."""
+
+    @staticmethod
+    def bivariate_degrees(univariate_degree):
+        sqrt = 1 << (math.ceil(math.sqrt(univariate_degree + 1)) - 1).bit_length()  # :222-227
+        skew = 4 if sqrt >= 8 else sqrt // 2
+        return sqrt // skew - 1, sqrt * skew - 1
+
+    @staticmethod
+    def degrees_from_ck(ck):
+        return len(ck[1]) - 1, len(ck[0]) - 1
+
+    @classmethod
+    def commit(cls, ck, coeffs):
+        form = UnivariatePolynomialCommitment.bivariate_form(cls.degrees_from_ck(ck), coeffs)
+        return TransparentBivariatePolynomialCommitment.commit(ck, form)
+
+    @classmethod
+    def open(cls, ck, coeffs, y_polynomial_comms, point):
+        xd, yd = cls.degrees_from_ck(ck)
+        form = UnivariatePolynomialCommitment.bivariate_form((xd, yd), coeffs)
+        return TransparentBivariatePolynomialCommitment.open(ck, form, y_polynomial_comms, (pow(point, yd + 1, R), point))
+
+    @classmethod
+    def verify(cls, ck, com, point, evaluation, proof):
+        _, yd = cls.degrees_from_ck(ck)
+        return TransparentBivariatePolynomialCommitment.verify(ck, com, (pow(point, yd + 1, R), point), evaluation, proof)

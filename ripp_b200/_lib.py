@@ -34,7 +34,7 @@ class RippError(RuntimeError):
 
 
 GIPA_PAIRING, GIPA_MULTIEXP_PEDERSEN, GIPA_MULTIEXP_SSM = 0, 1, 2
-GIPA_SCALAR_PEDERSEN_G2_G2, GIPA_SCALAR_PEDERSEN_G2_G1, GIPA_SCALAR_SSM = 3, 4, 5
+GIPA_SCALAR_PEDERSEN_G2_G2, GIPA_SCALAR_PEDERSEN_G2_G1, GIPA_SCALAR_SSM, GIPA_SCALAR_SSM_G1 = 3, 4, 5, 6
 
 
 class LengthMismatch(RippError):

@@ -252,6 +252,7 @@ static bool gipa_spec(int kind, GipaSpec* s) {
     case RIPP_GIPA_SCALAR_PEDERSEN_G2_G2: *s = {VT_FR, VT_FR, VT_G2, VT_G2}; return true;
     case RIPP_GIPA_SCALAR_PEDERSEN_G2_G1: *s = {VT_FR, VT_FR, VT_G2, VT_G1}; return true;
     case RIPP_GIPA_SCALAR_SSM: *s = {VT_FR, VT_FR, VT_G2, VT_NONE}; return true;
+    case RIPP_GIPA_SCALAR_SSM_G1: *s = {VT_FR, VT_FR, VT_G1, VT_NONE}; return true;
   }
   return false;
 }

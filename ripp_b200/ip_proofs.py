@@ -20,6 +20,7 @@ _KIND_TYPES = {
     _lib.GIPA_SCALAR_PEDERSEN_G2_G2: ("Fr", "Fr", "G2", "G2"),
     _lib.GIPA_SCALAR_PEDERSEN_G2_G1: ("Fr", "Fr", "G2", "G1"),
     _lib.GIPA_SCALAR_SSM: ("Fr", "Fr", "G2", None),
+    _lib.GIPA_SCALAR_SSM_G1: ("Fr", "Fr", "G1", None),
 }
 
 

@@ -47,7 +47,8 @@ import hashlib
 from . import codec
 
 _KIND_TYPES = {0: ("G1", "G2", "G2", "G1"), 1: ("G1", "Fr", "G2", "G1"), 2: ("G1", "Fr", "G2", None),
-               3: ("Fr", "Fr", "G2", "G2"), 4: ("Fr", "Fr", "G2", "G1"), 5: ("Fr", "Fr", "G2", None)}
+               3: ("Fr", "Fr", "G2", "G2"), 4: ("Fr", "Fr", "G2", "G1"), 5: ("Fr", "Fr", "G2", None),
+               6: ("Fr", "Fr", "G1", None)}
 _WORDS = {"G1": 24, "G2": 48, "Fr": 8, "GT": 144}
 _SUM_ID = {"G1": 1, "G2": 2, "Fr": 3}
 _DEC = {"G1": codec.g1_dec, "G2": codec.g2_dec, "Fr": codec.fr_dec, "GT": codec.gt_dec}

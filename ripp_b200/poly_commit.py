@@ -205,3 +205,110 @@ class UnivariatePolynomialCommitment:
     def verify(cls, v_srs, max_degree, com, point, evaluation, proof, ctx=None):
         _, yd = cls.bivariate_degrees(max_degree)
         return BivariatePolynomialCommitment.verify(v_srs, com, (pow(point, yd + 1, R), point), evaluation, proof, ctx)
+
+
+# ------------------------------------------------------------------------------------------------
+# Transparent variant (applications/poly_commit/transparent.rs): no trusted setup.  First tier = Pedersen<G1>
+# commitments to the Y polynomials (MSMs over the first-tier key), second tier = AFGHO over them.  Openings are the two
+# GIPAs with structured scalar message (second tier: MULTIEXP_SSM; first tier: SCALAR_SSM_G1), both resident provers;
+# the verifier's final commitment keys are one MSM over each key vector (`ripp_gipa_verify_dev`).
+# ck = dict(first=(DeviceBuffer, y_degree + 1) G1 points, second=(DeviceBuffer, x_degree + 1) G2 points).
+# ------------------------------------------------------------------------------------------------
+def _gipa_ssm_prove(ctx, kind, a_dev, b_dev, v_dev, n):
+    return ctx.gipa_prove_dev(kind, a_dev, b_dev, v_dev, None, n)[0]
+
+
+class TransparentBivariatePolynomialCommitment:
+    """transparent.rs:85-213."""
+
+    @staticmethod
+    def setup_from_points(first_tier_ck, second_tier_ck, ctx=None):
+        """The reference draws the keys with `random_generators`; here they are given (affine tuples)."""
+        ctx = ctx or default_context()
+        return {"first": (ctx.to_device(codec.g1_vec_enc(first_tier_ck)), len(first_tier_ck)),
+                "second": (ctx.to_device(codec.g2_vec_enc(second_tier_ck)), len(second_tier_ck))}
+
+    @staticmethod
+    def commit(ck, y_polynomials, ctx=None):
+        ctx = ctx or default_context()
+        n = ck["second"][1]
+        assert n >= len(y_polynomials)  # :106
+        padded = list(y_polynomials) + [[]] * (n - len(y_polynomials))
+        coms = [_msm_g1(ctx, ck["first"][0], ck["first"][1], yp) for yp in padded]  # PedersenCommitment::commit (:119)
+        d = ctx.to_device(codec.g1_vec_enc(coms))
+        out = ctx.alloc(576)
+        ctx.pairing_ip_dev(d, ck["second"][0], n, out)
+        ctx.sync()
+        return codec.gt_dec(out.download(144)), coms
+
+    @staticmethod
+    def open(ck, y_polynomials, y_polynomial_comms, point, ctx=None):
+        """-> OpeningProof bytes: second_tier_ip_proof || y_eval_comm || first_tier_ip_proof (:79-83)."""
+        ctx = ctx or default_context()
+        x, y = point
+        n, m = ck["second"][1], ck["first"][1]
+        assert n >= len(y_polynomials)  # :137
+        powers_of_x = _powers(x, n)
+        y_eval_coeffs = [0] * m
+        for i, yp in enumerate(y_polynomials):
+            px = powers_of_x[i]
+            for j, c in enumerate(yp):
+                y_eval_coeffs[j] = (y_eval_coeffs[j] + px * c) % R
+        y_eval_comm = _msm_g1(ctx, ck["first"][0], m, y_eval_coeffs)
+        a = ctx.to_device(codec.g1_vec_enc(y_polynomial_comms))
+        b = ctx.to_device(codec.fr_vec_enc(powers_of_x))
+        second = _gipa_ssm_prove(ctx, _lib.GIPA_MULTIEXP_SSM, a, b, ck["second"][0], n)
+        a1 = ctx.to_device(codec.fr_vec_enc(y_eval_coeffs))
+        b1 = ctx.to_device(codec.fr_vec_enc(_powers(y, m)))
+        first = _gipa_ssm_prove(ctx, _lib.GIPA_SCALAR_SSM_G1, a1, b1, ck["first"][0], m)
+        return second + codec.ser_g1(y_eval_comm) + first
+
+    @staticmethod
+    def _split(proof, n):
+        """second-tier GIPAProof length for n = 2^k keys: 8 + k * 2 * (576 + 32 + 8 + 96) + 96 + 32."""
+        k = n.bit_length() - 1
+        s = 8 + k * 2 * (576 + 32 + 8 + 96) + 96 + 32
+        return proof[:s], proof[s:s + 96], proof[s + 96:]
+
+    @staticmethod
+    def verify(ck, com, point, evaluation, proof, ctx=None):
+        ctx = ctx or default_context()
+        x, y = point
+        second, y_eval_b, first = TransparentBivariatePolynomialCommitment._split(proof, ck["second"][1])
+        st2 = codec.ser_gt(com) + codec.ser_identity_output(y_eval_b)
+        ok2 = ctx.gipa_verify_dev(_lib.GIPA_MULTIEXP_SSM, ck["second"][0], None, ck["second"][1], st2, second,
+                                  codec.fr_enc(x).copy())
+        st1 = y_eval_b + codec.ser_identity_output(codec.ser_fr(evaluation))
+        ok1 = ctx.gipa_verify_dev(_lib.GIPA_SCALAR_SSM_G1, ck["first"][0], None, ck["first"][1], st1, first,
+                                  codec.fr_enc(y).copy())
+        return ok2 and ok1
+
+
+class TransparentUnivariatePolynomialCommitment:
+    """transparent.rs:215-318."""
+
+    @staticmethod
+    def bivariate_degrees(univariate_degree):
+        sqrt = 1 << (math.ceil(math.sqrt(univariate_degree + 1)) - 1).bit_length()  # :222-227
+        skew = 4 if sqrt >= 8 else sqrt // 2
+        return sqrt // skew - 1, sqrt * skew - 1
+
+    @staticmethod
+    def degrees_from_ck(ck):
+        return ck["second"][1] - 1, ck["first"][1] - 1
+
+    @classmethod
+    def commit(cls, ck, coeffs, ctx=None):
+        form = UnivariatePolynomialCommitment.bivariate_form(cls.degrees_from_ck(ck), coeffs)
+        return TransparentBivariatePolynomialCommitment.commit(ck, form, ctx)
+
+    @classmethod
+    def open(cls, ck, coeffs, y_polynomial_comms, point, ctx=None):
+        xd, yd = cls.degrees_from_ck(ck)
+        form = UnivariatePolynomialCommitment.bivariate_form((xd, yd), coeffs)
+        return TransparentBivariatePolynomialCommitment.open(ck, form, y_polynomial_comms, (pow(point, yd + 1, R), point), ctx)
+
+    @classmethod
+    def verify(cls, ck, com, point, evaluation, proof, ctx=None):
+        _, yd = cls.degrees_from_ck(ck)
+        return TransparentBivariatePolynomialCommitment.verify(ck, com, (pow(point, yd + 1, R), point), evaluation, proof, ctx)

@@ -63,3 +63,42 @@ def test_univariate_round_trip_at_reference_size(ctx):
     assert U.verify(srs["v_srs"], degree, com, z, ev, proof, ctx)
     assert not U.verify(srs["v_srs"], degree, com, z, (ev + 1) % E.R, proof, ctx)
     assert not U.verify(srs["v_srs"], degree, com, (z + 1) % E.R, ev, proof, ctx)
+
+
+def test_transparent_bivariate_matches_oracle(ctx):
+    """transparent.rs:338-393 at x_degree = y_degree = 7: the two GIPAs with structured scalar message."""
+    xd = yd = 7
+    first, second = OS.g1_points("pct-ck1", yd + 1), OS.g2_points("pct-ck2", xd + 1)
+    T, OT = PC.TransparentBivariatePolynomialCommitment, OPC.TransparentBivariatePolynomialCommitment
+    ck = T.setup_from_points(first, second, ctx)
+    ys = [[rnd.randrange(E.R) for _ in range(yd + 1)] for _ in range(xd + 1)]
+    com, y_coms = T.commit(ck, ys, ctx)
+    o_com, o_y_coms = OT.commit((first, second), ys)
+    assert com == o_com and y_coms == o_y_coms
+    point = (rnd.randrange(E.R), rnd.randrange(E.R))
+    ev = OPC.bivariate_evaluate(ys, point)
+    proof = T.open(ck, ys, y_coms, point, ctx)
+    o_proof = OT.open((first, second), ys, o_y_coms, point)
+    assert proof == OPC.ser_transparent_opening_proof(o_proof)
+    assert OT.verify((first, second), o_com, point, ev, o_proof)
+    assert T.verify(ck, com, point, ev, proof, ctx)
+    assert not T.verify(ck, com, point, (ev + 1) % E.R, proof, ctx)
+    assert not T.verify(ck, com, (point[1], point[0]), ev, proof, ctx)
+
+
+def test_transparent_univariate_round_trip(ctx):
+    """transparent.rs:395-430 shape at degree 4095 -> (x_degree, y_degree) = (15, 255); keys generated on the GPU."""
+    from ripp_b200 import synth
+
+    degree = 4095
+    U = PC.TransparentUnivariatePolynomialCommitment
+    xd, yd = U.bivariate_degrees(degree)
+    assert (xd, yd) == (15, 255)
+    ck = {"first": (synth.g1_points_dev(ctx, "pct-ck1", yd + 1), yd + 1), "second": (synth.g2_points_dev(ctx, "pct-ck2", xd + 1), xd + 1)}
+    poly = [rnd.randrange(E.R) for _ in range(degree + 1)]
+    com, y_coms = U.commit(ck, poly, ctx)
+    z = rnd.randrange(E.R)
+    ev = OPC.poly_eval(poly, z)
+    proof = U.open(ck, poly, y_coms, z, ctx)
+    assert U.verify(ck, com, z, ev, proof, ctx)
+    assert not U.verify(ck, com, z, (ev + 1) % E.R, proof, ctx)

@@ -45,3 +45,23 @@ def test_bivariate_round_trip():
     assert PC.BivariatePolynomialCommitment.verify(v_srs, com, point, ev, proof)
     assert not PC.BivariatePolynomialCommitment.verify(v_srs, com, point, (ev + 1) % E.R, proof)
     assert not PC.BivariatePolynomialCommitment.verify(v_srs, com, (point[1], point[0]), ev, proof)
+
+
+def test_transparent_round_trip():
+    """transparent.rs:338-393 at x_degree = y_degree = 3 (no trusted setup: Pedersen first tier, two GIPAs with SSM)."""
+    T = PC.TransparentBivariatePolynomialCommitment
+    ck = (OS.g1_points("pct-ck1", 4), OS.g2_points("pct-ck2", 4))
+    ys = [[rnd.randrange(E.R) for _ in range(4)] for _ in range(3)]  # one Y polynomial short: zero padded
+    com, y_coms = T.commit(ck, ys)
+    point = (rnd.randrange(E.R), rnd.randrange(E.R))
+    ev = PC.bivariate_evaluate(ys, point)
+    proof = T.open(ck, ys, y_coms, point)
+    assert T.verify(ck, com, point, ev, proof)
+    assert not T.verify(ck, com, point, (ev + 1) % E.R, proof)
+    U = PC.TransparentUnivariatePolynomialCommitment
+    assert U.bivariate_degrees(65535) == (63, 1023) and U.bivariate_degrees(15) == (1, 7)
+    coeffs = [rnd.randrange(E.R) for _ in range(14)]
+    ck2 = (OS.g1_points("pct-ck1", 8), OS.g2_points("pct-ck2", 2))
+    com, y_coms = U.commit(ck2, coeffs)
+    z = rnd.randrange(E.R)
+    assert U.verify(ck2, com, z, PC.poly_eval(coeffs, z), U.open(ck2, coeffs, y_coms, z))
