@@ -14,6 +14,8 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ms
     python tools/time_msm.py 18 > $O/${TAG}_ncu_msm.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_fold -s 30 -c 2 -o $O/${TAG}_prof_fold -f \
     python tools/time_tipp.py 12 1 > $O/${TAG}_ncu_fold.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_final_exp6 -s 10 -c 1 -o $O/${TAG}_prof_fexp -f \
+    python tools/time_tipp.py 12 1 > $O/${TAG}_ncu_fexp.log 2>&1
 timeout 400 python tools/sweep.py 20 22 > $O/${TAG}_sweep.jsonl 2> $O/${TAG}_sweep.err
 tail -3 $O/${TAG}_pytest.log
 cat $O/${TAG}_bench.json | cut -c1-600
