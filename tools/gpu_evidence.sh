@@ -16,6 +16,11 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_fo
     python tools/time_tipp.py 12 1 > $O/${TAG}_ncu_fold.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_final_exp6 -s 10 -c 1 -o $O/${TAG}_prof_fexp -f \
     python tools/time_tipp.py 12 1 > $O/${TAG}_ncu_fexp.log 2>&1
+# gpurun merges at most 64 MiB back: export the raw pages here and drop the reports
+for k in miller6 msm_acc fold fexp; do
+  ncu -i $O/${TAG}_prof_$k.ncu-rep --page raw --csv > $O/${TAG}_ncu_${k}_raw.csv 2>/dev/null
+  rm -f $O/${TAG}_prof_$k.ncu-rep
+done
 timeout 400 python tools/sweep.py 20 22 > $O/${TAG}_sweep.jsonl 2> $O/${TAG}_sweep.err
 tail -3 $O/${TAG}_pytest.log
 cat $O/${TAG}_bench.json | cut -c1-600
