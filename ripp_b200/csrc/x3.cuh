@@ -135,7 +135,9 @@ RIPP_HD Jac<Fq2> plain(const Jac<Fq2x3>& a) { return {plain(a.x), plain(a.y), pl
 RIPP_HD Jac<Fq2x3> coop(const Jac<Fq2>& a) { return {coop(a.x), coop(a.y), coop(a.z)}; }
 
 // the same for G2: madd-2007-bl over the cooperative Fq2 (11 exchanges instead of 29 Fq products in a row)
-static RIPP_FN Jac<Fq2x3> g2_madd(Jac<Fq2x3> p, Aff<Fq2x3> q) {
+// (inlined at its few call sites: 120 words of operands do not fit the register-passing convention of an
+// out-of-line call and would travel through local memory -- 20 % of the kernel's instructions when they did)
+RIPP_HD Jac<Fq2x3> g2_madd(const Jac<Fq2x3>& p, const Aff<Fq2x3>& q) {
   typedef Fq2x3 F;
   F Z1Z1 = p.z.sqr();
   F U2 = q.x * Z1Z1;
@@ -186,11 +188,17 @@ RIPP_FN Jac<F> endo_mul(const Aff<F>& p, const EndoBits& c) {
   base[0] = p;
   for (int t = 1; t < c.m; t++) base[t] = endo_map_x(base[t - 1]);
   Jac<F> acc = Jac<F>::inf();
+#pragma unroll 1
   for (int j = c.nbits - 1; j >= 0; j--) {
     acc = Ops<F>::dbl(acc);
+#pragma unroll 1
     for (int t = 0; t < c.m; t++) {
-      if ((c.pos[t][j >> 5] >> (j & 31)) & 1) acc = Ops<F>::madd(acc, base[t]);
-      if ((c.neg[t][j >> 5] >> (j & 31)) & 1) acc = Ops<F>::madd(acc, base[t].neg());
+      const bool ps = (c.pos[t][j >> 5] >> (j & 31)) & 1, ng = (c.neg[t][j >> 5] >> (j & 31)) & 1;
+      if (ps || ng) {  // one call site: the addition body is inlined once
+        Aff<F> q = base[t];
+        if (ng) q = q.neg();
+        acc = Ops<F>::madd(acc, q);
+      }
     }
   }
   return acc;

@@ -344,3 +344,76 @@ class ShardedTIPA:
             return proof + ck_base + codec.ser_g2(open_a)
         open_b = self._open(1, srs_g1_slice, slice_lo, n_srs, transcript, 1, z)
         return proof + ck_base + codec.ser_g2(open_a) + codec.ser_g1(open_b)
+
+
+def _sharded_products(ctx, comm, g1_list, g2_list, n_local):
+    """prod_i e(g1[i], g2[i]) over vectors partitioned across the ranks, for several vector pairs at once:
+    one Miller launch on the local shares, one all-gather, one combine + final-exponentiation launch."""
+    import torch
+
+    k = len(g1_list)
+    dev = g1_list[0].device
+    part = torch.zeros((k, 144), dtype=torch.int32, device=dev)
+    ctx.miller_partial_batch_dev([t.data_ptr() for t in g1_list], [t.data_ptr() for t in g2_list], n_local, part.data_ptr())
+    gathered = comm.all_gather(part).permute(1, 0, 2).contiguous()  # (k, world, 144)
+    out = torch.zeros((k, 144), dtype=torch.int32, device=dev)
+    ctx.gt_combine_batch_dev(gathered.data_ptr(), gathered.shape[1], k, out.data_ptr())
+    torch.cuda.current_stream().synchronize()
+    host = out.cpu().numpy().view(np.uint32)
+    return [codec.gt_dec(host[i]) for i in range(k)]
+
+
+def sharded_aggregate_proofs(ctx, comm, srs_g1_slice, srs_g2_slice, slice_lo, n, ck1, ck2, a, b, c, tail_len=None):
+    """aggregate_proofs (applications/groth16_aggregation.rs:77-160) for ONE batch of n Groth16 proofs partitioned
+    over the ranks of `comm`.  a, b, c (the proofs' A, B, C) and ck1 = h^(beta^(2i)), ck2 = g^(alpha^(2i)) are this
+    rank's CYCLIC shares (global index j g + k at local index j); srs_g{1,2}_slice its CONTIGUOUS slice
+    [slice_lo, ...) of the 2 n - 1 SRS powers (for the KZG openings).  All ranks return the AggregateProof bytes
+    ripp_tipp_aggregate_dev returns on one GPU."""
+    import torch
+
+    world, rank = comm.world, comm.rank
+    m = a.shape[0]
+    assert m * world == n and n & (n - 1) == 0
+    # :100-102 com_a = IP(a, ck_1), com_b = IP(ck_2, b), com_c = IP(c, ck_1)
+    com_a, com_b, com_c = _sharded_products(ctx, comm, [a, ck2, c], [ck1, b, ck1], m)
+    # :105-116 r
+    r = challenge_from_random_bytes(codec.ser_gt(com_a) + codec.ser_gt(com_b) + codec.ser_gt(com_c))
+    r_inv = pow(r, -1, codec.R)
+    # :118-131 r_vec and the rescaled vectors, for this rank's global indices j g + k
+    step, step_inv = pow(r, world, codec.R), pow(r_inv, world, codec.R)
+    rv, rvi = [pow(r, rank, codec.R)], [pow(r_inv, rank, codec.R)]
+    for _ in range(m - 1):
+        rv.append(rv[-1] * step % codec.R)
+        rvi.append(rvi[-1] * step_inv % codec.R)
+    r_vec = torch.from_numpy(codec.fr_vec_enc(rv).view(np.int32)).to(a.device)
+    r_vec_inv = torch.from_numpy(codec.fr_vec_enc(rvi).view(np.int32)).to(a.device)
+    a_r, ck1_r = torch.empty_like(a), torch.empty_like(ck1)
+    ctx.g1_scale_dev(a.data_ptr(), r_vec.data_ptr(), m, a_r.data_ptr())
+    ctx.g2_scale_dev(ck1.data_ptr(), r_vec_inv.data_ptr(), m, ck1_r.data_ptr())
+    # :124 ip_ab and the :133-136 sanity product
+    ip_ab, check = _sharded_products(ctx, comm, [a_r, a_r], [b, ck1_r], m)
+    if check != com_a:
+        raise _lib_error("com_a != IP(a_r, ck_1_r) (groth16_aggregation.rs:133-136)")
+    # :125 agg_c = MSM(c, r_vec)
+    part = torch.zeros(24, dtype=torch.int32, device=a.device)
+    ctx.msm_g1_dev(c.data_ptr(), r_vec.data_ptr(), m, part.data_ptr())
+    gathered = comm.all_gather(part).contiguous()
+    agg = torch.zeros(24, dtype=torch.int32, device=a.device)
+    ctx.seg_sum_dev(1, gathered.data_ptr(), gathered.shape[0], 1, agg.data_ptr())
+    torch.cuda.current_stream().synchronize()
+    agg_c = codec.g1_dec(agg.cpu().numpy().view(np.uint32))
+    # :138-149 the two TIPA proofs
+    n_srs = 2 * n - 1
+    t_ab, t_c = ShardedTIPA(0, ctx, comm), ShardedTIPA(2, ctx, comm)
+    if tail_len is not None:
+        t_ab.gipa.tail_len = t_c.gipa.tail_len = tail_len
+    proof_ab = t_ab.prove_with_srs_shift(srs_g1_slice, srs_g2_slice, slice_lo, n_srs, a_r, b, ck1_r, ck2, r_shift=r)
+    proof_c = t_c.prove_with_srs_shift(srs_g1_slice, srs_g2_slice, slice_lo, n_srs, c, r_vec, ck1, None)
+    return (codec.ser_gt(com_a) + codec.ser_gt(com_b) + codec.ser_gt(com_c) + codec.ser_gt(ip_ab) + codec.ser_g1(agg_c)
+            + proof_ab + proof_c)
+
+
+def _lib_error(msg):
+    from . import _lib
+
+    return _lib.RippError(_lib.RIPP_ERR_INNER_PRODUCT, msg)

@@ -174,3 +174,63 @@ def test_sharded_tipa_matches_single_gpu(kind, world):
     assert sorted(r[0] for r in res) == list(range(world))
     for r in res:
         assert r[1] is True, r[2]
+
+
+def _agg_case(ctx, n):
+    from ripp_b200 import synth
+
+    inst = synth.tipp_instance_dev(ctx, n)
+    want = ctx.tipp_aggregate_dev(inst["srs_g1"], inst["srs_g2"], inst["a"], inst["b"], inst["c"], n)
+    host = {"s1": inst["srs_g1"].download((2 * n - 1, 24)), "s2": inst["srs_g2"].download((2 * n - 1, 48)),
+            "a": inst["a"].download((n, 24)), "b": inst["b"].download((n, 48)), "c": inst["c"].download((n, 24))}
+    return host, want, inst
+
+
+def _agg_worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ripp_b200 import _lib
+        from ripp_b200.parallel import Comm, cyclic_share, shard_bounds, sharded_aggregate_proofs
+
+        torch.cuda.set_device(0)
+        ctx = _lib.Context(0)
+        h, want, inst = _agg_case(ctx, n)
+        _with_stream(ctx)
+        lo, hi = shard_bounds(2 * n - 1, rank, world)
+        sh = lambda v: _cuda(np.ascontiguousarray(cyclic_share(v, rank, world)))
+        got = sharded_aggregate_proofs(ctx, Comm(), _cuda(h["s1"][lo:hi]), _cuda(h["s2"][lo:hi]), lo, n, sh(h["s2"][::2][:n]),
+                                       sh(h["s1"][::2][:n]), sh(h["a"]), sh(h["b"]), sh(h["c"]), tail_len=2)
+        torch.cuda.synchronize()
+        ok = got == want and ctx.tipp_verify_aggregate(inst["vsrs"], inst["vk"], inst["inputs"], got)
+        q.put((rank, bool(ok), len(got)))
+    except Exception:
+        import traceback
+
+        q.put((rank, False, traceback.format_exc()))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_sharded_aggregate_matches_single_gpu(world):
+    """aggregate_proofs of ONE batch partitioned over the ranks: same AggregateProof bytes, accepted by the GPU verifier."""
+    import torch.multiprocessing as mp
+
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    port = 29900 + os.getpid() % 90 + world
+    procs = [mpc.Process(target=_agg_worker, args=(r, world, port, 16, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        assert r[1] is True, r[2]
