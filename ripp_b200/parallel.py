@@ -283,26 +283,51 @@ class ShardedGIPA:
             transcript.append(c)
             m = split
 
-        # all-gather what is left into global order (global index j g + k = local index j of rank k) ...
+        state = self._gather_tail((A, B, V, W), m, steps, transcript)
+        return state if getattr(self, "_defer", False) else self._finish(state)
+
+    def _gather_tail(self, vecs, m, steps, transcript):
+        """all-gather what is left into global order (global index j g + k = local index j of rank k): collective."""
+        import torch
+
+        world = self.comm.world
+
         def whole(t):
             if t is None:
                 return None
             t = t[:m].contiguous()
             return t if world == 1 else self.comm.all_gather(t).permute(1, 0, 2).reshape(m * world, t.shape[1]).contiguous()
 
-        A, B, V, W = whole(A), whole(B), whole(V), whole(W)
+        vecs = tuple(whole(t) for t in vecs)
         torch.cuda.current_stream().synchronize()
-        # ... and finish on every rank with the resident prover, continuing the transcript
+        return vecs, m * world, steps, transcript
+
+    def _finish(self, state, ctx=None):
+        """... and finish on every rank with the resident prover, continuing the transcript: local, no collective (so two
+        instances may finish concurrently from two host threads on two contexts)."""
+        (A, B, V, W), n_tail, steps, transcript = state
+        ctx = ctx or self.ctx
         prev = codec.fr_enc(transcript[-1]).copy() if transcript else None
-        tail, tail_tr, ck_base = self.ctx.gipa_prove_resume_dev(self.kind, A.data_ptr(), B.data_ptr(), V.data_ptr(),
-                                                                None if W is None else W.data_ptr(), m * world, prev)
+        tail, tail_tr, ck_base = ctx.gipa_prove_resume_dev(self.kind, A.data_ptr(), B.data_ptr(), V.data_ptr(),
+                                                           None if W is None else W.data_ptr(), n_tail, prev)
         k_tail = int.from_bytes(tail[:8], "little")
-        base_len = len(tail) - 8 - (len(steps[0]) * k_tail if steps else 0)
         if not steps:  # everything was proved by the resident prover
             return tail, codec.fr_vec_dec(tail_tr), ck_base
+        base_len = len(tail) - 8 - len(steps[0]) * k_tail
         tail_steps, r_base = tail[8:len(tail) - base_len], tail[len(tail) - base_len:]
         proof = (k_tail + len(steps)).to_bytes(8, "little") + tail_steps + b"".join(reversed(steps)) + r_base
         return proof, codec.fr_vec_dec(tail_tr) + transcript[::-1], ck_base
+
+    def rounds_dev(self, a, b, v, w=None, tail_len=None):
+        """The collective part only: partitioned rounds + the gather of the tail vectors.  -> state for finish()."""
+        self._defer = True
+        try:
+            return self.prove_with_aux_dev(a, b, v, w, tail_len)
+        finally:
+            self._defer = False
+
+    def finish(self, state, ctx=None):
+        return self._finish(state, ctx)
 
 
 class ShardedTIPA:
@@ -333,8 +358,12 @@ class ShardedTIPA:
     def prove_with_srs_shift(self, srs_g1_slice, srs_g2_slice, slice_lo, n_srs, a, b, v, w=None, r_shift=1):
         """srs_g{1,2}_slice: this rank's CONTIGUOUS slice [slice_lo, slice_lo + len) of g^(alpha^i) / h^(beta^i),
         i < n_srs = 2 n - 1; a, b, v, w: this rank's cyclic shares.  -> TIPAProof / TIPAWithSSMProof bytes."""
+        return self.open_keys(srs_g1_slice, srs_g2_slice, slice_lo, n_srs, self.gipa.prove_with_aux_dev(a, b, v, w), r_shift)
+
+    def open_keys(self, srs_g1_slice, srs_g2_slice, slice_lo, n_srs, gipa_out, r_shift=1):
+        """The KZG challenge and the sharded openings of the final commitment keys (tipa/mod.rs:191-229), given the GIPA output."""
         g = self.gipa
-        proof, transcript, ck_base = g.prove_with_aux_dev(a, b, v, w)
+        proof, transcript, ck_base = gipa_out
         ssm = g.tw is None
         tinv = [pow(x, -1, codec.R) for x in transcript]
         z = challenge_from_random_bytes(codec.ser_fr(transcript[0]) + ck_base)
@@ -407,8 +436,32 @@ def sharded_aggregate_proofs(ctx, comm, srs_g1_slice, srs_g2_slice, slice_lo, n,
     t_ab, t_c = ShardedTIPA(0, ctx, comm), ShardedTIPA(2, ctx, comm)
     if tail_len is not None:
         t_ab.gipa.tail_len = t_c.gipa.tail_len = tail_len
-    proof_ab = t_ab.prove_with_srs_shift(srs_g1_slice, srs_g2_slice, slice_lo, n_srs, a_r, b, ck1_r, ck2, r_shift=r)
-    proof_c = t_c.prove_with_srs_shift(srs_g1_slice, srs_g2_slice, slice_lo, n_srs, c, r_vec, ck1, None)
+    # partitioned rounds of both recursions (collectives, one after the other), then the two latency-bound tails
+    # concurrently: two host threads, two contexts (the library releases the GIL inside the C call)
+    import threading
+
+    st_ab = t_ab.gipa.rounds_dev(a_r, b, ck1_r, ck2)
+    st_c = t_c.gipa.rounds_dev(c, r_vec, ck1, None)
+    side_ctx, side_stream = t_c.gipa._helper(0)
+    t_c.gipa._fork(side_stream)
+    res = {}
+
+    def run(name, gipa, state, cx):
+        try:
+            res[name] = gipa.finish(state, cx)
+        except Exception as e:  # re-raised below on the calling thread
+            res[name] = e
+
+    th = threading.Thread(target=run, args=("c", t_c.gipa, st_c, side_ctx))
+    th.start()
+    run("ab", t_ab.gipa, st_ab, ctx)
+    th.join()
+    t_c.gipa._join(side_stream)
+    for v in res.values():
+        if isinstance(v, Exception):
+            raise v
+    proof_ab = t_ab.open_keys(srs_g1_slice, srs_g2_slice, slice_lo, n_srs, res["ab"], r_shift=r)
+    proof_c = t_c.open_keys(srs_g1_slice, srs_g2_slice, slice_lo, n_srs, res["c"])
     return (codec.ser_gt(com_a) + codec.ser_gt(com_b) + codec.ser_gt(com_c) + codec.ser_gt(ip_ab) + codec.ser_g1(agg_c)
             + proof_ab + proof_c)
 
