@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 # Algorithmic Fq-product counts of the reference algorithm, measured by tests/test_hostsim.py::test_op_counts
 # (own Fq12 accumulator per pair); one Fq Montgomery product = 2*12^2 + 12 = 300 MAC32.
 FQ_MUL_PER_MILLER_PAIR = 6700
-FQ_MUL_PER_FINAL_EXP = 8276
+FQ_MUL_PER_FINAL_EXP = 7668   # + one Fq inversion, which is divsteps (modinv.cuh), not field products
 FQ_MUL_PER_G1_MUL_255 = 255 * 7 + 127 * 11 + 4        # dbl-2009-l 2M+5S, madd-2007-bl 7M+4S, + to-affine products
 FQ_MUL_PER_G2_MUL_128 = (128 * 16 + 64 * 29 + 10)     # same formulas over Fq2 (M2 = 3, S2 = 2 Fq products)
 FQ_MUL_PER_G1_MSM_POINT = 26 * 11                      # c = 10 -> 26 windows x one mixed addition per point

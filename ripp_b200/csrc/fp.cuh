@@ -10,6 +10,7 @@
 #pragma once
 #include "limb.cuh"
 #include "constants.cuh"
+#include "modinv.cuh"
 
 namespace ripp {
 
@@ -382,18 +383,23 @@ struct alignas(16) Fp {
     detail::final_sub<P>(r.v);
     return r;
   }
+  // a - b, plus p if that borrowed.  The add-back chain does not wait for the borrow (it would make the two
+  // 12-link carry chains strictly sequential: ~110 cycles on a lone warp): t + p is formed limb by limb right
+  // behind t = a - b, and the borrow only selects between the two at the end.
   RIPP_HD Fp operator-(const Fp& b) const {
     using namespace limb;
     Fp r;
-    uint32_t mask;
-    sub_cc(r.v[0], v[0], b.v[0]);
+    uint32_t t[N], u[N], mask;
+    sub_cc(t[0], v[0], b.v[0]);
 #pragma unroll
-    for (int i = 1; i < N; i++) subc_cc(r.v[i], v[i], b.v[i]);
+    for (int i = 1; i < N; i++) subc_cc(t[i], v[i], b.v[i]);
     subc(mask, 0, 0);
-    add_cc(r.v[0], r.v[0], P::p(0) & mask);
+    add_cc(u[0], t[0], P::p(0));
 #pragma unroll
-    for (int i = 1; i < N - 1; i++) addc_cc(r.v[i], r.v[i], P::p(i) & mask);
-    addc(r.v[N - 1], r.v[N - 1], P::p(N - 1) & mask);
+    for (int i = 1; i < N - 1; i++) addc_cc(u[i], t[i], P::p(i));
+    addc(u[N - 1], t[N - 1], P::p(N - 1));
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = mask ? u[i] : t[i];
     return r;
   }
   RIPP_HD Fp operator-() const { return zero() - *this; }
@@ -436,8 +442,18 @@ struct alignas(16) Fp {
     o.v[0] = 1;
     return *this * o;
   }
-  // a^(p-2); returns 0 for a = 0
+  // a^-1 (0 for a = 0) by safegcd divsteps (modinv.cuh): ~25 k simple instructions instead of the ~570 products in
+  // series of Fermat's a^(p-2).  The Montgomery value a R is inverted as an integer, (a R)^-1 = a^-1 R^-1, and
+  // brought back to Montgomery form with one product by R^3.
   RIPP_FN Fp inv() const {
+    Fp x, r2;
+    modinv::inverse_words<P>(x.v, v);
+#pragma unroll
+    for (int i = 0; i < N; i++) r2.v[i] = P::r2(i);
+    return x * (r2 * r2);
+  }
+  // a^(p-2), kept as the independent cross-check of inv() (tests) and for A/B timing
+  RIPP_FN Fp inv_fermat() const {
     Fp r = one();
     for (int i = P::BITS - 1; i >= 0; i--) {
       r = r.sqr();

@@ -25,9 +25,12 @@ def test_prime_field(hostsim, pre, p, n, radix):
         assert C._int(hostsim.call("hs_%s_add" % pre, w(a), w(b), out=n)) == (a + b) % p
         assert C._int(hostsim.call("hs_%s_sub" % pre, w(a), w(b), out=n)) == (a - b) % p
         assert C._int(hostsim.call("hs_%s_half" % pre, w(a), w(b), out=n)) == a * pow(2, -1, p) % p
-    for _ in range(10):
-        a = rnd.randrange(1, p)
-        assert C._int(hostsim.call("hs_%s_inv" % pre, w(a * radix % p), w(0), out=n)) == pow(a, -1, p) * radix % p
+    # inversion (safegcd divsteps, modinv.cuh) on Montgomery values, incl. the ends of the range and 0 -> 0
+    edge = [1, 2, 3, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, 1 << 30, (1 << 30) - 1, 1 << (32 * n - 4) if (1 << (32 * n - 4)) < p else 5,
+            pow(2, -1, p), rinv, radix % p]
+    for a in edge + [rnd.randrange(1, p) for _ in range(400)]:
+        assert C._int(hostsim.call("hs_%s_inv" % pre, w(a * radix % p), w(0), out=n)) == pow(a, -1, p) * radix % p, a
+    assert C._int(hostsim.call("hs_%s_inv" % pre, w(0), w(0), out=n)) == 0
 
 
 def test_fq2(hostsim):
