@@ -33,7 +33,12 @@ static MsmPlan msm_plan(size_t n, int bits = 255) {
   MsmPlan p;
   // ~32 points per bucket: long enough that the Poisson spread of bucket sizes does not idle most of a
   // warp (at 4 per bucket a warp runs at max/mean ~ 2.5x), short enough for the small MSMs of late rounds
-  p.c = lg - 5;
+  static int shift = -1;  // RIPP_B200_MSM_SHIFT: log2 of the target points per bucket (tuning runs)
+  if (shift < 0) {
+    const char* e = getenv("RIPP_B200_MSM_SHIFT");
+    shift = e ? atoi(e) : 5;
+  }
+  p.c = lg - shift;
   if (p.c < 4) p.c = 4;
   if (p.c > 16) p.c = 16;
   p.nw = (bits + p.c - 1) / p.c;
