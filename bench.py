@@ -48,7 +48,7 @@ LOG_PAIRS = 16
 LOG_MSM = 18
 LOG_GIPA = 18
 # per-launch DRAM traffic of the kernel classes measured once with `ncu --set full` (profiles/README.md)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"fold": 82176, "miller": 19165440, "msm": 109165824}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {"fold": 150144, "miller": 19164928, "msm": 108558848, "final_exp": 711168}
 METRIC = "tipp_groth16_aggregate_prove_seconds_at_2^12_proofs"
 DTYPE = "u32-limb Montgomery (BLS12-381 Fq 381-bit / Fr 255-bit)"
 
@@ -337,8 +337,8 @@ def main():
         "kernel": "%s kernels of one aggregation (%d timed scopes)" % (dom, dom_launches),
         "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TMAC32/s", "frac": achieved / imad_peak,
         # dram__bytes_read + write per launch of the dominant class from the committed `ncu --set full` capture
-        # (profiles/r1c_ncu_fold_raw.csv: 63 KB G1 / 101 KB G2 per late-round fold launch; Miller 2^16: 19 MB)
-        "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(dom), "traffic_source": "profiles/r1c_ncu_*_raw.csv (static, from the committed ncu capture)",
+        # (profiles/r1f_ncu_fold_raw.csv: 100 KB G1 / 201 KB G2 per late-round team-fold launch; Miller 2^16: 19 MB)
+        "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(dom), "traffic_source": "profiles/r1f_ncu_*_raw.csv (static, from the committed ncu capture)",
         "kernel_ms": dom_ms,
         "peak_source": "ripp_bench_imad in this run: independent IMAD.WIDE.U32 chains, all SMs",
         "peak_imad32_tmacs": imad32_peak / 1e12, "peak_carry_chain_tmacs": chain_peak / 1e12,
