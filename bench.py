@@ -119,6 +119,114 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_config5(args):
+    """BASELINE configs[4]: scaling sweep of the two leaf inner products.  Each point is ONE instance of n elements
+    sharded by contiguous slices over the ranks: per-rank partial (Miller product without final exponentiation / MSM
+    point), one all-gather, combine on every rank.  CUDA events on the shared stream, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ripp_b200 import _lib, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    os.environ["NCCL_DEBUG_FILE"] = "/tmp/ripp_b200_nccl_%h_%p.log"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = _lib.Context(local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    imad_peak, _ = ctx.bench_imad(0, 4096)
+    max_p, max_m = 20, 22
+
+    def timed(fn, reps=3):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for s_, e_ in evs:
+            s_.record()
+            fn()
+            e_.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([min(s_.elapsed_time(e_) for s_, e_ in evs)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def emit(line):
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+
+    nl_p = (1 << max_p) // world
+    a = synth.g1_points_dev(ctx, "cfg5-a", nl_p, seed=rank)
+    b = synth.g2_points_dev(ctx, "cfg5-b", nl_p, seed=rank)
+    part = torch.zeros(144, dtype=torch.int32, device="cuda")
+    gath = torch.zeros(world * 144, dtype=torch.int32, device="cuda")
+    res = torch.zeros(144, dtype=torch.int32, device="cuda")
+    for lg in range(10, max_p + 1, 2):
+        n = 1 << lg
+        nl = n // world
+
+        def pairing():
+            if world == 1:
+                ctx.pairing_ip_dev(a, b, nl, res.data_ptr())
+            else:
+                ctx.miller_partial_dev(a, b, nl, part.data_ptr())
+                dist.all_gather_into_tensor(gath, part)
+                ctx.gt_combine_dev(gath.data_ptr(), world, res.data_ptr())
+
+        ms = timed(pairing)
+        emit({"config": "BASELINE configs[4]", "op": "PairingInnerProduct", "log_n": lg, "n_gpus": world, "scaling": "strong",
+              "ms": round(ms, 3), "pairs_per_s": round(n / ms * 1e3),
+              "frac_of_imad_wide_peak_all_gpus": round(n * FQ_MUL_PER_MILLER_PAIR * MAC32_PER_FQ_MUL / (ms * 1e-3) / (imad_peak * world), 4)})
+    a.free()
+    b.free()
+    nl_m = (1 << max_m) // world
+    bases = synth.g1_points_dev(ctx, "cfg5-m", nl_m, seed=rank)
+    sc = ctx.to_device(synth.scalars_mont("cfg5-s", nl_m, seed=rank))
+    ppt = torch.zeros(24, dtype=torch.int32, device="cuda")
+    gpt = torch.zeros(world * 24, dtype=torch.int32, device="cuda")
+    rpt = torch.zeros(24, dtype=torch.int32, device="cuda")
+    for lg in range(10, max_m + 1, 2):
+        n = 1 << lg
+        nl = n // world
+
+        def msm():
+            if world == 1:
+                ctx.msm_g1_dev(bases, sc, nl, rpt.data_ptr())
+            else:
+                ctx.msm_g1_dev(bases, sc, nl, ppt.data_ptr())
+                dist.all_gather_into_tensor(gpt, ppt)
+                ctx.seg_sum_dev(1, gpt.data_ptr(), world, 1, rpt.data_ptr())
+
+        ms = timed(msm)
+        emit({"config": "BASELINE configs[4]", "op": "MultiexponentiationInnerProduct<G1>", "log_n": lg, "n_gpus": world,
+              "scaling": "strong", "ms": round(ms, 3), "points_per_s": round(n / ms * 1e3)})
+    bases.free()
+    sc.free()
+    if world == 1:
+        # the reference's CPU path beside it (compiled restatement, all host cores), bounded sizes
+        from oracle import cpu_baseline
+
+        for lg in (10, 14):
+            r = cpu_baseline.pairing_pairs_per_s(1 << lg)
+            emit({"config": "BASELINE configs[4]", "op": "PairingInnerProduct", "impl": "cpu restatement (port)", "log_n": lg,
+                  "cores": r["cores"], "ms": round(1e3 * r["seconds"], 1), "pairs_per_s": round(r["value"])})
+        for lg in (14, 18):
+            r = cpu_baseline.msm_points_per_s(1 << lg)
+            emit({"config": "BASELINE configs[4]", "op": "MultiexponentiationInnerProduct<G1>", "impl": "cpu restatement (port)",
+                  "log_n": lg, "cores": r["cores"], "ms": round(1e3 * r["seconds"], 1), "points_per_s": round(r["value"])})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -128,9 +236,15 @@ def main():
     ap.add_argument("--logn", type=int, default=LOG_PROOFS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub-metrics", action="store_true")
+    ap.add_argument("--config5", action="store_true",
+                    help="BASELINE configs[4] instead of the headline: sweep n = 2^10 .. 2^22 of the pairing and MSM inner "
+                         "products, ONE instance of n elements sharded over the N ranks (strong scaling), one JSON line per point; "
+                         "at N = 1 the CPU restatement is timed beside it on bounded sizes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config5:
+        return run_config5(args)
 
     import numpy as np
     import torch

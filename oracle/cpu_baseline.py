@@ -69,3 +69,19 @@ def pairing_pairs_per_s(sample_pairs=2048, threads=None):
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "pairs/s", "cores": be.cpu.threads, "kind": "port", "seconds": dt,
             "sample": "%d pairs" % n}
+
+
+def msm_points_per_s(sample_points=1 << 14, threads=None):
+    """G1 MSM (arkworks' bucket method as restated in oracle/cpu) on `sample_points` synthetic points."""
+    from .cpu import binding
+
+    be = binding.CppBackend(threads)
+    n = sample_points
+    sc = synth.scalars("cfg3-b", n)
+    g1 = be.mul_vec_g1(be.vec_g1([E.G1_GEN] * n), synth.scalars("cfg3-a", n))
+    fr = be.vec_fr(sc)
+    t0 = time.perf_counter()
+    be.msm_g1(g1, fr)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "points/s", "cores": be.cpu.threads, "kind": "port", "seconds": dt,
+            "sample": "%d points" % n}
