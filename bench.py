@@ -53,6 +53,28 @@ METRIC = "tipp_groth16_aggregate_prove_seconds_at_2^12_proofs"
 DTYPE = "u32-limb Montgomery (BLS12-381 Fq 381-bit / Fr 255-bit)"
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly the JSON line(s): anything a library prints to fd 1 (NCCL's version banner, whatever
+    NCCL_DEBUG the box sets) is sent to stderr; the JSON is written to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def _clock_sampler(stop, samples):
     q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -132,8 +154,8 @@ def run_config5(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    _claim_stdout()
     torch.cuda.set_device(local_rank)
-    os.environ["NCCL_DEBUG_FILE"] = "/tmp/ripp_b200_nccl_%h_%p.log"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)
@@ -162,7 +184,7 @@ def run_config5(args):
 
     def emit(line):
         if rank == 0:
-            print(json.dumps(line), flush=True)
+            _emit_json(line)
 
     nl_p = (1 << max_p) // world
     a = synth.g1_points_dev(ctx, "cfg5-a", nl_p, seed=rank)
@@ -256,9 +278,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
-    # rank 0 prints exactly ONE JSON line on stdout: NCCL's version banner / debug output (it writes to stdout at
-    # NCCL_DEBUG >= VERSION) goes to a file instead
-    os.environ["NCCL_DEBUG_FILE"] = "/tmp/ripp_b200_nccl_%h_%p.log"
+    # rank 0 prints exactly ONE JSON line on stdout: NCCL's version banner (it goes to fd 1 whenever NCCL_DEBUG is
+    # set, whatever NCCL_DEBUG_FILE says) is diverted to stderr
+    _claim_stdout()
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = _lib.Context(local_rank)
@@ -499,7 +521,7 @@ def main():
                                         "sample": info["sample"]}
             except Exception as ex:  # the GPU numbers stand on their own
                 line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
-        print(json.dumps(line))
+        _emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
