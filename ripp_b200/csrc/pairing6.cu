@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(32) k_gt_pow6(const Fq12* __restrict__ in, con
 // out = prod_i in[i]^sc[i]  (device memory; in: n Fq12, sc: n Fr Montgomery)
 int ripp_gt_multiexp_l6(ripp_ctx* ctx, const void* in, const void* sc, size_t n, void* out) {
   CU(cudaSetDevice(ctx->device));
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};  // function attributes are per device
+  bool& attr_done = attr_done_dev[ctx->device & 63];
   if (!attr_done) {
     CU(cudaFuncSetAttribute(k_reduce6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * R6_GROUP_WORDS * 4));
     attr_done = true;
@@ -185,7 +186,8 @@ int ripp_gt_multiexp_l6(ripp_ctx* ctx, const void* in, const void* sc, size_t n,
 template <int KP>
 static int launch_miller6(ripp_ctx* ctx, Miller6Batch& b, size_t n, Fq12* dst, size_t* nwarps_out) {
   constexpr int SM = M6_WARPS * 6 * group_words(M6_NREG, KP) * 4;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};  // function attributes are per device
+  bool& attr_done = attr_done_dev[ctx->device & 63];
   if (!attr_done) {
     CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
     attr_done = true;
@@ -203,7 +205,8 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
                           bool with_final_exp) {
   if (nseg <= 0 || nseg > RIPP_MAX_BATCH) return fail(RIPP_ERR_ARG, "bad segment count");
   CU(cudaSetDevice(ctx->device));
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};  // function attributes are per device
+  bool& attr_done = attr_done_dev[ctx->device & 63];
   if (!attr_done) {
     CU(cudaFuncSetAttribute(k_reduce6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * R6_GROUP_WORDS * 4));
     CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
@@ -270,7 +273,8 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
 // out[s] = final_exponentiation(prod_j in[s*T + j])
 int ripp_final_exp_l6(ripp_ctx* ctx, const void* in, uint32_t T, void* out, int nseg) {
   CU(cudaSetDevice(ctx->device));
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};  // function attributes are per device
+  bool& attr_done = attr_done_dev[ctx->device & 63];
   if (!attr_done) {
     CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
     attr_done = true;
