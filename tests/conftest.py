@@ -37,16 +37,26 @@ class HostSim:
         return o
 
 
-@pytest.fixture(scope="session")
-def hostsim():
+def _build_hostsim(flags):
     src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
-    flags = os.environ.get("RIPP_HOSTSIM_FLAGS", "").split()  # e.g. -DRIPP_L6_SHARED_CODE=0 to test the inlined engine
     so = os.path.join(ROOT, "tests", "hostsim", "_hostsim%s.so" % ("_" + str(abs(hash(tuple(flags))) % 10**6) if flags else ""))
     csrc = os.path.join(ROOT, "ripp_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC"] + flags + ["-o", so, src], check=True)
     return HostSim(ctypes.CDLL(so))
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    # RIPP_HOSTSIM_FLAGS: extra -D flags for the default harness (development runs)
+    return _build_hostsim(os.environ.get("RIPP_HOSTSIM_FLAGS", "").split())
+
+
+@pytest.fixture(scope="session")
+def hostsim_shared_code():
+    """The device headers with the opt-in single-copy multiply-accumulate engine (l6.cuh: -DRIPP_L6_SHARED_CODE)."""
+    return _build_hostsim(["-DRIPP_L6_SHARED_CODE"])
 
 
 @pytest.fixture(scope="session")

@@ -263,3 +263,21 @@ def test_endo_scalar_multiplication(hostsim):
         kw = C.scalar_words(k)
         assert C.g1_dec(hostsim.call("hs_g1_endo_mul", C.g1_enc(p), kw, out=24)) == E.g1_mul(p, k), k
         assert C.g2_dec(hostsim.call("hs_g2_endo_mul", C.g2_enc(q), kw, out=48)) == E.g2_mul(q, k), k
+
+
+def test_l6_shared_code_engine(hostsim_shared_code):
+    """The opt-in out-of-line engine (one copy of the multiply-accumulate loop for product / squaring / line product)
+    computes the same values as the inlined one."""
+    hs = hostsim_shared_code
+    a, b = rf12(), rf12()
+    ea, eb = C.gt_enc(a), C.gt_enc(b)
+    op = lambda code, x, y: C.gt_dec(hs.call("hs_l6_op", code, x, y, out=144))
+    assert op(0, ea, eb) == E.f12_mul(a, b)
+    assert op(1, ea, eb) == E.f12_sqr(a)
+    assert op(5, ea, eb) == E.f12_inv(a)
+    d0, d1, d4 = rf2(), rf2(), rf2()
+    got = hs.call("hs_l6_mul_line", ea, C.fq2_enc(d0), C.fq2_enc(d1), C.fq2_enc(d4), out=144)
+    assert C.gt_dec(got) == E.f12_mul(a, (d0, (0, 0), d1, d4, (0, 0), (0, 0)))
+    p, q = E.g1_mul(E.G1_GEN, 321), E.g2_mul(E.G2_GEN, 654)
+    f = E.miller_loop(p, q)
+    assert C.gt_dec(hs.call("hs_l6_op", 7, C.gt_enc(f), C.gt_enc(f), out=144)) == E.final_exponentiation(f)
