@@ -31,6 +31,7 @@ def _oracle_gipa(kind):
         _lib.GIPA_SCALAR_PEDERSEN_G2_G2: (O.ScalarInnerProduct, O.PedersenCommitment(G2), O.PedersenCommitment(G2), O.IdentityCommitment(Fr)),
         _lib.GIPA_SCALAR_PEDERSEN_G2_G1: (O.ScalarInnerProduct, O.PedersenCommitment(G2), O.PedersenCommitment(G1), O.IdentityCommitment(Fr)),
         _lib.GIPA_SCALAR_SSM: (O.ScalarInnerProduct, O.PedersenCommitment(G2), O.SSMPlaceholderCommitment, O.IdentityCommitment(Fr)),
+        _lib.GIPA_SCALAR_SSM_G1: (O.ScalarInnerProduct, O.PedersenCommitment(G1), O.SSMPlaceholderCommitment, O.IdentityCommitment(Fr)),
     }
     return table[kind]
 
@@ -43,6 +44,7 @@ def _inputs(kind, n, seed=0):
         _lib.GIPA_SCALAR_PEDERSEN_G2_G2: ("Fr", "Fr", "G2", "G2"),
         _lib.GIPA_SCALAR_PEDERSEN_G2_G1: ("Fr", "Fr", "G2", "G1"),
         _lib.GIPA_SCALAR_SSM: ("Fr", "Fr", "G2", None),
+        _lib.GIPA_SCALAR_SSM_G1: ("Fr", "Fr", "G1", None),
     }[kind]
 
     def gen(t, tag):
@@ -57,7 +59,7 @@ def _inputs(kind, n, seed=0):
     return gen(ta, "gipa-a"), gen(tb, "gipa-b"), gen(tv, "gipa-v"), gen(tw, "gipa-w")
 
 
-@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4, 5, 6])
 def test_gipa_proof_bytes_match_oracle(ctx, kind):
     a, b, v, w = _inputs(kind, N)
     IP, LMC, RMC, IPC = _oracle_gipa(kind)

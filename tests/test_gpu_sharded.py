@@ -15,7 +15,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
-KINDS = [0, 1, 2, 3, 4, 5]
+KINDS = [0, 1, 2, 3, 4, 5, 6]
 
 
 def _vectors(ctx, kind, n):

@@ -54,7 +54,7 @@ def test_gt_multiexp(ctx):
         assert C.gt_dec(out.download(144)) == acc
 
 
-@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("kind", [0, 1, 2, 3, 4, 5, 6])
 def test_gipa_verify(ctx, kind):
     a, b, v, w = _inputs(kind, N)
     IP, LMC, RMC, IPC = _oracle_gipa(kind)
