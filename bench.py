@@ -41,7 +41,9 @@ FQ_MUL_PER_MILLER_PAIR = 6700
 FQ_MUL_PER_FINAL_EXP = 7668   # + one Fq inversion, which is divsteps (modinv.cuh), not field products
 FQ_MUL_PER_G1_MUL_255 = 255 * 7 + 127 * 11 + 4        # dbl-2009-l 2M+5S, madd-2007-bl 7M+4S, + to-affine products
 FQ_MUL_PER_G2_MUL_128 = (128 * 16 + 64 * 29 + 10)     # same formulas over Fq2 (M2 = 3, S2 = 2 Fq products)
-FQ_MUL_PER_G1_MSM_POINT = 26 * 11                      # c = 10 -> 26 windows x one mixed addition per point
+# arkworks-style Pippenger, c = 16 -> 16 windows x one mixed Jacobian addition (11 Fq products)
+# per point, bucket reduction not counted.  (Round 1 used 26 x 11 for its own c = 10 plan, which flattered the fraction.)
+FQ_MUL_PER_G1_MSM_POINT = 16 * 11
 MAC32_PER_FQ_MUL = 300
 LOG_PROOFS = 12
 LOG_PAIRS = 16
@@ -103,6 +105,13 @@ def _clocks_summary(samples):
             "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None, "reasons": sorted(reasons)}
 
 
+def _host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def tipp_algorithmic_macs(n):
     """MAC32 per aggregation by kernel class (SURVEY.md App. C op inventory)."""
     lg = n.bit_length() - 1
@@ -122,15 +131,15 @@ def run_reference(args):
     from oracle import cpu_baseline
 
     n = 1 << args.logn
-    work = cpu_baseline.TippWorkload(n)
-    for _ in range(min(args.warmup, 1)):
-        work.run()
-    times = [work.run() for _ in range(args.steps)]
-    v = sum(times) / len(times)
+    # all host cores, whatever OMP_NUM_THREADS says (torch.distributed.run exports OMP_NUM_THREADS=1 to every rank)
+    work = cpu_baseline.TippWorkload(n, threads=_host_threads())
+    work.run()  # one untimed warm-up: page in the tables, spin up the OpenMP team
+    times = sorted(work.run() for _ in range(args.steps))
+    v = times[len(times) // 2]  # median
     info = work.info()
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * v, "higher_is_better": False, "scaling": "weak",
+        "warmup": 1, "ms_per_step": 1e3 * v, "higher_is_better": False, "scaling": "weak",
         "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
         "config": {"workload": "TIPP aggregate_proofs of 2^%d Groth16 proofs, BLS12-381 (BASELINE configs[3]); CPU restatement of the reference path" % args.logn,
                    "proofs": n},
@@ -514,11 +523,19 @@ def main():
             try:
                 from oracle import cpu_baseline
 
-                work = cpu_baseline.TippWorkload(n)
-                secs = work.run()
+                work = cpu_baseline.TippWorkload(n, threads=_host_threads())
+                work.run()  # warm-up
+                secs = sorted(work.run() for _ in range(3))[1]
                 info = work.info()
                 line["cpu_baseline"] = {"value": secs, "unit": "s", "cores": info["cores"], "kind": info["kind"],
-                                        "sample": info["sample"]}
+                                        "sample": info["sample"] + "; median of 3 after one warm-up"}
+                # the checker's proof of the same seeded statement, byte for byte against the GPU's (the oracle is the
+                # checker here, never the thing measured)
+                from oracle import protocols as O
+
+                line["parity_bytes_equal"] = bool(O.ser_aggregate_proof(work.proof) == proof == host_proof)
+                line["parity_note"] = ("AggregateProof bytes (%d B) of the timed GPU step == the CPU oracle's proof of the same "
+                                       "synthetic instance (seed 0)" % len(proof))
             except Exception as ex:  # the GPU numbers stand on their own
                 line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
         _emit_json(line)

@@ -367,3 +367,65 @@ def msm(points, scalars, add, mul):
     for pt, s in zip(points, scalars):
         acc = add(acc, mul(pt, s))
     return acc
+
+
+# ----------------------------------------------------------------------------- subgroup membership
+# What ark-serialize's `Valid::check` enforces when the reference deserialises proof elements
+# (ark-ec short_weierstrass Affine: on curve and in the prime-order subgroup; PairingOutput: order r).
+# The definition ([r]P = O, f^r = 1) and the endomorphism forms the CUDA verifier evaluates
+# (M. Scott, "A note on group membership tests for G1, G2 and GT on BLS pairing-friendly curves", ePrint
+# 2021/1130); tests/test_oracle.py checks that the two agree on points outside the subgroups.
+def _mul_raw(pt, k, add):
+    """[k]pt without reducing k modulo r (pt may lie outside the prime-order subgroup)."""
+    acc = None
+    for bit in bin(k)[2:] if k else "":
+        acc = add(acc, acc)
+        if bit == "1":
+            acc = add(acc, pt)
+    return acc
+
+
+def g1_in_subgroup(pt):
+    return pt is None or (g1_is_on_curve(pt) and _mul_raw(pt, R, g1_add) is None)
+
+
+def g2_in_subgroup(pt):
+    return pt is None or (g2_is_on_curve(pt) and _mul_raw(pt, R, g2_add) is None)
+
+
+def gt_in_subgroup(f):
+    return f12_pow(f, R) == F12_ONE
+
+
+ENDO_BETA = 0x1A0111EA397FE699EC02408663D4DE85AA0D857D89759AD4897D29650FB85F9B409427EB4F49FFFD8BFD00000000AAAC
+_PSI_CX = f2_inv(f2_pow(XI, (P - 1) // 3))
+_PSI_CY = f2_inv(f2_pow(XI, (P - 1) // 2))
+
+
+def g1_phi(pt):
+    """(x, y) -> (beta x, y): acts on G1 as multiplication by lambda = x^2 - 1; lambda^2 + lambda + 1 = r."""
+    return None if pt is None else (pt[0] * ENDO_BETA % P, pt[1])
+
+
+def g2_psi(pt):
+    """Untwist-Frobenius-twist: acts on G2 as multiplication by x (= p mod r)."""
+    return None if pt is None else (f2_mul(f2_conj(pt[0]), _PSI_CX), f2_mul(f2_conj(pt[1]), _PSI_CY))
+
+
+def g1_in_subgroup_fast(pt):
+    """phi(P) == [x^2 - 1] P; since phi^2 + phi + 1 = 0 on the whole curve this forces [r] P = O."""
+    return pt is None or (g1_is_on_curve(pt) and g1_phi(pt) == _mul_raw(pt, X_ABS * X_ABS - 1, g1_add))
+
+
+def g2_in_subgroup_fast(pt):
+    """psi(P) == [x] P, i.e. -psi(P) == [|x|] P."""
+    if pt is None:
+        return True
+    return g2_is_on_curve(pt) and g2_neg(g2_psi(pt)) == _mul_raw(pt, X_ABS, g2_add)
+
+
+def gt_in_subgroup_fast(f):
+    """f in the cyclotomic subgroup (f^(p^4) f == f^(p^2)) and f^p == f^x."""
+    if f12_mul(f12_frob(f, 4), f) != f12_frob(f, 2):
+        return False
+    return f12_frob(f, 1) == f12_cyc_pow(f, X)

@@ -61,3 +61,60 @@ def groth16_instance(n, num_inputs=5, seed=0):
     }
     pts = [(E.g1_mul(E.G1_GEN, a), E.g2_mul(E.G2_GEN, b), E.g1_mul(E.G1_GEN, c)) for a, b, c in proofs]
     return vk, pts, inputs
+
+
+# ---- adversarial inputs for the verifiers: ON the curve but OUTSIDE the prime-order subgroup ---------------------
+def _fp_sqrt(a):
+    r = pow(a, (E.P + 1) // 4, E.P)
+    return r if r * r % E.P == a % E.P else None
+
+
+def _fp2_sqrt(a):
+    a0, a1 = a
+    if a1 == 0:
+        s = _fp_sqrt(a0)
+        if s is not None:
+            return (s, 0)
+        s = _fp_sqrt(-a0 % E.P)
+        return None if s is None else (0, s)
+    alpha = _fp_sqrt((a0 * a0 + a1 * a1) % E.P)
+    if alpha is None:
+        return None
+    inv2 = pow(2, -1, E.P)
+    for delta in ((a0 + alpha) * inv2 % E.P, (a0 - alpha) * inv2 % E.P):
+        x0 = _fp_sqrt(delta)
+        if x0:
+            r = (x0, a1 * pow(2 * x0, -1, E.P) % E.P)
+            if E.f2_sqr(r) == (a0 % E.P, a1 % E.P):
+                return r
+    return None
+
+
+def g1_point_off_subgroup(seed=0):
+    """A point of E(Fp): y^2 = x^3 + 4 that is not in G1 (the cofactor is ~2^126, so a random point almost never is)."""
+    i = 0
+    while True:
+        x = scalar("off-g1", i, seed) * scalar("off-g1'", i, seed) % E.P
+        y = _fp_sqrt((x**3 + 4) % E.P)
+        if y is not None and not E.g1_in_subgroup((x, y)):
+            return (x, y)
+        i += 1
+
+
+def g2_point_off_subgroup(seed=0):
+    i = 0
+    while True:
+        x = (scalar("off-g2", i, seed) * scalar("off-g2'", i, seed) % E.P, scalar("off-g2''", i, seed))
+        y = _fp2_sqrt(E.f2_add(E.f2_mul(E.f2_sqr(x), x), E.B2))
+        if y is not None and not E.g2_in_subgroup((x, y)):
+            return (x, y)
+        i += 1
+
+
+def gt_cyclotomic_off_subgroup(seed=0):
+    """An element of the cyclotomic subgroup of Fq12* (passes the cheap half of the GT test) whose order is not r."""
+    f = tuple((scalar("off-gt", 2 * k, seed) ** 2 % E.P, scalar("off-gt", 2 * k + 1, seed) ** 2 % E.P) for k in range(6))
+    c = E.f12_mul(E.f12_conj(f), E.f12_inv(f))
+    c = E.f12_mul(E.f12_frob(c, 2), c)
+    assert not E.gt_in_subgroup(c)
+    return c

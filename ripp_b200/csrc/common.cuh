@@ -104,4 +104,6 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
                           bool with_final_exp);
 int ripp_final_exp_l6(ripp_ctx* ctx, const void* in, uint32_t T, void* out, int nseg);
 int ripp_gt_multiexp_l6(ripp_ctx* ctx, const void* in, const void* sc, size_t n, void* out);
+int ripp_gt_check_l6(ripp_ctx* ctx, const void* in, size_t n, uint32_t* bad_dev, uint32_t flag);
 bool ripp_use_l6();
+int ripp_pairing6_init_device();  // per-device kernel attributes; called by ripp_ctx_create with the device current

@@ -20,9 +20,8 @@ typedef std::vector<uint8_t> Bytes;
 // RIPP_B200_TRACE=1: host wall-clock phase trace on stderr (development aid)
 #include <chrono>
 static bool trace_on() {
-  static int v = -1;
-  if (v < 0) v = getenv("RIPP_B200_TRACE") ? 1 : 0;
-  return v == 1;
+  static const bool v = getenv("RIPP_B200_TRACE") != nullptr;
+  return v;
 }
 static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -485,6 +484,9 @@ static int tipa_prove(ripp_ctx* ctx, int kind, const void* srs_g1, const void* s
   GipaSpec sp;
   if (!gipa_spec(kind, &sp)) return fail(RIPP_ERR_ARG, "bad GIPA kind");
   if (sp.v != VT_G2 || (sp.w != VT_G1 && sp.w != VT_NONE)) return fail(RIPP_ERR_ARG, "TIPA needs keys in (G2, G1)");
+  // the reference panics on `transcript.first().unwrap()` for a length-1 instance (tipa/mod.rs:199)
+  if (n < 2) return fail(RIPP_ERR_ARG, "TIPA needs at least two elements (the KZG challenge hashes the last round's challenge)");
+  if (!srs_g2 || (sp.w != VT_NONE && (!srs_g1 || !w))) return fail(RIPP_ERR_ARG, "null SRS or right key");
   GipaOut g;
   double t_g0 = now_ms();
   OK(gipa_prove(ctx, sp, a, b, v, w, n, &g));
@@ -571,6 +573,7 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
                                        size_t* proof_len) {
   if (!ctx || !srs_g1_dev || !srs_g2_dev || !a_dev || !b_dev || !c_dev) return fail(RIPP_ERR_ARG, "null argument");
   if (n == 0 || (n & (n - 1))) return fail(RIPP_ERR_NOT_POW2, "number of proofs must be a power of two");
+  if (n < 2) return fail(RIPP_ERR_ARG, "aggregation needs at least two proofs (tipa/mod.rs:199 unwraps the first challenge)");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   // layout of the aggregation workspace

@@ -8,12 +8,11 @@
 #include "x3.cuh"
 
 static bool use_endo() {
-  static int v = -1;
-  if (v < 0) {
+  static const bool v = [] {
     const char* e = getenv("RIPP_B200_FOLD");  // "plain" = no endomorphism (A/B runs)
-    v = (e && strcmp(e, "plain") == 0) ? 0 : 1;
-  }
-  return v == 1;
+    return !(e && strcmp(e, "plain") == 0);
+  }();
+  return v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -33,11 +32,10 @@ static MsmPlan msm_plan(size_t n, int bits = 255) {
   MsmPlan p;
   // ~32 points per bucket: long enough that the Poisson spread of bucket sizes does not idle most of a
   // warp (at 4 per bucket a warp runs at max/mean ~ 2.5x), short enough for the small MSMs of late rounds
-  static int shift = -1;  // RIPP_B200_MSM_SHIFT: log2 of the target points per bucket (tuning runs)
-  if (shift < 0) {
+  static const int shift = [] {  // RIPP_B200_MSM_SHIFT: log2 of the target points per bucket (tuning runs)
     const char* e = getenv("RIPP_B200_MSM_SHIFT");
-    shift = e ? atoi(e) : 5;
-  }
+    return e ? atoi(e) : 5;
+  }();
   p.c = lg - shift;
   if (p.c < 4) p.c = 4;
   if (p.c > 16) p.c = 16;
@@ -241,20 +239,18 @@ __global__ void k_msm_horner(const Jac<F>* __restrict__ sums, int nw, int c, Aff
 // RIPP_B200_FOLD = "w3" / "endo" / "plain" forces a fold kernel (A/B runs); default: three-warp teams (x3.cuh) while the
 // vector is short enough that the GPU is otherwise empty, one thread per element with the endomorphism above that.
 static int fold_mode() {
-  static int v = -1;
-  if (v < 0) {
+  static const int v = [] {
     const char* e = getenv("RIPP_B200_FOLD");
-    v = !e ? 0 : (strcmp(e, "w3") == 0 ? 1 : (strcmp(e, "endo") == 0 ? 2 : (strcmp(e, "plain") == 0 ? 3 : 0)));
-  }
+    return !e ? 0 : (strcmp(e, "w3") == 0 ? 1 : (strcmp(e, "endo") == 0 ? 2 : (strcmp(e, "plain") == 0 ? 3 : 0)));
+  }();
   return v;
 }
 // 3 warps per 32 elements: the team kernels pay off while the GPU is otherwise empty (RIPP_B200_W3_MAX overrides)
 static size_t w3_max_n() {
-  static long v = -1;
-  if (v < 0) {
+  static const long v = [] {
     const char* e = getenv("RIPP_B200_W3_MAX");
-    v = e ? atol(e) : 512;  // TIPP 2^12: 148.5 ms without teams, 143.1 at 512, 146.2 at 4096 (the early rounds already fill the GPU)
-  }
+    return e ? atol(e) : 512L;  // TIPP 2^12: 148.5 ms without teams, 143.1 at 512, 146.2 at 4096 (the early rounds already fill the GPU)
+  }();
   return (size_t)v;
 }
 

@@ -144,15 +144,43 @@ __global__ void __launch_bounds__(32) k_gt_pow6(const Fq12* __restrict__ in, con
   if (live) reinterpret_cast<Fq2*>(out + t)[tower_slot(c.k)] = ld2(freg(c, 0) + c.k * FQ2W);
 }
 
+// GT membership of untrusted Fq12 values (what ark-serialize's Valid::check establishes for PairingOutput when the
+// reference deserialises a proof): f is in the cyclotomic subgroup, f^(p^4) f == f^(p^2), and f^p == f^x
+// (Scott, ePrint 2021/1130; oracle: gt_in_subgroup_fast, checked there against f^r == 1).  One group per element;
+// a failing element ORs `flag` into *bad.
+constexpr int GC_NREG = 3;
+constexpr int GC_GROUP_WORDS = group_words(GC_NREG, 0);
+__global__ void __launch_bounds__(32) k_gt_check6(const Fq12* __restrict__ in, uint32_t n, uint32_t* __restrict__ bad,
+                                                  uint32_t flag) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int g = lane / 6;
+  Ctx c{lane % 6, smem + g * GC_GROUP_WORDS};
+  uint32_t t = blockIdx.x * 5 + g;
+  bool live = g < 5 && t < n;
+  const Fq2* src = reinterpret_cast<const Fq2*>(in + (live ? t : 0));
+  st2(freg(c, 0) + c.k * FQ2W, src[tower_slot(c.k)]);
+  __syncwarp();
+  frob(c, 1, 0, 2);
+  frob(c, 2, 1, 2);
+  mul(c, 2, 2, 0);
+  bool ne = !(ld2(freg(c, 2) + c.k * FQ2W) == ld2(freg(c, 1) + c.k * FQ2W));
+  __syncwarp();
+  exp_by_x(c, 2, 0);  // cyclotomic squarings: meaningful only when the first test passed, and only then consulted
+  frob(c, 1, 0, 1);
+  ne = ne || !(ld2(freg(c, 2) + c.k * FQ2W) == ld2(freg(c, 1) + c.k * FQ2W));
+  if (live && ne) atomicOr(bad, flag);
+}
+int ripp_gt_check_l6(ripp_ctx* ctx, const void* in, size_t n, uint32_t* bad_dev, uint32_t flag) {
+  if (n == 0) return RIPP_OK;
+  k_gt_check6<<<(unsigned)((n + 4) / 5), 32, 6 * GC_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, (uint32_t)n, bad_dev, flag);
+  LAUNCHED(ctx);
+  return RIPP_OK;
+}
+
 // out = prod_i in[i]^sc[i]  (device memory; in: n Fq12, sc: n Fr Montgomery)
 int ripp_gt_multiexp_l6(ripp_ctx* ctx, const void* in, const void* sc, size_t n, void* out) {
   CU(cudaSetDevice(ctx->device));
-  static bool attr_done_dev[64] = {false};  // function attributes are per device
-  bool& attr_done = attr_done_dev[ctx->device & 63];
-  if (!attr_done) {
-    CU(cudaFuncSetAttribute(k_reduce6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * R6_GROUP_WORDS * 4));
-    attr_done = true;
-  }
   if (n == 0) {
     Fq12 one = Fq12::one();
     CU(cudaMemcpyAsync(out, &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
@@ -186,12 +214,6 @@ int ripp_gt_multiexp_l6(ripp_ctx* ctx, const void* in, const void* sc, size_t n,
 template <int KP>
 static int launch_miller6(ripp_ctx* ctx, Miller6Batch& b, size_t n, Fq12* dst, size_t* nwarps_out) {
   constexpr int SM = M6_WARPS * 6 * group_words(M6_NREG, KP) * 4;
-  static bool attr_done_dev[64] = {false};  // function attributes are per device
-  bool& attr_done = attr_done_dev[ctx->device & 63];
-  if (!attr_done) {
-    CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
-    attr_done = true;
-  }
   b.wps = (uint32_t)((n + 5 * KP - 1) / (5 * KP));
   size_t nwarps = (size_t)b.wps * b.nseg;
   unsigned blocks = (unsigned)((nwarps + M6_WARPS - 1) / M6_WARPS);
@@ -205,13 +227,6 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
                           bool with_final_exp) {
   if (nseg <= 0 || nseg > RIPP_MAX_BATCH) return fail(RIPP_ERR_ARG, "bad segment count");
   CU(cudaSetDevice(ctx->device));
-  static bool attr_done_dev[64] = {false};  // function attributes are per device
-  bool& attr_done = attr_done_dev[ctx->device & 63];
-  if (!attr_done) {
-    CU(cudaFuncSetAttribute(k_reduce6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * R6_GROUP_WORDS * 4));
-    CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
-    attr_done = true;
-  }
   Fq12 one = Fq12::one();
   if (n == 0) {
     for (int s = 0; s < nseg; s++)
@@ -273,14 +288,19 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
 // out[s] = final_exponentiation(prod_j in[s*T + j])
 int ripp_final_exp_l6(ripp_ctx* ctx, const void* in, uint32_t T, void* out, int nseg) {
   CU(cudaSetDevice(ctx->device));
-  static bool attr_done_dev[64] = {false};  // function attributes are per device
-  bool& attr_done = attr_done_dev[ctx->device & 63];
-  if (!attr_done) {
-    CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
-    attr_done = true;
-  }
   TimeScope ts_(ctx, RIPP_T_FINAL_EXP);
   k_final_exp6<<<(nseg + 9) / 10, 64, 2 * 6 * FE_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, T, (Fq12*)out, nseg);
   LAUNCHED(ctx);
+  return RIPP_OK;
+}
+
+// Opt-in shared-memory sizes of the six-lane kernels: function attributes are per device, set once per context
+// creation (ripp_ctx_create) -- never from the launch paths, which run concurrently on several host threads.
+int ripp_pairing6_init_device() {
+  CU(cudaFuncSetAttribute(k_reduce6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * R6_GROUP_WORDS * 4));
+  CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 1) * 4));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 2) * 4));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 4) * 4));
   return RIPP_OK;
 }

@@ -16,6 +16,7 @@ extern "C" int ripp_ctx_create(int device, ripp_ctx** out) {
     return fail(RIPP_ERR_NO_DEVICE, std::string("no CUDA device (ripp_b200 has no CPU fallback): ") + cudaGetErrorString(e));
   if (device < 0 || device >= count) return fail(RIPP_ERR_ARG, "bad device ordinal");
   CU(cudaSetDevice(device));
+  OK(ripp_pairing6_init_device());
   ripp_ctx* c = new ripp_ctx();
   memset(c, 0, sizeof(*c));
   c->device = device;
@@ -207,7 +208,9 @@ template <class F, bool GEN>
 __global__ void __launch_bounds__(64, 4) k_scale(const Aff<F>* __restrict__ pts, const Fr* __restrict__ sc, size_t n,
                                               Aff<F>* __restrict__ out, Aff<F> gen) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  // every lane stays alive for the full-mask shuffles below: lanes past n redo element n - 1 and do not store
+  const bool live = i < n;
+  if (!live) i = n - 1;
   Fr s = sc[i].from_mont();
   Aff<F> p = GEN ? gen : pts[i];
   EndoBits eb;  // GLV / GLS decomposition of this element's scalar (endo.cuh)
@@ -215,10 +218,13 @@ __global__ void __launch_bounds__(64, 4) k_scale(const Aff<F>* __restrict__ pts,
   // warp-uniform trip counts (every lane walks the longest digit of the warp)
   int nb = eb.nbits, mm = eb.m;
   for (int o = 16; o >= 1; o >>= 1) {
-    nb = max(nb, __shfl_xor_sync(__activemask(), nb, o));
-    mm = max(mm, __shfl_xor_sync(__activemask(), mm, o));
+    nb = max(nb, __shfl_xor_sync(0xffffffffu, nb, o));
+    mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, o));
   }
-  out[i] = endo_mul_simt<F>(p, eb, mm, nb).to_affine();
+  nb = min(nb, 160);  // bounds of EndoBits::pos / neg and base[4], whatever the decomposition returned
+  mm = min(mm, 4);
+  Aff<F> r = endo_mul_simt<F>(p, eb, mm, nb).to_affine();
+  if (live) out[i] = r;
 }
 
 template <class F, class XF>
@@ -571,12 +577,11 @@ __global__ void k_final_exp_seg(const Fq12* __restrict__ in, uint32_t T, Fq12* _
 }
 
 bool ripp_use_l6() {
-  static int v = -1;
-  if (v < 0) {
+  static const bool v = [] {  // thread-safe one-time initialisation
     const char* e = getenv("RIPP_B200_PAIRING");  // "thread" selects the one-thread-per-pair kernels (A/B runs)
-    v = (e && strcmp(e, "thread") == 0) ? 0 : 1;
-  }
-  return v == 1;
+    return !(e && strcmp(e, "thread") == 0);
+  }();
+  return v;
 }
 
 int ripp_pairing_batch_internal(ripp_ctx* ctx, int nseg, const void* const* g1, const void* const* g2, size_t n, void* out) {

@@ -16,9 +16,11 @@
 // (GT: k_gt_pow6 + product tree; G1/G2: the MSM kernels; Fr: host), the final commitment keys are one MSM
 // over the key vector (the reference's naive sum, gipa.rs:383 "TODO use MSM"), and every remaining check is
 // an inner product of length-1 vectors evaluated by the same kernels the prover uses.
-// Inputs are arkworks serialize_uncompressed bytes, as the provers emit them.  Decoding checks canonical
-// field encodings and curve membership; subgroup membership is what ark-serialize's validation on the Rust
-// side of the shim has already established for typed values.
+// Inputs are arkworks serialize_uncompressed bytes, as the provers emit them.  Decoding validates exactly what
+// ark-serialize's `deserialize_uncompressed` (Valid::check) validates: canonical field encodings, curve membership
+// (host, while parsing) and membership of the prime-order subgroups of G1 / G2 / GT (one batch of GPU checks over
+// every decoded element, `validate_subgroups`, before any of them reaches the endomorphism-based MSM / fold
+// kernels, whose GLV / GLS maps are scalar multiplications only inside the r-torsion).
 #pragma once
 
 // ------------------------------------------------------------------------------------------------
@@ -28,6 +30,10 @@ struct Reader {
   const uint8_t* p;
   size_t n, off;
   bool ok;
+  // every group element decoded from these bytes, for the subgroup checks
+  std::vector<G1Aff> g1s;
+  std::vector<G2Aff> g2s;
+  std::vector<Fq12> gts;
   Reader(const void* data, size_t len) : p((const uint8_t*)data), n(len), off(0), ok(data != nullptr || len == 0) {}
   const uint8_t* take(size_t k) {
     if (!ok || n - off < k) {
@@ -94,6 +100,7 @@ static bool get_gt(Reader& r, Fq12* f) {
   Fq* c = reinterpret_cast<Fq*>(f);
   for (int i = 0; i < 12; i++)
     if (!get_fq_le(r, &c[i])) return false;
+  r.gts.push_back(*f);
   return true;
 }
 static Fq fq_small(int k) {
@@ -113,6 +120,7 @@ static bool get_g1(Reader& r, G1Aff* p) {
   }
   if (y.sqr() != x.sqr() * x + fq_small(4)) return r.ok = false;  // y^2 = x^3 + 4
   *p = G1Aff{x, y};
+  r.g1s.push_back(*p);
   return true;
 }
 static bool get_g2(Reader& r, G2Aff* p) {
@@ -130,6 +138,7 @@ static bool get_g2(Reader& r, G2Aff* p) {
   Fq four = fq_small(4);
   if (y.sqr() != x.sqr() * x + Fq2{four, four}) return r.ok = false;  // y^2 = x^3 + 4 (1 + u)
   *p = G2Aff{x, y};
+  r.g2s.push_back(*p);
   return true;
 }
 static bool get_val(Reader& r, int t, Val* v) {
@@ -156,6 +165,80 @@ static Val val_fr(const Fr& f) {
   memset(v.raw, 0, sizeof(v.raw));
   memcpy(v.raw, f.v, 32);
   return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// subgroup membership of everything the readers decoded (ark-ec: is_in_correct_subgroup_assuming_on_curve;
+// PairingOutput::check).  G1: phi(P) == [x^2 - 1] P, which forces [r] P = O because phi^2 + phi + 1 = 0 on the
+// whole curve and lambda^2 + lambda + 1 = r; G2: -psi(P) == [|x|] P; GT: k_gt_check6 (pairing6.cu).  The scalar
+// multiplications here are plain double-and-add: no endomorphism is trusted before the test has passed.
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(64) k_subgroup_check(const Aff<F>* __restrict__ pts, uint32_t n, uint32_t* __restrict__ bad,
+                                                       uint32_t flag) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Aff<F> p = pts[i];
+  if (p.is_inf()) return;
+  uint32_t bits[4];
+  int nbits;
+  if (sizeof(F) == sizeof(Fq)) {
+    for (int j = 0; j < 4; j++) bits[j] = k::ENDO_LAMBDA(j);
+    nbits = 128;
+  } else {
+    bits[0] = (uint32_t)k::X_ABS;
+    bits[1] = (uint32_t)(k::X_ABS >> 32);
+    bits[2] = bits[3] = 0;
+    nbits = 64;
+  }
+  Jac<F> r = scalar_mul<F>(p, bits, nbits);
+  Aff<F> q = endo_map(p);
+  F z2 = r.z.sqr();
+  bool ok = !r.is_inf() && r.x == q.x * z2 && r.y == q.y * z2 * r.z;
+  if (!ok) atomicOr(bad, flag);
+}
+
+// *bad_mask: bit 0 = a G1 element, bit 1 = a G2 element, bit 2 = a GT element outside its prime-order subgroup
+static int validate_subgroups(ripp_ctx* ctx, std::initializer_list<Reader*> readers, uint32_t* bad_mask) {
+  std::vector<G1Aff> g1;
+  std::vector<G2Aff> g2;
+  std::vector<Fq12> gt;
+  for (Reader* r : readers) {
+    g1.insert(g1.end(), r->g1s.begin(), r->g1s.end());
+    g2.insert(g2.end(), r->g2s.begin(), r->g2s.end());
+    gt.insert(gt.end(), r->gts.begin(), r->gts.end());
+  }
+  *bad_mask = 0;
+  if (g1.empty() && g2.empty() && gt.empty()) return RIPP_OK;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o_g2 = up(g1.size() * 96), o_gt = o_g2 + up(g2.size() * 192), o_flag = o_gt + up(gt.size() * 576);
+  void* d;
+  OK(scratch(ctx, 21, o_flag + 256, &d));
+  char* D = (char*)d;
+  cudaStream_t st = ctx->stream;
+  uint32_t* flag = (uint32_t*)(D + o_flag);
+  CU(cudaMemsetAsync(flag, 0, 4, st));
+  if (!g1.empty()) {
+    CU(cudaMemcpyAsync(D, g1.data(), g1.size() * 96, cudaMemcpyHostToDevice, st));
+    k_subgroup_check<Fq><<<(unsigned)((g1.size() + 63) / 64), 64, 0, st>>>((const G1Aff*)D, (uint32_t)g1.size(), flag, 1u);
+    LAUNCHED(ctx);
+  }
+  if (!g2.empty()) {
+    CU(cudaMemcpyAsync(D + o_g2, g2.data(), g2.size() * 192, cudaMemcpyHostToDevice, st));
+    k_subgroup_check<Fq2><<<(unsigned)((g2.size() + 63) / 64), 64, 0, st>>>((const G2Aff*)(D + o_g2), (uint32_t)g2.size(), flag, 2u);
+    LAUNCHED(ctx);
+  }
+  if (!gt.empty()) {
+    CU(cudaMemcpyAsync(D + o_gt, gt.data(), gt.size() * 576, cudaMemcpyHostToDevice, st));
+    OK(ripp_gt_check_l6(ctx, D + o_gt, gt.size(), flag, 4u));
+  }
+  CU(cudaMemcpyAsync(bad_mask, flag, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return RIPP_OK;
+}
+static int subgroup_error(uint32_t mask) {
+  return fail(RIPP_ERR_ARG, std::string("proof element outside the prime-order subgroup (ark-serialize would reject: InvalidData):") +
+                                (mask & 1 ? " G1" : "") + (mask & 2 ? " G2" : "") + (mask & 4 ? " GT" : ""));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -365,6 +448,9 @@ extern "C" int ripp_gipa_verify_dev(ripp_ctx* ctx, int kind, const void* v_dev, 
   GipaProofP pf;
   if (!parse_coms(rc, sp, ssm, cm) || !rc.done()) return fail(RIPP_ERR_ARG, "malformed commitment bytes");
   if (!parse_gipa_proof(rp, sp, &pf) || !rp.done()) return fail(RIPP_ERR_ARG, "malformed GIPA proof bytes");
+  uint32_t bad = 0;
+  OK(validate_subgroups(ctx, {&rc, &rp}, &bad));
+  if (bad) return subgroup_error(bad);
   if (((size_t)1 << pf.steps.size()) != n) return RIPP_OK;  // transcript length does not match the keys: reject
   std::vector<Fr> transcript, c_round, cinv_round;
   recursive_challenges(pf, &transcript, &c_round, &cinv_round);
@@ -534,6 +620,9 @@ extern "C" int ripp_tipa_verify(ripp_ctx* ctx, int kind, const void* vsrs, const
   TipaProofP tp;
   if (!parse_coms(rc, sp, ssm, cm) || !rc.done()) return fail(RIPP_ERR_ARG, "malformed commitment bytes");
   if (!parse_tipa_proof(rp, sp, &tp) || !rp.done()) return fail(RIPP_ERR_ARG, "malformed TIPA proof bytes");
+  uint32_t bad = 0;
+  OK(validate_subgroups(ctx, {&rc, &rp}, &bad));
+  if (bad) return subgroup_error(bad);
   bool ok = false;
   OK(tipa_verify_parsed(ctx, sp, vs, cm, sh, tp.gipa, tp.ck_a, ssm ? nullptr : &tp.ck_b, tp.pi_a, ssm ? nullptr : &tp.pi_b, &ok));
   *accept = ok ? 1 : 0;
@@ -579,6 +668,9 @@ extern "C" int ripp_tipp_verify_aggregate(ripp_ctx* ctx, const void* vsrs, const
       !get_val(rp, VT_GT, &ip_ab) || !get_val(rp, VT_G1, &agg_c) || !parse_tipa_proof(rp, sp_ab, &pab) ||
       !parse_tipa_proof(rp, sp_c, &pc) || !rp.done())
     return fail(RIPP_ERR_ARG, "malformed AggregateProof bytes");
+  uint32_t bad = 0;
+  OK(validate_subgroups(ctx, {&rp}, &bad));
+  if (bad) return subgroup_error(bad);
   // :174-186 r
   Bytes parts;
   put_val(parts, com_a);
@@ -691,6 +783,9 @@ extern "C" int ripp_sipp_verify(ripp_ctx* ctx, const void* a_aff, const void* b_
     el.push_back(zr);
     sc.push_back(xi);
   }
+  uint32_t bad = 0;
+  OK(validate_subgroups(ctx, {&rp}, &bad));
+  if (bad) return subgroup_error(bad);
   // lib.rs:152-160 z' = value + sum (z_l x + z_r x^-1)
   Val zp;
   OK(combine(ctx, VT_GT, el, sc, &zp));

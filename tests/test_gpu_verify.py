@@ -197,3 +197,45 @@ def test_full_size_round_trips(ctx):
     r2 = r.copy()
     r2[5] = r[6]
     assert not ctx.sipp_verify(a, b, r2, z, sp)
+
+
+def test_verifiers_reject_on_curve_points_outside_the_subgroups(ctx):
+    """ark-serialize's deserialize_uncompressed runs Valid::check (curve AND prime-order subgroup, order r for GT) on
+    every proof element; the C-ABI verifiers take raw bytes, so they must do the same before the points reach the
+    endomorphism-based MSM / fold kernels.  Each substitution below is a well-formed encoding of an element that is
+    on the curve (in the cyclotomic subgroup for GT) but outside the prime-order subgroup."""
+    from oracle.encoding import ser_g1, ser_g2, ser_gt
+
+    n = 4
+    srs = _srs(n)
+    vs = srs.get_verifier_key()
+    vk, proofs, inputs = OS.groth16_instance(n)
+    agg = aggregate_proofs((srs.g_alpha_powers, srs.h_beta_powers), proofs, ctx)
+    assert verify_aggregate_proof(vs, vk, inputs, agg, ctx)
+    off1, off2, offt = OS.g1_point_off_subgroup(), OS.g2_point_off_subgroup(), OS.gt_cyclotomic_off_subgroup()
+    assert E.g1_is_on_curve(off1) and E.g2_is_on_curve(off2)
+
+    def splice(b, at, new):
+        return b[:at] + new + b[at + len(new):]
+
+    # AggregateProof = com_a | com_b | com_c | ip_ab (4 GT) | agg_c (G1) | TIPA proof ab | TIPA-SSM proof c;
+    # the SSM proof ends with final_ck (G2) | final_ck_proof (G2)
+    cases = {
+        "G1": splice(agg, 4 * 576, ser_g1(off1)),
+        "G2": splice(agg, len(agg) - 192, ser_g2(off2)),
+        "GT": splice(agg, 576, ser_gt(offt)),
+    }
+    for name, bad in cases.items():
+        with pytest.raises(_lib.RippError) as e:
+            verify_aggregate_proof(vs, vk, inputs, bad, ctx)
+        assert e.value.status == _lib.RIPP_ERR_ARG and "subgroup" in str(e.value) and name in str(e.value), name
+
+    # SIPP: the proof's GT elements
+    from ripp_b200.sipp import SIPP, product_of_pairings_with_coeffs
+
+    a, b, r = OS.g1_points("sipp-a", n), OS.g2_points("sipp-b", n), OS.scalars("sipp-r", n)
+    z = product_of_pairings_with_coeffs(a, b, r, ctx)
+    sp = SIPP.prove(a, b, r, z, ctx)
+    with pytest.raises(_lib.RippError) as e:
+        SIPP.verify(a, b, r, z, splice(sp, 576, ser_gt(offt)), ctx)
+    assert "subgroup" in str(e.value)

@@ -150,3 +150,21 @@ def test_sipp_round_trip():
     proof = O.sipp_prove(a, b, r, z)
     assert O.sipp_verify(a, b, r, z, proof)
     assert not O.sipp_verify(a, b, r, E.gt_mul(z, z), proof)
+
+
+def test_subgroup_membership_forms_agree():
+    """The endomorphism forms of the membership tests (what the CUDA verifiers evaluate) against the definitions
+    [r]P = O / f^r = 1, on members and on points of the curves outside the prime-order subgroups."""
+    g, h = E.g1_mul(E.G1_GEN, 31337), E.g2_mul(E.G2_GEN, 271828)
+    assert E.g1_in_subgroup(g) and E.g1_in_subgroup_fast(g) and E.g1_in_subgroup_fast(None)
+    assert E.g2_in_subgroup(h) and E.g2_in_subgroup_fast(h) and E.g2_in_subgroup_fast(None)
+    e = E.pairing(g, h)
+    assert E.gt_in_subgroup(e) and E.gt_in_subgroup_fast(e) and E.gt_in_subgroup_fast(E.F12_ONE)
+    for seed in range(3):
+        p, q, c = OS.g1_point_off_subgroup(seed), OS.g2_point_off_subgroup(seed), OS.gt_cyclotomic_off_subgroup(seed)
+        assert E.g1_is_on_curve(p) and not E.g1_in_subgroup(p) and not E.g1_in_subgroup_fast(p)
+        assert E.g2_is_on_curve(q) and not E.g2_in_subgroup(q) and not E.g2_in_subgroup_fast(q)
+        assert not E.gt_in_subgroup(c) and not E.gt_in_subgroup_fast(c)
+    # a sum of a member and a non-member is a non-member
+    assert not E.g1_in_subgroup_fast(E.g1_add(g, OS.g1_point_off_subgroup()))
+    assert (E.X_ABS**2 - 1) ** 2 + (E.X_ABS**2 - 1) + 1 == E.R
