@@ -32,19 +32,36 @@ constexpr int PB_VALID = PB_Q + 2 * FQ2W; // 1 = finite pair, 0 = contributes th
 constexpr int PAIR_WORDS = PB_VALID + 8;
 RIPP_HD constexpr int group_words(int nreg, int npairs) { return OFF_F + nreg * F12W + npairs * PAIR_WORDS; }
 
-struct Ctx {
-  int k;          // lane within the group, 0..5
+// W = 1: the coefficient's lane does the whole Fq2 arithmetic (throughput shape: five groups per warp).
+// W = 3: THREE lanes per coefficient (18 lanes per Fq12, one group per warp; lanes 18..31 mirror lanes 0..13 and
+// recompute the same values), one Karatsuba role each -- role 0: a0 b0, role 1: a1 b1, role 2: (a0 + a1)(b0 + b1) --
+// so every Fq2 product level costs ONE Fq product of latency instead of three.  A warp instruction holds the
+// multiplier pipe for the same time however many lanes are active, so for the lone warps of the late GIPA rounds,
+// the final exponentiation and the verifier's GT powers this is a ~2.5x shorter chain at no extra pipe time.
+// The three lanes of a coefficient hold identical Fq2 state; partial products are exchanged through `bus`.
+constexpr int BUS_WORDS = 6 * 3 * 12;  // one Fq per (coefficient, role); two buffers are used alternately
+template <int W_>
+struct CtxT {
+  static constexpr int W = W_;
+  int k;          // coefficient (lane within the group for W = 1), 0..5
   uint32_t* sm;   // group scratch
 #if !defined(__CUDA_ARCH__)
   void* bar;      // host: barrier object
 #endif
+  int role;       // W = 3: Karatsuba role of this lane, 0..2
+  uint32_t* bus;  // W = 3: 2 * BUS_WORDS words of the group's scratch
+  mutable int par;  // W = 3: which bus buffer the next exchange uses
 };
+using Ctx = CtxT<1>;
+using Ctx3 = CtxT<3>;
 
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ void sync(const Ctx&) { __syncwarp(); }
+template <class C>
+__device__ __forceinline__ void sync(const C&) { __syncwarp(); }
 #else
 void host_barrier(void* bar);
-inline void sync(const Ctx& c) { host_barrier(c.bar); }
+template <class C>
+inline void sync(const C& c) { host_barrier(c.bar); }
 #endif
 
 // ---- force-inlined field helpers (everything stays in registers inside an L6 kernel) -------------
@@ -60,62 +77,159 @@ RIPP_HD Fq2 f2dbl(const Fq2& a) { return {a.c0 + a.c0, a.c1 + a.c1}; }
 RIPP_HD Fq2 f2half(const Fq2& a) { return {a.c0.half(), a.c1.half()}; }
 RIPP_HD Fq2 f2xi(const Fq2& a) { return {a.c0 - a.c1, a.c0 + a.c1}; }
 RIPP_HD Fq2 f2conj(const Fq2& a) { return {a.c0, -a.c1}; }
+RIPP_HD Fq ld1(const uint32_t* p) {
+  Fq r;
+#if defined(__CUDA_ARCH__)
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    uint4 v = q[i];
+    r.v[4 * i] = v.x;
+    r.v[4 * i + 1] = v.y;
+    r.v[4 * i + 2] = v.z;
+    r.v[4 * i + 3] = v.w;
+  }
+#else
+  for (int i = 0; i < 12; i++) r.v[i] = p[i];
+#endif
+  return r;
+}
+RIPP_HD void st1(uint32_t* p, const Fq& a) {
+#if defined(__CUDA_ARCH__)
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 3; i++) q[i] = make_uint4(a.v[4 * i], a.v[4 * i + 1], a.v[4 * i + 2], a.v[4 * i + 3]);
+#else
+  for (int i = 0; i < 12; i++) p[i] = a.v[i];
+#endif
+}
+RIPP_HD Fq sel3(int r, const Fq& a, const Fq& b, const Fq& c) {
+  Fq o;
+#pragma unroll
+  for (int i = 0; i < 12; i++) o.v[i] = r == 0 ? a.v[i] : (r == 1 ? b.v[i] : c.v[i]);
+  return o;
+}
+// W = 3: every lane of a coefficient's triple contributes `mine`; all three get (t0, t1, t2) = the values of roles 0, 1, 2.
+// Two buffers used alternately: a lane may start writing exchange n + 2 only after the barrier of exchange n + 1,
+// which every lane reaches after it has read exchange n -- so one barrier per exchange is enough.
+template <class C>
+RIPP_HD void gather3(const C& c, const Fq& mine, Fq& t0, Fq& t1, Fq& t2) {
+  uint32_t* b = c.bus + c.par * BUS_WORDS + c.k * 36;
+  c.par ^= 1;
+  st1(b + c.role * 12, mine);
+  sync(c);
+  t0 = ld1(b);
+  t1 = ld1(b + 12);
+  t2 = ld1(b + 24);
+}
 // One out-of-line copy of the Fq2 product on the device (operands by value, in registers) instead of an inlined
 // copy per use: the Miller loop body drops from 24 k to 18 k instructions (2^16 pairs: 21.4 -> 21.1 ms, small
 // batches 3.0 -> 2.7 ms: fewer instruction-cache misses for the lone warps of the late GIPA rounds).
+RIPP_HD Fq2 f2mul_body(const Fq2& a, const Fq2& b) {
+  Fq t0 = fqmul(a.c0, b.c0);
+  Fq t1 = fqmul(a.c1, b.c1);
+  Fq t2 = fqmul(a.c0 + a.c1, b.c0 + b.c1);
+  return {t0 - t1, t2 - t0 - t1};
+}
+// the role's Karatsuba product of a b (W = 3); the caller exchanges the three and combines
+RIPP_HD Fq f2mul_part_body(const Fq2& a, const Fq2& b, int role) {
+  return fqmul(sel3(role, a.c0, a.c1, a.c0 + a.c1), sel3(role, b.c0, b.c1, b.c0 + b.c1));
+}
 #if defined(__CUDA_ARCH__) && !defined(RIPP_L6_INLINE_F2MUL)
-static __device__ __noinline__ Fq2 f2mul_fn(Fq2 a, Fq2 b) {
-  Fq t0 = fqmul(a.c0, b.c0);
-  Fq t1 = fqmul(a.c1, b.c1);
-  Fq t2 = fqmul(a.c0 + a.c1, b.c0 + b.c1);
-  return {t0 - t1, t2 - t0 - t1};
-}
-RIPP_HD Fq2 f2mul(const Fq2& a, const Fq2& b) { return f2mul_fn(a, b); }
+static __device__ __noinline__ Fq2 f2mul_fn(Fq2 a, Fq2 b) { return f2mul_body(a, b); }
+static __device__ __noinline__ Fq f2mul_part_fn(Fq2 a, Fq2 b, int role) { return f2mul_part_body(a, b, role); }
 #else
-RIPP_HD Fq2 f2mul(const Fq2& a, const Fq2& b) {
-  Fq t0 = fqmul(a.c0, b.c0);
-  Fq t1 = fqmul(a.c1, b.c1);
-  Fq t2 = fqmul(a.c0 + a.c1, b.c0 + b.c1);
-  return {t0 - t1, t2 - t0 - t1};
-}
+RIPP_HD Fq2 f2mul_fn(const Fq2& a, const Fq2& b) { return f2mul_body(a, b); }
+RIPP_HD Fq f2mul_part_fn(const Fq2& a, const Fq2& b, int role) { return f2mul_part_body(a, b, role); }
 #endif
+template <class C>
+RIPP_HD Fq2 f2mul(const C& c, const Fq2& a, const Fq2& b) {
+  if constexpr (C::W == 1) {
+    return f2mul_fn(a, b);
+  } else {
+    Fq t0, t1, t2;
+    gather3(c, f2mul_part_fn(a, b, c.role), t0, t1, t2);
+    return {t0 - t1, t2 - t0 - t1};
+  }
+}
 // ---- lazy Fq2 multiply-accumulate: sum_i a_i b_i with ONE Montgomery reduction per output limb vector ----
 // Karatsuba in the wide (768-bit) domain: S0 += a0 b0, S1 += a1 b1, K += (a0 + a1)(b0 + b1); then
-// c0 = REDC(S0) - REDC(S1), c1 = REDC(K - S0 - S1).  Operand components must be < p; up to six products.
+// c0 = REDC(S0 + p R - S1), c1 = REDC(K - S0 - S1).  Operand components must be < p; up to six products.
+// W = 1: the lane keeps all three sums (Acc3).  W = 3: each role keeps its own (Acc1), reduces it, and the three
+// reduced values are exchanged (REDC is linear modulo p, so REDC(K) - REDC(S0) - REDC(S1) is the same c1).
 struct Acc3 {
   uint32_t s0[24], s1[24], k[24];
 };
+struct Acc1 {
+  uint32_t s[24];
+};
+template <class C> struct AccOf { typedef Acc3 type; };
+template <> struct AccOf<CtxT<3>> { typedef Acc1 type; };
 RIPP_HD void acc_zero(Acc3& A) {
 #pragma unroll
   for (int i = 0; i < 24; i++) A.s0[i] = A.s1[i] = A.k[i] = 0;
 }
-RIPP_HD void f2_mac(Acc3& A, const Fq2& a, const Fq2& b) {
+RIPP_HD void acc_zero(Acc1& A) {
+#pragma unroll
+  for (int i = 0; i < 24; i++) A.s[i] = 0;
+}
+// c0 + c1 over the integers (< 2p < 2^382): operand of the Karatsuba cross product
+RIPP_HD void add_unreduced(uint32_t* s, const Fq& a, const Fq& b) {
   using namespace limb;
+  add_cc(s[0], a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) addc_cc(s[i], a.v[i], b.v[i]);
+  addc(s[11], a.v[11], b.v[11]);
+}
+template <class C>
+RIPP_HD void f2_mac(const C&, Acc3& A, const Fq2& a, const Fq2& b) {
   uint32_t t[24];
   detail::wide_mul<FqParams>(t, a.c0.v, b.c0.v);
   detail::wide_add<24>(A.s0, t);
   detail::wide_mul<FqParams>(t, a.c1.v, b.c1.v);
   detail::wide_add<24>(A.s1, t);
-  uint32_t sa[12], sb[12];  // unreduced sums (< 2p < 2^382)
-  add_cc(sa[0], a.c0.v[0], a.c1.v[0]);
-#pragma unroll
-  for (int i = 1; i < 11; i++) addc_cc(sa[i], a.c0.v[i], a.c1.v[i]);
-  addc(sa[11], a.c0.v[11], a.c1.v[11]);
-  add_cc(sb[0], b.c0.v[0], b.c1.v[0]);
-#pragma unroll
-  for (int i = 1; i < 11; i++) addc_cc(sb[i], b.c0.v[i], b.c1.v[i]);
-  addc(sb[11], b.c0.v[11], b.c1.v[11]);
+  uint32_t sa[12], sb[12];
+  add_unreduced(sa, a.c0, a.c1);
+  add_unreduced(sb, b.c0, b.c1);
   detail::wide_mul<FqParams>(t, sa, sb);
   detail::wide_add<24>(A.k, t);
 }
-RIPP_HD Fq2 f2_finish(Acc3& A) {
+template <class C>
+RIPP_HD void f2_mac(const C& c, Acc1& A, const Fq2& a, const Fq2& b) {
+  uint32_t sa[12], sb[12], u[12], v[12], t[24];
+  add_unreduced(sa, a.c0, a.c1);
+  add_unreduced(sb, b.c0, b.c1);
+  const int r = c.role;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    u[i] = r == 0 ? a.c0.v[i] : (r == 1 ? a.c1.v[i] : sa[i]);
+    v[i] = r == 0 ? b.c0.v[i] : (r == 1 ? b.c1.v[i] : sb[i]);
+  }
+  detail::wide_mul<FqParams>(t, u, v);
+  detail::wide_add<24>(A.s, t);
+}
+template <class C>
+RIPP_HD Fq2 f2_finish(const C&, Acc3& A) {
+  using namespace limb;
   detail::wide_sub<24>(A.k, A.s0);
   detail::wide_sub<24>(A.k, A.s1);
-  Fq r0, r1, c1;
-  detail::redc_wide<FqParams>(r0.v, A.s0, 1);  // < 6 p^2 / R + p < 1.7 p
-  detail::redc_wide<FqParams>(r1.v, A.s1, 1);
+  // S0 + p 2^384 - S1 >= 0 (S1 < 6 p^2 < p 2^384): one reduction gives c0 directly
+  add_cc(A.s0[12], A.s0[12], FqParams::p(0));
+#pragma unroll
+  for (int i = 1; i < 11; i++) addc_cc(A.s0[12 + i], A.s0[12 + i], FqParams::p(i));
+  addc(A.s0[23], A.s0[23], FqParams::p(11));
+  detail::wide_sub<24>(A.s0, A.s1);
+  Fq c0, c1;
+  detail::redc_wide<FqParams>(c0.v, A.s0, 2);  // < (6 p^2 + p R) / R + p < 2.7 p
   detail::redc_wide<FqParams>(c1.v, A.k, 2);   // < 12 p^2 / R + p < 2.3 p
-  return {r0 - r1, c1};
+  return {c0, c1};
+}
+template <class C>
+RIPP_HD Fq2 f2_finish(const C& c, Acc1& A) {
+  Fq r, t0, t1, t2;
+  detail::redc_wide<FqParams>(r.v, A.s, 3);  // role 2: < 24 p^2 / R + p < 3.5 p
+  gather3(c, r, t0, t1, t2);
+  return {t0 - t1, t2 - t0 - t1};
 }
 
 RIPP_HD Fq2 f2sel(bool c, const Fq2& a, const Fq2& b) {  // c ? a : b, branch-free
@@ -164,94 +278,14 @@ RIPP_HD void st2(uint32_t* p, const Fq2& a) {
 #endif
 }
 
-RIPP_HD uint32_t* freg(const Ctx& c, int r) { return c.sm + OFF_F + r * F12W; }
+template <class C>
+RIPP_HD uint32_t* freg(const C& c, int r) { return c.sm + OFF_F + r * F12W; }
 
-// ---- one out-of-line copy of the multiply-accumulate engine (opt-in: -DRIPP_L6_SHARED_CODE) ----------
-// Measured on B200: Miller 2^16 22.3 ms (vs 21.1 inlined), small batches 2.7 ms (same), TIPP 2^12 146.9 ms (vs 147.5);
-// builds 5x faster.  Kept opt-in because the throughput kernel is what the roofline is quoted on.
-// D[k] = sum_s x_s y_s for the lane's output coefficient k, where the (x_s, y_s) are chosen by `op`:
-//   0  Fq12 product      A * B              six terms   (A_i, B_(k-i))
-//   1  Fq12 squaring     A^2                <= four     (A_i, A_j), i <= j, cross terms doubled
-//   2  sparse product    A * (d0 + d1 w^2 + d4 w^3), line at OFF_LINE: three terms
-// with xi folded into the operand when the index wraps (w^6 = xi).  `op` is uniform over the warp, so the
-// branches below never diverge and the __syncwarp at the end is reached by all lanes together.  One copy of
-// f2_mac / f2_finish serves every Fq12 operation of a kernel: the Miller loop body shrinks from ~11 k to
-// ~4 k instructions and the final exponentiation from 58 k to ~10 k (instruction-cache footprint).
-RIPP_FN void f12_op(Ctx c, int op, uint32_t* D, const uint32_t* A, const uint32_t* B) {
-  const int k = c.k;
-  uint32_t* const sm = c.sm;
-  Acc3 acc;
-  acc_zero(acc);
-  const int nterm = op == 0 ? 6 : (op == 1 ? 4 : 3);
-#pragma unroll 1
-  for (int s = 0; s < nterm; s++) {
-    int ia, ib;
-    bool xi, dbl = false, zero = false;
-    const uint32_t* Y = B;
-    if (op == 0) {
-      int j = k - s;
-      xi = j < 0;
-      j += xi ? 6 : 0;
-      ia = s;
-      ib = j;
-    } else if (op == 1) {
-      // s-th solution of i + j = k (mod 6), i <= j, for this lane
-      int cnt = -1, ii = 0, jj = 0;
-      bool wrap = false, found = false;
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        int j = k - i;
-        bool w = j < 0;
-        j += w ? 6 : 0;
-        bool ok = j >= i;
-        cnt += ok ? 1 : 0;
-        bool take = ok && cnt == s && !found;
-        ii = take ? i : ii;
-        jj = take ? j : jj;
-        wrap = take ? w : wrap;
-        found = found || take;
-      }
-      ia = ii;
-      ib = jj;
-      Y = A;
-      xi = wrap;
-      dbl = ii != jj;
-      zero = !found;
-    } else {
-      int sh = s == 0 ? 0 : (s == 1 ? 2 : 3);
-      int j = k - sh;
-      xi = j < 0;
-      j += xi ? 6 : 0;
-      ia = j;
-      ib = s;
-      Y = sm + OFF_LINE;
-    }
-    Fq2 x = ld2(A + ia * FQ2W), y = ld2(Y + ib * FQ2W);
-    if (op == 1) {
-      y = f2sel(dbl, f2dbl(y), y);
-      x = f2sel(zero, Fq2::zero(), x);
-    }
-    y = f2sel(xi, f2xi(y), y);
-    f2_mac(acc, x, y);
-  }
-  Fq2 out = f2_finish(acc);
-  sync(c);
-  st2(D + k * FQ2W, out);
-  sync(c);
-}
-
-// ---- Fq12 ops on smem registers (collective: all six lanes call with the same arguments) ---------
+// ---- Fq12 ops on smem registers (collective: all lanes of the group call with the same arguments) ---------
 // D = A * B on raw coefficient arrays (6 x Fq2, flat w-basis); D may alias A or B
-RIPP_HD void mul_p(const Ctx& c, uint32_t* D, const uint32_t* A, const uint32_t* B);
-// dst = a * b;  dst may alias a or b
-RIPP_HD void mul(const Ctx& c, int dst, int a, int b) { mul_p(c, freg(c, dst), freg(c, a), freg(c, b)); }
-#if defined(RIPP_L6_SHARED_CODE)
-RIPP_HD void mul_p(const Ctx& c, uint32_t* D, const uint32_t* A, const uint32_t* B) { f12_op(c, 0, D, A, B); }
-RIPP_HD void sqr(const Ctx& c, int dst, int a) { f12_op(c, 1, freg(c, dst), freg(c, a), freg(c, a)); }
-RIPP_HD void mul_line(const Ctx& c, int dst, int a) { f12_op(c, 2, freg(c, dst), freg(c, a), c.sm + OFF_LINE); }
-#else
-RIPP_HD void mul_p(const Ctx& c, uint32_t* D, const uint32_t* A, const uint32_t* B) {
-  Acc3 acc;
+template <class C>
+RIPP_HD void mul_p(const C& c, uint32_t* D, const uint32_t* A, const uint32_t* B) {
+  typename AccOf<C>::type acc;
   acc_zero(acc);
 #pragma unroll 1
   for (int i = 0; i < 6; i++) {
@@ -259,22 +293,26 @@ RIPP_HD void mul_p(const Ctx& c, uint32_t* D, const uint32_t* A, const uint32_t*
     bool wrap = j < 0;
     j += wrap ? 6 : 0;
     Fq2 b = ld2(B + j * FQ2W);
-    f2_mac(acc, ld2(A + i * FQ2W), f2sel(wrap, f2xi(b), b));  // xi applied to the operand: stays linear
+    f2_mac(c, acc, ld2(A + i * FQ2W), f2sel(wrap, f2xi(b), b));  // xi applied to the operand: stays linear
   }
-  Fq2 out = f2_finish(acc);
+  Fq2 out = f2_finish(c, acc);
   sync(c);
   st2(D + c.k * FQ2W, out);
   sync(c);
 }
-// dst = a^2: 21 distinct products over six lanes (cross terms doubled)
-RIPP_HD void sqr(const Ctx& c, int dst, int a) {
+// dst = a * b;  dst may alias a or b
+template <class C>
+RIPP_HD void mul(const C& c, int dst, int a, int b) { mul_p(c, freg(c, dst), freg(c, a), freg(c, b)); }
+// dst = a^2: 21 distinct products over six coefficients (cross terms doubled)
+template <class C>
+RIPP_HD void sqr(const C& c, int dst, int a) {
   const uint32_t* A = freg(c, a);
-  Acc3 acc;
+  typename AccOf<C>::type acc;
   acc_zero(acc);
-  // pairs (i, j), i <= j, i + j = k or k + 6:  i runs over 0..3 slots; slots beyond the lane's count are masked
+  // pairs (i, j), i <= j, i + j = k or k + 6:  i runs over 0..3 slots; slots beyond the coefficient's count are masked
 #pragma unroll 1
   for (int s = 0; s < 4; s++) {
-    // s-th solution for this lane: enumerate i = 0..5 with j = (k - i) mod 6 >= i
+    // s-th solution for this coefficient: enumerate i = 0..5 with j = (k - i) mod 6 >= i
     int cnt = -1, ii = 0, jj = 0;
     bool wrap = false, found = false;
 #pragma unroll
@@ -293,16 +331,17 @@ RIPP_HD void sqr(const Ctx& c, int dst, int a) {
     Fq2 x = ld2(A + ii * FQ2W), y = ld2(A + jj * FQ2W);
     y = f2sel(ii != jj, f2dbl(y), y);
     y = f2sel(wrap, f2xi(y), y);
-    x = f2sel(found, x, Fq2::zero());  // lanes with only three terms add 0 in the fourth slot
-    f2_mac(acc, x, y);
+    x = f2sel(found, x, Fq2::zero());  // coefficients with only three terms add 0 in the fourth slot
+    f2_mac(c, acc, x, y);
   }
-  Fq2 out = f2_finish(acc);
+  Fq2 out = f2_finish(c, acc);
   sync(c);
   st2(freg(c, dst) + c.k * FQ2W, out);
   sync(c);
 }
 // dst = a * (d0 + d1 w^2 + d4 w^3), line coefficients at OFF_LINE (the ark-ec `mul_by_014` shape)
-RIPP_HD void mul_line(const Ctx& c, int dst, int a) {
+template <class C>
+RIPP_HD void mul_line(const C& c, int dst, int a) {
   const uint32_t* A = freg(c, a);
   const uint32_t* L = c.sm + OFF_LINE;
   int k = c.k;
@@ -310,34 +349,36 @@ RIPP_HD void mul_line(const Ctx& c, int dst, int a) {
   bool w2 = k2 < 0, w3 = k3 < 0;
   k2 += w2 ? 6 : 0;
   k3 += w3 ? 6 : 0;
-  Acc3 acc;
+  typename AccOf<C>::type acc;
   acc_zero(acc);
-  f2_mac(acc, ld2(A + k * FQ2W), ld2(L));
+  f2_mac(c, acc, ld2(A + k * FQ2W), ld2(L));
   Fq2 d = ld2(L + FQ2W);
-  f2_mac(acc, ld2(A + k2 * FQ2W), f2sel(w2, f2xi(d), d));
+  f2_mac(c, acc, ld2(A + k2 * FQ2W), f2sel(w2, f2xi(d), d));
   d = ld2(L + 2 * FQ2W);
-  f2_mac(acc, ld2(A + k3 * FQ2W), f2sel(w3, f2xi(d), d));
-  Fq2 out = f2_finish(acc);
+  f2_mac(c, acc, ld2(A + k3 * FQ2W), f2sel(w3, f2xi(d), d));
+  Fq2 out = f2_finish(c, acc);
   sync(c);
   st2(freg(c, dst) + k * FQ2W, out);
   sync(c);
 }
-#endif  // RIPP_L6_SHARED_CODE
 // dst = conj(a)  (w -> -w)
-RIPP_HD void conj(const Ctx& c, int dst, int a) {
+template <class C>
+RIPP_HD void conj(const C& c, int dst, int a) {
   Fq2 v = ld2(freg(c, a) + c.k * FQ2W);
   v = f2sel(c.k & 1, f2neg(v), v);
   sync(c);
   st2(freg(c, dst) + c.k * FQ2W, v);
   sync(c);
 }
-RIPP_HD void copy(const Ctx& c, int dst, int a) {
+template <class C>
+RIPP_HD void copy(const C& c, int dst, int a) {
   Fq2 v = ld2(freg(c, a) + c.k * FQ2W);
   sync(c);
   st2(freg(c, dst) + c.k * FQ2W, v);
   sync(c);
 }
-RIPP_HD void set_one(const Ctx& c, int dst) {
+template <class C>
+RIPP_HD void set_one(const C& c, int dst) {
   st2(freg(c, dst) + c.k * FQ2W, f2sel(c.k == 0, Fq2::one(), Fq2::zero()));
   sync(c);
 }
@@ -350,18 +391,20 @@ RIPP_HD Fq2 frob_gamma(int npow, int k) {
   }
   return g;
 }
-// dst = a^(p^npow), npow in {1, 2}: lane-local
-RIPP_HD void frob(const Ctx& c, int dst, int a, int npow) {
+// dst = a^(p^npow), npow in {1, 2}: coefficient-local
+template <class C>
+RIPP_HD void frob(const C& c, int dst, int a, int npow) {
   Fq2 v = ld2(freg(c, a) + c.k * FQ2W);
   v = f2sel(npow & 1, f2conj(v), v);
-  v = f2mul(v, frob_gamma(npow, c.k));
+  v = f2mul(c, v, frob_gamma(npow, c.k));
   sync(c);
   st2(freg(c, dst) + c.k * FQ2W, v);
   sync(c);
 }
 // dst = a^-1 via the norm to Fq2: N = a conj(a) in Fq6, d = N N^(p^2) N^(p^4) in Fq2, a^-1 = conj(a) N^(p^2) N^(p^4) / d.
 // Clobbers registers t0, t1, t2 (all distinct from a and dst).
-RIPP_HD void inv(const Ctx& c, int dst, int a, int t0, int t1, int t2) {
+template <class C>
+RIPP_HD void inv(const C& c, int dst, int a, int t0, int t1, int t2) {
   conj(c, t0, a);
   mul(c, t1, a, t0);      // N
   frob(c, t2, t1, 2);     // N^(p^2)
@@ -371,20 +414,21 @@ RIPP_HD void inv(const Ctx& c, int dst, int a, int t0, int t1, int t2) {
   Fq2 d = ld2(freg(c, dst));
   Fq dn = (fqmul(d.c0, d.c0) + fqmul(d.c1, d.c1)).inv();
   Fq2 dinv = {fqmul(d.c0, dn), -fqmul(d.c1, dn)};
-  Fq2 tk = f2mul(ld2(freg(c, t2) + c.k * FQ2W), dinv);
+  Fq2 tk = f2mul(c, ld2(freg(c, t2) + c.k * FQ2W), dinv);
   sync(c);
   st2(freg(c, t2) + c.k * FQ2W, tk);  // N^-1
   sync(c);
   mul(c, dst, t0, t2);
 }
 
-// dst = a^2 for a in the cyclotomic subgroup (Granger-Scott): ONE Fq2 product per lane.
-// In the flat basis the three Fq4 pairs are (a0, a3), (a1, a4), (a2, a5); lane k < 3 forms a_k a_{k+3},
-// lane k >= 3 forms (a_{k-3} + a_k)(a_{k-3} + xi a_k), and with
+// dst = a^2 for a in the cyclotomic subgroup (Granger-Scott): ONE Fq2 product per coefficient.
+// In the flat basis the three Fq4 pairs are (a0, a3), (a1, a4), (a2, a5); coefficient k < 3 forms a_k a_{k+3},
+// coefficient k >= 3 forms (a_{k-3} + a_k)(a_{k-3} + xi a_k), and with
 //   t_even(pair) = (ra + rb)(ra + xi rb) - (1 + xi) ra rb,  t_odd(pair) = 2 ra rb
 // the outputs are  a0' = 3 t_even(A) - 2 a0,  a3' = 3 t_odd(A) + 2 a3,  a1' = 3 xi t_odd(C) + 2 a1,
 // a4' = 3 t_even(C) - 2 a4,  a2' = 3 t_even(B) - 2 a2,  a5' = 3 t_odd(B) + 2 a5   (A, B, C = pairs 0, 1, 2).
-RIPP_HD void cyc_sqr(const Ctx& c, int dst, int a) {
+template <class C>
+RIPP_HD void cyc_sqr(const C& c, int dst, int a) {
   const uint32_t* A = freg(c, a);
   uint32_t* R = c.sm + OFF_R;
   const int k = c.k, pr = k % 3;
@@ -392,9 +436,9 @@ RIPP_HD void cyc_sqr(const Ctx& c, int dst, int a) {
   Fq2 u = f2sel(k < 3, ra, f2add(ra, rb));
   Fq2 v = f2sel(k < 3, rb, f2add(ra, f2xi(rb)));
   Fq2 own = ld2(A + k * FQ2W);
-  st2(R + k * FQ2W, f2mul(u, v));
+  st2(R + k * FQ2W, f2mul(c, u, v));
   sync(c);
-  // source pair of this lane's output: a0,a3 <- A(0); a2,a5 <- B(1); a1,a4 <- C(2)
+  // source pair of this coefficient's output: a0,a3 <- A(0); a2,a5 <- B(1); a1,a4 <- C(2)
   const int src = (k % 3 == 0) ? 0 : (k % 3 == 2 ? 1 : 2);
   Fq2 prod = ld2(R + src * FQ2W), cross = ld2(R + (src + 3) * FQ2W);
   Fq2 t_even = f2sub(cross, f2add(prod, f2xi(prod)));
@@ -410,7 +454,8 @@ RIPP_HD void cyc_sqr(const Ctx& c, int dst, int a) {
 }
 
 // a^x (x = -|x|) for a in the cyclotomic subgroup; dst != a; clobbers nothing else
-RIPP_HD void exp_by_x(const Ctx& c, int dst, int a) {
+template <class C>
+RIPP_HD void exp_by_x(const C& c, int dst, int a) {
   copy(c, dst, a);
 #pragma unroll 1
   for (int i = 62; i >= 0; i--) {
@@ -425,7 +470,8 @@ RIPP_HD void exp_by_x(const Ctx& c, int dst, int a) {
 // (mul_helper on GT, gipa.rs:355-357; sipp/src/lib.rs:148-156).  Fixed 2-bit windows; the window digit
 // selects an operand ADDRESS (1, a, a^2, a^3), so groups with different exponents share one instruction stream.
 // a in register t1; clobbers t2, t3, one.
-RIPP_HD void pow_fr(const Ctx& c, int acc, int t1, int t2, int t3, int one, const uint32_t* e) {
+template <class C>
+RIPP_HD void pow_fr(const C& c, int acc, int t1, int t2, int t3, int one, const uint32_t* e) {
   set_one(c, one);
   set_one(c, acc);
   sqr(c, t2, t1);
@@ -441,7 +487,8 @@ RIPP_HD void pow_fr(const Ctx& c, int acc, int t1, int t2, int t3, int one, cons
 }
 
 // Register 0 <- final_exponentiation(register 0) (ark-ec convention, see pairing.cuh); needs 8 registers.
-RIPP_HD void final_exp(const Ctx& c) {
+template <class C>
+RIPP_HD void final_exp(const C& c) {
   enum { F = 0, R = 1, Y0 = 2, Y1 = 3, Y2 = 4, T0 = 5, T1 = 6, T2 = 7 };
   inv(c, R, F, T0, T1, T2);   // R = f^-1
   conj(c, Y0, F);
@@ -471,7 +518,8 @@ RIPP_HD void final_exp(const Ctx& c) {
 // ---- Miller loop --------------------------------------------------------------------------------
 // smem: T = (x, y, z) at OFF_T, P = (xP, yP) at OFF_P, Q = (xQ, yQ) at OFF_Q, accumulator in register 0.
 // One doubling step: two rounds of at most six parallel Fq2 products.
-RIPP_HD void dbl_step(const Ctx& c, uint32_t* pb) {
+template <class C>
+RIPP_HD void dbl_step(const C& c, uint32_t* pb) {
   uint32_t* T = pb + PB_T;
   uint32_t* R = c.sm + OFF_R;
   const int k = c.k;
@@ -480,7 +528,7 @@ RIPP_HD void dbl_step(const Ctx& c, uint32_t* pb) {
   Fq2 yz = f2add(y, z);
   Fq2 u = f2sel(k == 0 || k == 4, x, f2sel(k == 3, yz, f2sel(k == 2, z, y)));
   Fq2 v = f2sel(k == 0 || k == 1, y, f2sel(k == 3, yz, f2sel(k == 2, z, x)));
-  st2(R + k * FQ2W, f2mul(u, v));
+  st2(R + k * FQ2W, f2mul(c, u, v));
   sync(c);
   Fq2 a = f2half(ld2(R)), b = ld2(R + FQ2W), cc = ld2(R + 2 * FQ2W), d = ld2(R + 3 * FQ2W), j = ld2(R + 4 * FQ2W);
   Fq2 e = f2dbl(f2dbl(f2xi(f2add(f2dbl(cc), cc))));  // 4 xi * 3 z^2
@@ -495,7 +543,7 @@ RIPP_HD void dbl_step(const Ctx& c, uint32_t* pb) {
   Fq2 sxp = {xp, Fq::zero()}, syp = {yp, Fq::zero()};
   u = f2sel(k == 0, a, f2sel(k == 1, g, f2sel(k == 2, b, f2sel(k == 3, e, f2sel(k == 4, j3, f2neg(h))))));
   v = f2sel(k == 0, f2sub(b, f), f2sel(k == 1, g, f2sel(k == 2, h, f2sel(k == 3, e, f2sel(k == 4, sxp, syp)))));
-  st2(R + k * FQ2W, f2mul(u, v));
+  st2(R + k * FQ2W, f2mul(c, u, v));
   sync(c);
   // new T and the line (d0, d1, d4) = (e - b, 3j xP, -h yP)
   Fq2 e2 = ld2(R + 3 * FQ2W);
@@ -516,28 +564,29 @@ RIPP_HD void dbl_step(const Ctx& c, uint32_t* pb) {
 }
 
 // One addition step T <- T + Q with the chord line.
-RIPP_HD void add_step(const Ctx& c, uint32_t* pb) {
+template <class C>
+RIPP_HD void add_step(const C& c, uint32_t* pb) {
   uint32_t* T = pb + PB_T;
   uint32_t* R = c.sm + OFF_R;
   const int k = c.k;
   Fq2 x = ld2(T), y = ld2(T + FQ2W), z = ld2(T + 2 * FQ2W);
   Fq2 qx = ld2(pb + PB_Q), qy = ld2(pb + PB_Q + FQ2W);
   // round 1: R0 = qy z, R1 = qx z
-  st2(R + k * FQ2W, f2mul(f2sel(k == 0, qy, qx), z));
+  st2(R + k * FQ2W, f2mul(c, f2sel(k == 0, qy, qx), z));
   sync(c);
   Fq2 theta = f2sub(y, ld2(R)), lambda = f2sub(x, ld2(R + FQ2W));
   sync(c);
   // round 2: R0 = theta^2, R1 = lambda^2, R2 = theta qx, R3 = lambda qy
   Fq2 u = f2sel(k == 0 || k == 2, theta, lambda);
   Fq2 v = f2sel(k == 0, theta, f2sel(k == 1, lambda, f2sel(k == 2, qx, qy)));
-  st2(R + k * FQ2W, f2mul(u, v));
+  st2(R + k * FQ2W, f2mul(c, u, v));
   sync(c);
   Fq2 cc = ld2(R), d = ld2(R + FQ2W), jv = f2sub(ld2(R + 2 * FQ2W), ld2(R + 3 * FQ2W));
   sync(c);
   // round 3: R0 = lambda d (= e), R1 = z c (= f), R2 = x d (= g)
   u = f2sel(k == 0, lambda, f2sel(k == 1, z, x));
   v = f2sel(k == 1, cc, d);
-  st2(R + k * FQ2W, f2mul(u, v));
+  st2(R + k * FQ2W, f2mul(c, u, v));
   sync(c);
   Fq2 e = ld2(R), f = ld2(R + FQ2W), g = ld2(R + 2 * FQ2W);
   Fq2 h = f2sub(f2add(e, f), f2dbl(g));
@@ -548,7 +597,7 @@ RIPP_HD void add_step(const Ctx& c, uint32_t* pb) {
   Fq2 sxp = {xp, Fq::zero()}, syp = {yp, Fq::zero()};
   u = f2sel(k == 0, lambda, f2sel(k == 1, theta, f2sel(k == 2, e, f2sel(k == 3, z, f2sel(k == 4, f2neg(theta), lambda)))));
   v = f2sel(k == 0, h, f2sel(k == 1, f2sub(g, h), f2sel(k == 2, y, f2sel(k == 3, e, f2sel(k == 4, sxp, syp)))));
-  st2(R + k * FQ2W, f2mul(u, v));
+  st2(R + k * FQ2W, f2mul(c, u, v));
   sync(c);
   Fq2 nx = ld2(R), ny = f2sub(ld2(R + FQ2W), ld2(R + 2 * FQ2W)), nz = ld2(R + 3 * FQ2W);
   Fq2 d1 = ld2(R + 4 * FQ2W), d4 = ld2(R + 5 * FQ2W);
@@ -569,7 +618,8 @@ RIPP_HD void add_step(const Ctx& c, uint32_t* pb) {
 // Register 0 <- prod_j f_{|x|,Q_j}(P_j), conjugated, over the npairs pair blocks at `pairs` (P, Q and the
 // valid flag staged by the caller; masked pairs must still hold finite points).  One accumulator squaring per
 // bit is shared by all the group's pairs.
-RIPP_HD void miller(const Ctx& c, uint32_t* pairs, int npairs) {
+template <class C>
+RIPP_HD void miller(const C& c, uint32_t* pairs, int npairs) {
   if (c.k == 0) {
     for (int j = 0; j < npairs; j++) {
       uint32_t* pb = pairs + j * PAIR_WORDS;
