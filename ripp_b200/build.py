@@ -44,9 +44,22 @@ def build_lib(force=False, verbose=False):
     out_lib = os.environ.get("RIPP_B200_OUT", LIB)
     os.makedirs(objdir, exist_ok=True)
 
+    def obj_stale(obj, dep):
+        # per-object staleness from the dependency file nvcc wrote with the object (-MD): only the translation
+        # units that include an edited header are recompiled (pairing6.cu alone takes minutes)
+        if force or not os.path.exists(obj) or not os.path.exists(dep):
+            return True
+        t = os.path.getmtime(obj)
+        words = open(dep).read().replace("\\\n", " ").split()
+        files = [w for w in words[1:] if not w.endswith(":")]
+        return any((not os.path.exists(f)) or os.path.getmtime(f) > t for f in files)
+
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        dep = obj[:-2] + ".d"
+        if not obj_stale(obj, dep):
+            return obj
+        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-MD", "-MF", dep, "-c", "-o", obj, src]
         print("[ripp_b200.build]", " ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True, cwd=CSRC)
         return obj

@@ -45,9 +45,7 @@ struct CtxT {
   static constexpr int W = W_;
   int k;          // coefficient (lane within the group for W = 1), 0..5
   uint32_t* sm;   // group scratch
-#if !defined(__CUDA_ARCH__)
-  void* bar;      // host: barrier object
-#endif
+  void* bar;      // host build (tests/hostsim): barrier object; unused on the device
   int role;       // W = 3: Karatsuba role of this lane, 0..2
   uint32_t* bus;  // W = 3: 2 * BUS_WORDS words of the group's scratch
   mutable int par;  // W = 3: which bus buffer the next exchange uses

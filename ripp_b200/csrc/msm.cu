@@ -6,6 +6,7 @@
 // sipp/src/lib.rs:87-100; scalar-mul primitive `mul_helper`, ip_proofs/src/lib.rs:15-19).
 #include "common.cuh"
 #include "x3.cuh"
+#include "xt.cuh"
 
 static bool use_endo() {
   static const bool v = [] {
@@ -539,6 +540,39 @@ __global__ void __maxnreg__(255) k_fold_w3(const Aff<XF>* __restrict__ hi, const
   if (live && threadIdx.x < 32) out[i] = o;
 }
 
+// lane teams (xt.cuh): 3 lanes per G1 element (10 per warp), 9 lanes per G2 element (3 per warp); the remaining lanes
+// mirror the first ones (same element, same bus slice: identical values), elements past n redo element n - 1 on their
+// own bus slice and do not store.
+constexpr int XT_WARPS = 2;
+template <class F>
+__global__ void __launch_bounds__(32 * XT_WARPS) k_fold_xt(const Aff<F>* __restrict__ hi, const Aff<F>* __restrict__ lo, EndoBits c,
+                                                           size_t n, Aff<F>* __restrict__ out) {
+  typedef xt::TeamOf<F> TO;
+  constexpr int AW4 = 4 * sizeof(Aff<F>) / 4;  // four endomorphism images of the element
+  __shared__ __align__(16) uint32_t bus[XT_WARPS * TO::PER_WARP * (2 * TO::BUS_WORDS + AW4)];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vl = lane % (TO::LANES * TO::PER_WARP);
+  const int e = vl / TO::LANES;
+  size_t i = ((size_t)blockIdx.x * XT_WARPS + warp) * TO::PER_WARP + e;
+  const bool live = i < n && lane == vl;
+  if (i >= n) i = n - 1;
+  uint32_t* scratch = bus + (warp * TO::PER_WARP + e) * (2 * TO::BUS_WORDS + AW4);
+  xt::Team tm{vl % TO::LANES, scratch, 0, nullptr};
+  Jac<F> acc = xt::endo_mul<F>(tm, hi[i], c, scratch + 2 * TO::BUS_WORDS);
+  acc = xt::madd<F>(tm, acc, lo[i]);
+  Aff<F> o = xt::to_affine<F>(tm, acc);
+  if (live && tm.t == 0) out[i] = o;
+}
+// vectors up to this length run on lane teams (RIPP_B200_XT_MAX overrides): 2048 G2 elements are 683 warps, about one
+// per sub-partition
+static size_t xt_max_n() {
+  static const long v = [] {
+    const char* e = getenv("RIPP_B200_XT_MAX");
+    return e ? atol(e) : 2048L;
+  }();
+  return (size_t)v;
+}
+
 template <class F, class XF>
 static int fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c, size_t n, void* out) {
   if (!ctx || !c || (n && (!hi || !lo || !out))) return fail(RIPP_ERR_ARG, "null argument");
@@ -546,7 +580,12 @@ static int fold_dev(ripp_ctx* ctx, const void* hi, const void* lo, const void* c
   CU(cudaSetDevice(ctx->device));
   TimeScope ts_(ctx, RIPP_T_FOLD);
   const int mode = fold_mode();
-  if (mode == 1 || (mode == 0 && n <= w3_max_n())) {
+  if (mode == 0 && n <= xt_max_n()) {
+    typedef xt::TeamOf<F> TO;
+    unsigned warps = (unsigned)((n + TO::PER_WARP - 1) / TO::PER_WARP);
+    k_fold_xt<F><<<(warps + XT_WARPS - 1) / XT_WARPS, 32 * XT_WARPS, 0, ctx->stream>>>((const Aff<F>*)hi, (const Aff<F>*)lo,
+                                                                                     endo_bits<F>(c), n, (Aff<F>*)out);
+  } else if (mode == 1 || (mode == 0 && n <= w3_max_n())) {
     k_fold_w3<XF><<<(unsigned)((n + 31) / 32), 96, 0, ctx->stream>>>((const Aff<XF>*)hi, (const Aff<XF>*)lo, endo_bits<F>(c), n,
                                                                    (Aff<XF>*)out);
   } else if (mode != 3) {

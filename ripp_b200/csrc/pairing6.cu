@@ -144,21 +144,150 @@ __global__ void __launch_bounds__(32) k_gt_pow6(const Fq12* __restrict__ in, con
   if (live) reinterpret_cast<Fq2*>(out + t)[tower_slot(c.k)] = ld2(freg(c, 0) + c.k * FQ2W);
 }
 
+// ------------------------------------------------------------------------------------------------
+// W = 3 shape (l6.cuh): ONE Fq12 per warp on 18 lanes.  For the latency-bound end of the path -- the late GIPA
+// rounds, every final exponentiation, the verifiers' GT powers -- where there are fewer Fq12 chains than
+// sub-partitions and the length of ONE chain is the whole cost.
+// ------------------------------------------------------------------------------------------------
+static __device__ __forceinline__ Ctx3 ctx18(uint32_t* wsm, int group_words_no_bus) {
+  const int vl = (threadIdx.x & 31) % 18;  // lanes 18..31 mirror lanes 0..13: same addresses, same values
+  return Ctx3{vl / 3, wsm, nullptr, vl % 3, wsm + group_words_no_bus, 0};
+}
+constexpr int M18_WARPS = 4;
+template <int KP>
+RIPP_HD constexpr int m18_group_words() { return group_words(M6_NREG, KP) + 2 * BUS_WORDS; }
+
+// grid (ceil(wps / 4), nseg): warp w of segment s walks pairs [w KP, w KP + KP); the CTA's four Miller values are
+// multiplied in shared memory; one partial per CTA at partials[s * gridDim.x + blockIdx.x].
+template <int KP>
+__global__ void __launch_bounds__(32 * M18_WARPS) k_miller18(Miller6Batch b, Fq12* __restrict__ partials) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  constexpr int GW = m18_group_words<KP>();
+  const int warp = threadIdx.x >> 5;
+  uint32_t* wsm = smem + warp * GW;
+  Ctx3 c = ctx18(wsm, group_words(M6_NREG, KP));
+  uint32_t* pairs = c.sm + OFF_F + M6_NREG * F12W;
+  const uint32_t seg = blockIdx.y, wl = blockIdx.x * M18_WARPS + warp;
+  if (c.k == 0 && c.role == 0) {
+    for (int j = 0; j < KP; j++) {
+      const uint32_t i = wl * KP + j;
+      G1Aff P = g1_generator();
+      G2Aff Q = g2_generator();
+      uint32_t valid = 0;
+      if (i < b.n) {
+        G1Aff p = b.p[seg][i];
+        G2Aff q = b.q[seg][i];
+        if (!p.is_inf() && !q.is_inf()) {
+          P = p;
+          Q = q;
+          valid = 1;
+        }
+      }
+      uint32_t* pb = pairs + j * PAIR_WORDS;
+      st2(pb + PB_P, Fq2{P.x, P.y});
+      st2(pb + PB_Q, Q.x);
+      st2(pb + PB_Q + FQ2W, Q.y);
+      pb[PB_VALID] = valid;
+    }
+  }
+  __syncwarp();
+  miller(c, pairs, KP);
+  uint32_t* F0 = freg(c, 0);
+  auto other = [&](int w) { return smem + w * GW + OFF_F; };
+  __syncthreads();
+  if ((warp & 1) == 0) mul_p(c, F0, F0, other(warp + 1));
+  __syncthreads();
+  if (warp == 0) {
+    mul_p(c, F0, F0, other(2));
+    if (c.role == 0) {
+      Fq2* out = reinterpret_cast<Fq2*>(&partials[(size_t)seg * gridDim.x + blockIdx.x]);
+      out[tower_slot(c.k)] = ld2(F0 + c.k * FQ2W);
+    }
+  }
+}
+
+// out[s][j] = prod in[s][j*R .. min(T, j*R+R)); one warp per output
+constexpr int R18_GROUP_WORDS = group_words(2, 0) + 2 * BUS_WORDS;
+__global__ void __launch_bounds__(32 * M18_WARPS) k_reduce18(const Fq12* __restrict__ in, uint32_t T, uint32_t R, uint32_t To,
+                                                            Fq12* __restrict__ out, uint32_t total) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int warp = threadIdx.x >> 5;
+  Ctx3 c = ctx18(smem + warp * R18_GROUP_WORDS, group_words(2, 0));
+  uint32_t t = blockIdx.x * M18_WARPS + warp;
+  bool live = t < total;
+  uint32_t s = live ? t / To : 0, j = live ? t % To : 0;
+  uint32_t lo = j * R, hi = lo + R < T ? lo + R : T;
+  const Fq2* src = reinterpret_cast<const Fq2*>(in + (size_t)s * T);
+  st2(freg(c, 0) + c.k * FQ2W, src[(size_t)lo * 6 + tower_slot(c.k)]);
+  __syncwarp();
+  for (uint32_t r = 1; r < R; r++) {
+    bool on = lo + r < hi;
+    Fq2 v = on ? src[(size_t)(lo + r) * 6 + tower_slot(c.k)] : f2sel(c.k == 0, Fq2::one(), Fq2::zero());
+    st2(freg(c, 1) + c.k * FQ2W, v);
+    __syncwarp();
+    mul(c, 0, 0, 1);
+  }
+  if (live && c.role == 0) reinterpret_cast<Fq2*>(out + t)[tower_slot(c.k)] = ld2(freg(c, 0) + c.k * FQ2W);
+}
+
+// out[s] = final_exponentiation(prod_j in[s][j]), j < T; one warp (one CTA) per value
+constexpr int FE18_GROUP_WORDS = group_words(FE_NREG, 0) + 2 * BUS_WORDS;
+__global__ void __launch_bounds__(32) k_final_exp18(const Fq12* __restrict__ in, uint32_t T, Fq12* __restrict__ out) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  Ctx3 c = ctx18(smem, group_words(FE_NREG, 0));
+  const int s = blockIdx.x;
+  const Fq2* src = reinterpret_cast<const Fq2*>(in + (size_t)s * T);
+  st2(freg(c, 0) + c.k * FQ2W, src[tower_slot(c.k)]);
+  __syncwarp();
+  for (uint32_t r = 1; r < T; r++) {
+    st2(freg(c, 8) + c.k * FQ2W, src[(size_t)r * 6 + tower_slot(c.k)]);
+    __syncwarp();
+    mul(c, 0, 0, 8);
+  }
+  final_exp(c);
+  if (c.role == 0) reinterpret_cast<Fq2*>(out + s)[tower_slot(c.k)] = ld2(freg(c, 0) + c.k * FQ2W);
+}
+
+// out[i] = in[i]^sc[i], one warp per element (k_gt_pow6 on eighteen lanes)
+constexpr int GP18_GROUP_WORDS = group_words(GP_NREG, 0) + 2 * BUS_WORDS;
+__global__ void __launch_bounds__(32) k_gt_pow18(const Fq12* __restrict__ in, const Fr* __restrict__ sc, uint32_t n,
+                                                 Fq12* __restrict__ out) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  Ctx3 c = ctx18(smem, group_words(GP_NREG, 0));
+  const uint32_t t = blockIdx.x;
+  const Fq2* src = reinterpret_cast<const Fq2*>(in + t);
+  st2(freg(c, 1) + c.k * FQ2W, src[tower_slot(c.k)]);
+  uint32_t* e = c.sm + OFF_LINE;  // the line slot is free here: holds the canonical exponent
+  if (c.k == 0 && c.role == 0) {
+    Fr s = sc[t].from_mont();
+    for (int i = 0; i < 8; i++) e[i] = s.v[i];
+  }
+  __syncwarp();
+  pow_fr(c, 0, 1, 2, 3, 4, e);
+  if (c.role == 0) reinterpret_cast<Fq2*>(out + t)[tower_slot(c.k)] = ld2(freg(c, 0) + c.k * FQ2W);
+}
+
+// number of warps the eighteen-lane kernels may occupy before the throughput shape takes over: two per
+// sub-partition (a third warp on a sub-partition queues behind the same multiplier pipe).  RIPP_B200_L18_WARPS overrides.
+static size_t l18_max_warps() {
+  static const long v = [] {
+    const char* e = getenv("RIPP_B200_L18_WARPS");
+    return e ? atol(e) : 1184L;
+  }();
+  return (size_t)v;
+}
+
 // GT membership of untrusted Fq12 values (what ark-serialize's Valid::check establishes for PairingOutput when the
 // reference deserialises a proof): f is in the cyclotomic subgroup, f^(p^4) f == f^(p^2), and f^p == f^x
 // (Scott, ePrint 2021/1130; oracle: gt_in_subgroup_fast, checked there against f^r == 1).  One group per element;
 // a failing element ORs `flag` into *bad.
 constexpr int GC_NREG = 3;
-constexpr int GC_GROUP_WORDS = group_words(GC_NREG, 0);
-__global__ void __launch_bounds__(32) k_gt_check6(const Fq12* __restrict__ in, uint32_t n, uint32_t* __restrict__ bad,
-                                                  uint32_t flag) {
+constexpr int GC_GROUP_WORDS = group_words(GC_NREG, 0) + 2 * BUS_WORDS;
+__global__ void __launch_bounds__(32) k_gt_check18(const Fq12* __restrict__ in, uint32_t n, uint32_t* __restrict__ bad,
+                                                   uint32_t flag) {
   extern __shared__ __align__(16) uint32_t smem[];
-  const int lane = threadIdx.x & 31;
-  const int g = lane / 6;
-  Ctx c{lane % 6, smem + g * GC_GROUP_WORDS};
-  uint32_t t = blockIdx.x * 5 + g;
-  bool live = g < 5 && t < n;
-  const Fq2* src = reinterpret_cast<const Fq2*>(in + (live ? t : 0));
+  Ctx3 c = ctx18(smem, group_words(GC_NREG, 0));
+  const Fq2* src = reinterpret_cast<const Fq2*>(in + blockIdx.x);
   st2(freg(c, 0) + c.k * FQ2W, src[tower_slot(c.k)]);
   __syncwarp();
   frob(c, 1, 0, 2);
@@ -169,11 +298,11 @@ __global__ void __launch_bounds__(32) k_gt_check6(const Fq12* __restrict__ in, u
   exp_by_x(c, 2, 0);  // cyclotomic squarings: meaningful only when the first test passed, and only then consulted
   frob(c, 1, 0, 1);
   ne = ne || !(ld2(freg(c, 2) + c.k * FQ2W) == ld2(freg(c, 1) + c.k * FQ2W));
-  if (live && ne) atomicOr(bad, flag);
+  if (ne) atomicOr(bad, flag);
 }
 int ripp_gt_check_l6(ripp_ctx* ctx, const void* in, size_t n, uint32_t* bad_dev, uint32_t flag) {
   if (n == 0) return RIPP_OK;
-  k_gt_check6<<<(unsigned)((n + 4) / 5), 32, 6 * GC_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, (uint32_t)n, bad_dev, flag);
+  k_gt_check18<<<(unsigned)n, 32, GC_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, (uint32_t)n, bad_dev, flag);
   LAUNCHED(ctx);
   return RIPP_OK;
 }
@@ -191,8 +320,12 @@ int ripp_gt_multiexp_l6(ripp_ctx* ctx, const void* in, const void* sc, size_t n,
   OK(scratch(ctx, 17, n * sizeof(Fq12) + 4096, &bufA));
   OK(scratch(ctx, 18, n * sizeof(Fq12) / 4 + 8192, &bufB));
   TimeScope ts_(ctx, RIPP_T_OTHER);
-  k_gt_pow6<<<(unsigned)((n + 4) / 5), 32, 6 * GP_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, (const Fr*)sc, (uint32_t)n,
-                                                                                  n == 1 ? (Fq12*)out : (Fq12*)bufA);
+  if (n <= l18_max_warps())
+    k_gt_pow18<<<(unsigned)n, 32, GP18_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, (const Fr*)sc, (uint32_t)n,
+                                                                     n == 1 ? (Fq12*)out : (Fq12*)bufA);
+  else
+    k_gt_pow6<<<(unsigned)((n + 4) / 5), 32, 6 * GP_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, (const Fr*)sc, (uint32_t)n,
+                                                                                    n == 1 ? (Fq12*)out : (Fq12*)bufA);
   LAUNCHED(ctx);
   const uint32_t R = 8;
   Fq12 *src = (Fq12*)bufA, *dst = (Fq12*)bufB;
@@ -241,17 +374,56 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
     b.p[s] = (const G1Aff*)g1[s];
     b.q[s] = (const G2Aff*)g2[s];
   }
-  // pairs per group: the largest of {4, 2, 1} that still leaves ~one wave of groups (148 SMs x 8 warps x 5)
   size_t total = (size_t)nseg * n;
-  int kp = total >= 4 * 5920 ? 4 : (total >= 2 * 5920 ? 2 : 1);
-  size_t max_warps = (size_t)nseg * ((n + 4) / 5);
+  size_t max_partials = (size_t)nseg * ((n + 3) / 4 + 1);
   void *bufA, *bufB;
-  OK(scratch(ctx, 2, max_warps * sizeof(Fq12) + 4096, &bufA));
-  OK(scratch(ctx, 3, max_warps * sizeof(Fq12) / 4 + 8192, &bufB));
-  const uint32_t R = 8;
+  OK(scratch(ctx, 2, max_partials * sizeof(Fq12) + 4096, &bufA));
+  OK(scratch(ctx, 3, max_partials * sizeof(Fq12) / 4 + 8192, &bufB));
   Fq12 *src = (Fq12*)bufA, *dst = (Fq12*)bufB;
-  size_t nwarps = 0;
   uint32_t T;
+  const size_t w18 = l18_max_warps();
+  if (total <= 4 * w18) {
+    // latency shape: one pair (or 2 / 4 sharing an accumulator) per eighteen-lane warp, four warps per CTA combined
+    // in shared memory, then a tree of one-warp products and one warp per final exponentiation
+    {
+      TimeScope ts_(ctx, RIPP_T_MILLER);
+      const int kp = total <= w18 ? 1 : (total <= 2 * w18 ? 2 : 4);
+      const uint32_t wps = (uint32_t)((n + kp - 1) / kp), ctas = (wps + M18_WARPS - 1) / M18_WARPS;
+      b.wps = wps;
+      dim3 grid(ctas, nseg);
+      if (kp == 1)
+        k_miller18<1><<<grid, 32 * M18_WARPS, M18_WARPS * m18_group_words<1>() * 4, ctx->stream>>>(b, src);
+      else if (kp == 2)
+        k_miller18<2><<<grid, 32 * M18_WARPS, M18_WARPS * m18_group_words<2>() * 4, ctx->stream>>>(b, src);
+      else
+        k_miller18<4><<<grid, 32 * M18_WARPS, M18_WARPS * m18_group_words<4>() * 4, ctx->stream>>>(b, src);
+      LAUNCHED(ctx);
+      T = ctas;
+      const uint32_t R = 4, stop = with_final_exp ? R : 1;
+      while (T > stop) {
+        uint32_t To = (T + R - 1) / R, tot = (uint32_t)nseg * To;
+        k_reduce18<<<(tot + M18_WARPS - 1) / M18_WARPS, 32 * M18_WARPS, M18_WARPS * R18_GROUP_WORDS * 4, ctx->stream>>>(src, T, R, To,
+                                                                                                                     dst, tot);
+        LAUNCHED(ctx);
+        Fq12* t = src;
+        src = dst;
+        dst = t;
+        T = To;
+      }
+    }
+    if (!with_final_exp) {
+      CU(cudaMemcpyAsync(out, src, (size_t)nseg * sizeof(Fq12), cudaMemcpyDeviceToDevice, ctx->stream));
+      return RIPP_OK;
+    }
+    TimeScope ts2_(ctx, RIPP_T_FINAL_EXP);
+    k_final_exp18<<<nseg, 32, FE18_GROUP_WORDS * 4, ctx->stream>>>(src, T, (Fq12*)out);
+    LAUNCHED(ctx);
+    return RIPP_OK;
+  }
+  // throughput shape.  Pairs per group: the largest of {4, 2, 1} that still leaves ~one wave of groups (148 SMs x 8 warps x 5)
+  int kp = total >= 4 * 5920 ? 4 : (total >= 2 * 5920 ? 2 : 1);
+  const uint32_t R = 8;
+  size_t nwarps = 0;
   {
     TimeScope ts_(ctx, RIPP_T_MILLER);
     if (kp == 4)
@@ -261,13 +433,12 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
     else
       OK(launch_miller6<1>(ctx, b, n, src, &nwarps));
     T = b.wps;
-    uint32_t stop = with_final_exp ? R : 1;
+    uint32_t stop = with_final_exp ? 4 : 1;
     while (T > stop) {
       uint32_t To = (T + R - 1) / R;
       uint32_t tot = (uint32_t)nseg * To;
-      Fq12* o = (!with_final_exp && To == 1) ? (Fq12*)out : dst;
       unsigned blk = (tot + 5 * M6_WARPS - 1) / (5 * M6_WARPS);
-      k_reduce6<M6_WARPS><<<blk, 32 * M6_WARPS, M6_WARPS * 6 * R6_GROUP_WORDS * 4, ctx->stream>>>(src, T, R, To, o, tot);
+      k_reduce6<M6_WARPS><<<blk, 32 * M6_WARPS, M6_WARPS * 6 * R6_GROUP_WORDS * 4, ctx->stream>>>(src, T, R, To, dst, tot);
       LAUNCHED(ctx);
       Fq12* t = src;
       src = dst;
@@ -276,11 +447,11 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
     }
   }
   if (!with_final_exp) {
-    if (b.wps == 1) CU(cudaMemcpyAsync(out, bufA, (size_t)nseg * sizeof(Fq12), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(out, src, (size_t)nseg * sizeof(Fq12), cudaMemcpyDeviceToDevice, ctx->stream));
     return RIPP_OK;
   }
   TimeScope ts2_(ctx, RIPP_T_FINAL_EXP);
-  k_final_exp6<<<(nseg + 9) / 10, 64, 2 * 6 * FE_GROUP_WORDS * 4, ctx->stream>>>(src, T, (Fq12*)out, nseg);
+  k_final_exp18<<<nseg, 32, FE18_GROUP_WORDS * 4, ctx->stream>>>(src, T, (Fq12*)out);
   LAUNCHED(ctx);
   return RIPP_OK;
 }
@@ -289,7 +460,10 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
 int ripp_final_exp_l6(ripp_ctx* ctx, const void* in, uint32_t T, void* out, int nseg) {
   CU(cudaSetDevice(ctx->device));
   TimeScope ts_(ctx, RIPP_T_FINAL_EXP);
-  k_final_exp6<<<(nseg + 9) / 10, 64, 2 * 6 * FE_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, T, (Fq12*)out, nseg);
+  if ((size_t)nseg <= l18_max_warps())
+    k_final_exp18<<<nseg, 32, FE18_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, T, (Fq12*)out);
+  else
+    k_final_exp6<<<(nseg + 9) / 10, 64, 2 * 6 * FE_GROUP_WORDS * 4, ctx->stream>>>((const Fq12*)in, T, (Fq12*)out, nseg);
   LAUNCHED(ctx);
   return RIPP_OK;
 }

@@ -54,12 +54,6 @@ def hostsim():
 
 
 @pytest.fixture(scope="session")
-def hostsim_shared_code():
-    """The device headers with the opt-in single-copy multiply-accumulate engine (l6.cuh: -DRIPP_L6_SHARED_CODE)."""
-    return _build_hostsim(["-DRIPP_L6_SHARED_CODE"])
-
-
-@pytest.fixture(scope="session")
 def ctx():
     from ripp_b200 import _lib
 

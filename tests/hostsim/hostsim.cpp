@@ -5,6 +5,7 @@
 #define RIPP_HOSTSIM 1
 #include "../../ripp_b200/csrc/l6.cuh"
 #include "../../ripp_b200/csrc/x3.cuh"
+#include "../../ripp_b200/csrc/xt.cuh"
 #include "../../ripp_b200/csrc/endo.cuh"
 #include <pthread.h>
 #include <thread>
@@ -89,28 +90,35 @@ void host_barrier(void* bar) { pthread_barrier_wait((pthread_barrier_t*)bar); }
 }}
 static inline int tower_slot(int k) { return (k & 1) * 3 + (k >> 1); }
 
-template <class Fn>
+// W lanes per coefficient: 6 (W = 1) or 18 (W = 3) host threads per group
+template <int W, class Fn>
 static void run_group(Fn fn, int nreg = 8) {
-  std::vector<uint32_t> sm(l6::group_words(nreg, 4), 0);
+  std::vector<uint32_t> sm(l6::group_words(nreg, 4) + 2 * l6::BUS_WORDS, 0);
   pthread_barrier_t bar;
-  pthread_barrier_init(&bar, nullptr, 6);
+  pthread_barrier_init(&bar, nullptr, 6 * W);
   std::vector<std::thread> th;
-  for (int k = 0; k < 6; k++) th.emplace_back([&, k] { l6::Ctx c{k, sm.data(), &bar}; fn(c); });
+  for (int t = 0; t < 6 * W; t++)
+    th.emplace_back([&, t] {
+      l6::CtxT<W> c{t / W, sm.data(), &bar, t % W, sm.data() + l6::group_words(nreg, 4), 0};
+      fn(c);
+    });
   for (auto& t : th) t.join();
   pthread_barrier_destroy(&bar);
 }
-static void l6_load_reg(const l6::Ctx& c, int reg, const uint32_t* fq12_tower) {
+template <class C>
+static void l6_load_reg(const C& c, int reg, const uint32_t* fq12_tower) {
   l6::st2(l6::freg(c, reg) + c.k * l6::FQ2W, ld<Fq2>(fq12_tower + 24 * tower_slot(c.k)));
   l6::sync(c);
 }
-static void l6_store_reg(const l6::Ctx& c, int reg, uint32_t* fq12_tower) {
-  st<Fq2>(fq12_tower + 24 * tower_slot(c.k), l6::ld2(l6::freg(c, reg) + c.k * l6::FQ2W));
+template <class C>
+static void l6_store_reg(const C& c, int reg, uint32_t* fq12_tower) {
+  if (c.role == 0) st<Fq2>(fq12_tower + 24 * tower_slot(c.k), l6::ld2(l6::freg(c, reg) + c.k * l6::FQ2W));
   l6::sync(c);
 }
-extern "C" {
-// op: 0 mul, 1 sqr, 2 conj, 3 frob1, 4 frob2, 5 inv, 6 exp_by_x, 7 final_exp
-void hs_l6_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
-  run_group([&](const l6::Ctx& c) {
+// op: 0 mul, 1 sqr, 2 conj, 3 frob1, 4 frob2, 5 inv, 6 exp_by_x, 7 final_exp, 8 cyc_sqr, 9 pow_fr
+template <int W>
+static void l6_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  run_group<W>([&](const l6::CtxT<W>& c) {
     l6_load_reg(c, 0, a);
     l6_load_reg(c, 1, b);
     switch (op) {
@@ -134,8 +142,9 @@ void hs_l6_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
     l6_store_reg(c, 2, r);
   });
 }
-void hs_l6_mul_line(const uint32_t* f, const uint32_t* d0, const uint32_t* d1, const uint32_t* d4, uint32_t* r) {
-  run_group([&](const l6::Ctx& c) {
+template <int W>
+static void l6_mul_line(const uint32_t* f, const uint32_t* d0, const uint32_t* d1, const uint32_t* d4, uint32_t* r) {
+  run_group<W>([&](const l6::CtxT<W>& c) {
     l6_load_reg(c, 0, f);
     if (c.k == 0) {
       l6::st2(c.sm + l6::OFF_LINE, ld<Fq2>(d0));
@@ -148,8 +157,9 @@ void hs_l6_mul_line(const uint32_t* f, const uint32_t* d0, const uint32_t* d1, c
   });
 }
 // Miller loop (+ optional final exponentiation) over npairs pairs sharing one accumulator; valid[j] = 0 masks a pair
-void hs_l6_miller(const uint32_t* p, const uint32_t* q, const int* valid, int npairs, int with_final_exp, uint32_t* r) {
-  run_group([&](const l6::Ctx& c) {
+template <int W>
+static void l6_miller(const uint32_t* p, const uint32_t* q, const int* valid, int npairs, int with_final_exp, uint32_t* r) {
+  run_group<W>([&](const l6::CtxT<W>& c) {
     uint32_t* pairs = c.sm + l6::OFF_F + 8 * l6::F12W;
     if (c.k == 0) {
       for (int j = 0; j < npairs; j++) {
@@ -168,6 +178,13 @@ void hs_l6_miller(const uint32_t* p, const uint32_t* q, const int* valid, int np
     l6_store_reg(c, 0, r);
   });
 }
+extern "C" {
+void hs_l6_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) { l6_op<1>(op, a, b, r); }
+void hs_l18_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) { l6_op<3>(op, a, b, r); }
+void hs_l6_mul_line(const uint32_t* f, const uint32_t* d0, const uint32_t* d1, const uint32_t* d4, uint32_t* r) { l6_mul_line<1>(f, d0, d1, d4, r); }
+void hs_l18_mul_line(const uint32_t* f, const uint32_t* d0, const uint32_t* d1, const uint32_t* d4, uint32_t* r) { l6_mul_line<3>(f, d0, d1, d4, r); }
+void hs_l6_miller(const uint32_t* p, const uint32_t* q, const int* valid, int npairs, int with_final_exp, uint32_t* r) { l6_miller<1>(p, q, valid, npairs, with_final_exp, r); }
+void hs_l18_miller(const uint32_t* p, const uint32_t* q, const int* valid, int npairs, int with_final_exp, uint32_t* r) { l6_miller<3>(p, q, valid, npairs, with_final_exp, r); }
 }
 
 // ---- x3 (three lanes per point): each lane a host thread, gather3 through a shared bus -------------
@@ -236,5 +253,43 @@ void hs_x3_fold(int group, const uint32_t* p, const uint32_t* lo, const uint32_t
       if (r == 0) st(out, o);
     }
   });
+}
+}
+
+// ---- xt (lane teams: 3 lanes per G1 point, 9 per G2 point): each lane a host thread ----------------
+namespace ripp { namespace xt {
+void host_barrier(void* bar) { pthread_barrier_wait((pthread_barrier_t*)bar); }
+}}
+template <class F, class Fn>
+static void run_xt(Fn fn) {
+  constexpr int L = xt::TeamOf<F>::LANES;
+  std::vector<uint32_t> bus(2 * xt::TeamOf<F>::BUS_WORDS + sizeof(Aff<F>), 0);
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, L);
+  std::vector<std::thread> th;
+  for (int t = 0; t < L; t++) th.emplace_back([&, t] { xt::Team tm{t, bus.data(), 0, &bar}; fn(tm); });
+  for (auto& t : th) t.join();
+  pthread_barrier_destroy(&bar);
+}
+extern "C" {
+// out = k * p + lo exactly as k_fold_xt computes it (k = 8 canonical words; group 1 = G1, 2 = G2)
+void hs_xt_endo_fold(int group, const uint32_t* p, const uint32_t* lo, const uint32_t* k, uint32_t* out) {
+  EndoBits c;
+  if (group == 1) endo_decompose<1>(k, c); else endo_decompose<2>(k, c);
+  if (group == 1) {
+    run_xt<Fq>([&](const xt::Team& tm) {
+      Jac<Fq> acc = xt::endo_mul<Fq>(tm, ld<G1Aff>(p), c, tm.bus + 2 * xt::TeamOf<Fq>::BUS_WORDS);
+      acc = xt::madd<Fq>(tm, acc, ld<G1Aff>(lo));
+      G1Aff o = xt::to_affine<Fq>(tm, acc);
+      if (tm.t == 0) st(out, o);
+    });
+  } else {
+    run_xt<Fq2>([&](const xt::Team& tm) {
+      Jac<Fq2> acc = xt::endo_mul<Fq2>(tm, ld<G2Aff>(p), c, tm.bus + 2 * xt::TeamOf<Fq2>::BUS_WORDS);
+      acc = xt::madd<Fq2>(tm, acc, ld<G2Aff>(lo));
+      G2Aff o = xt::to_affine<Fq2>(tm, acc);
+      if (tm.t == 0) st(out, o);
+    });
+  }
 }
 }

@@ -65,6 +65,18 @@ def test_pairing_product_2p16_matches_cpu_oracle(ctx, be):
     assert C.gt_dec(ctx.pairing_ip(np.ascontiguousarray(ja), np.ascontiguousarray(jb))) == be.pairing_product(a, b)
 
 
+@pytest.mark.parametrize("n", [1500, 3000, 6000, 13000])
+def test_pairing_product_engine_shapes_match_cpu_oracle(ctx, be, n):
+    """The sizes at which ripp_pairing_batch_l6 switches shape: eighteen-lane warps with 2 and 4 pairs per accumulator
+    (1185..4736 pairs), the six-lane kernel with 1 pair per group (..11 839) and with 2 (..23 679)."""
+    a, b = _g1(be, "shape-a", n), _g2(be, "shape-b", n)
+    da, db = ctx.to_device(_u32(a)), ctx.to_device(_u32(b))
+    out = ctx.alloc(576)
+    ctx.pairing_ip_dev(da, db, n, out)
+    ctx.sync()
+    assert C.gt_dec(out.download(144)) == be.pairing_product(a, b)
+
+
 @pytest.mark.parametrize("logn", [13, 18])
 def test_msm_g1_matches_cpu_oracle(ctx, be, logn):
     """configs[2] leaf: 2^18 points (window plan c = 13, fat top-window buckets); 8191 = the KZG opening size of 2^12 proofs."""

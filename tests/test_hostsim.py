@@ -130,11 +130,13 @@ def test_op_counts(hostsim):
     assert fexp == bench.FQ_MUL_PER_FINAL_EXP
 
 
-def test_l6_six_lane_fq12(hostsim):
-    """The six-lane Fq12 engine (l6.cuh), each lane a host thread, against the oracle."""
+@pytest.mark.parametrize("eng", ["l6", "l18"])
+def test_l6_six_lane_fq12(hostsim, eng):
+    """The Fq12 engine of l6.cuh against the oracle, each lane a host thread: six lanes (W = 1, one lane per Fq2
+    coefficient) and eighteen (W = 3, three Karatsuba roles per coefficient exchanging through the bus)."""
     a, b = rf12(), rf12()
     ea, eb = C.gt_enc(a), C.gt_enc(b)
-    op = lambda code, x, y: C.gt_dec(hostsim.call("hs_l6_op", code, x, y, out=144))
+    op = lambda code, x, y: C.gt_dec(hostsim.call("hs_%s_op" % eng, code, x, y, out=144))
     assert op(0, ea, eb) == E.f12_mul(a, b)
     assert op(1, ea, eb) == E.f12_sqr(a)
     assert op(2, ea, eb) == E.f12_conj(a)
@@ -142,7 +144,7 @@ def test_l6_six_lane_fq12(hostsim):
     assert op(4, ea, eb) == E.f12_frob(a, 2)
     assert op(5, ea, eb) == E.f12_inv(a)
     d0, d1, d4 = rf2(), rf2(), rf2()
-    got = hostsim.call("hs_l6_mul_line", ea, C.fq2_enc(d0), C.fq2_enc(d1), C.fq2_enc(d4), out=144)
+    got = hostsim.call("hs_%s_mul_line" % eng, ea, C.fq2_enc(d0), C.fq2_enc(d1), C.fq2_enc(d4), out=144)
     assert C.gt_dec(got) == E.f12_mul(a, (d0, (0, 0), d1, d4, (0, 0), (0, 0)))
     c = E.f12_mul(E.f12_conj(a), E.f12_inv(a))
     c = E.f12_mul(E.f12_frob(c, 2), c)
@@ -158,21 +160,22 @@ def test_l6_six_lane_fq12(hostsim):
         assert op(9, ea, ew) == E.f12_pow(a, e)
 
 
-def test_l6_miller_and_final_exp(hostsim):
+@pytest.mark.parametrize("eng", ["l6", "l18"])
+def test_l6_miller_and_final_exp(hostsim, eng):
     p, q = E.g1_mul(E.G1_GEN, 123), E.g2_mul(E.G2_GEN, 456)
     f = E.miller_loop(p, q)
     ef = C.gt_enc(f)
-    assert C.gt_dec(hostsim.call("hs_l6_op", 7, ef, ef, out=144)) == E.final_exponentiation(f)
+    assert C.gt_dec(hostsim.call("hs_%s_op" % eng, 7, ef, ef, out=144)) == E.final_exponentiation(f)
     import numpy as np
 
     one = np.array([1], dtype=np.int32)
-    got = hostsim.call("hs_l6_miller", C.g1_enc(p), C.g2_enc(q), one.view(np.uint32), 1, 1, out=144)
+    got = hostsim.call("hs_%s_miller" % eng, C.g1_enc(p), C.g2_enc(q), one.view(np.uint32), 1, 1, out=144)
     assert C.gt_dec(got) == E.pairing(p, q)
     # three pairs sharing one accumulator, the middle one masked (contributes 1)
     ps = [E.g1_mul(E.G1_GEN, s) for s in (5, 6, 7)]
     qs = [E.g2_mul(E.G2_GEN, s) for s in (8, 9, 10)]
     valid = np.array([1, 0, 1], dtype=np.int32)
-    got = hostsim.call("hs_l6_miller", C.g1_vec_enc(ps), C.g2_vec_enc(qs), valid.view(np.uint32), 3, 1, out=144)
+    got = hostsim.call("hs_%s_miller" % eng, C.g1_vec_enc(ps), C.g2_vec_enc(qs), valid.view(np.uint32), 3, 1, out=144)
     assert C.gt_dec(got) == E.multi_pairing([ps[0], ps[2]], [qs[0], qs[2]])
 
 
@@ -236,6 +239,10 @@ def test_x3_three_warp_team_point_arithmetic(hostsim):
         enc, dec, w = (C.g1_enc, C.g1_dec, 24) if group == 1 else (C.g2_enc, C.g2_dec, 48)
         return dec(hostsim.call("hs_x3_endo_fold", group, enc(p), enc(lo), C.scalar_words(k), out=w))
 
+    _check_efold(efold, p1, l1, p2, l2)
+
+
+def _check_efold(efold, p1, l1, p2, l2):
     for k in (rnd.randrange(E.R), rnd.randrange(1 << 128), 1, 0, E.R - 1):
         assert efold(1, p1, l1, k) == E.g1_add(E.g1_mul(p1, k), l1), k
         assert efold(2, p2, l2, k) == E.g2_add(E.g2_mul(p2, k), l2), k
@@ -244,6 +251,19 @@ def test_x3_three_warp_team_point_arithmetic(hostsim):
     assert efold(1, p1, E.g1_mul(p1, k), k) == E.g1_mul(p1, 2 * k) and efold(2, p2, E.g2_mul(p2, k), k) == E.g2_mul(p2, 2 * k)
     assert efold(1, None, l1, k) == l1 and efold(2, None, l2, k) == l2
     assert efold(1, p1, None, k) == E.g1_mul(p1, k) and efold(2, p2, None, k) == E.g2_mul(p2, k)
+
+
+def test_xt_lane_team_folds(hostsim):
+    """xt.cuh: the fold out = k p + lo on a team of 3 lanes (G1) / 9 lanes (G2: 3 product units x 3 Karatsuba roles),
+    level-parallel dbl-2009-l / madd-2007-bl, exceptional cases patched by the complete formulas, team normalisation."""
+    p1, l1 = E.g1_mul(E.G1_GEN, 5), E.g1_mul(E.G1_GEN, 7)
+    p2, l2 = E.g2_mul(E.G2_GEN, 11), E.g2_mul(E.G2_GEN, 13)
+
+    def efold(group, p, lo, k):
+        enc, dec, w = (C.g1_enc, C.g1_dec, 24) if group == 1 else (C.g2_enc, C.g2_dec, 48)
+        return dec(hostsim.call("hs_xt_endo_fold", group, enc(p), enc(lo), C.scalar_words(k), out=w))
+
+    _check_efold(efold, p1, l1, p2, l2)
 
 
 def test_endomorphisms(hostsim):
@@ -263,21 +283,3 @@ def test_endo_scalar_multiplication(hostsim):
         kw = C.scalar_words(k)
         assert C.g1_dec(hostsim.call("hs_g1_endo_mul", C.g1_enc(p), kw, out=24)) == E.g1_mul(p, k), k
         assert C.g2_dec(hostsim.call("hs_g2_endo_mul", C.g2_enc(q), kw, out=48)) == E.g2_mul(q, k), k
-
-
-def test_l6_shared_code_engine(hostsim_shared_code):
-    """The opt-in out-of-line engine (one copy of the multiply-accumulate loop for product / squaring / line product)
-    computes the same values as the inlined one."""
-    hs = hostsim_shared_code
-    a, b = rf12(), rf12()
-    ea, eb = C.gt_enc(a), C.gt_enc(b)
-    op = lambda code, x, y: C.gt_dec(hs.call("hs_l6_op", code, x, y, out=144))
-    assert op(0, ea, eb) == E.f12_mul(a, b)
-    assert op(1, ea, eb) == E.f12_sqr(a)
-    assert op(5, ea, eb) == E.f12_inv(a)
-    d0, d1, d4 = rf2(), rf2(), rf2()
-    got = hs.call("hs_l6_mul_line", ea, C.fq2_enc(d0), C.fq2_enc(d1), C.fq2_enc(d4), out=144)
-    assert C.gt_dec(got) == E.f12_mul(a, (d0, (0, 0), d1, d4, (0, 0), (0, 0)))
-    p, q = E.g1_mul(E.G1_GEN, 321), E.g2_mul(E.G2_GEN, 654)
-    f = E.miller_loop(p, q)
-    assert C.gt_dec(hs.call("hs_l6_op", 7, C.gt_enc(f), C.gt_enc(f), out=144)) == E.final_exponentiation(f)
