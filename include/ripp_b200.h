@@ -36,7 +36,8 @@ typedef enum ripp_status {
   RIPP_ERR_CUDA = -3,
   RIPP_ERR_ARG = -4,
   RIPP_ERR_INNER_PRODUCT = -5, /* InnerProductArgumentError::InnerProductInvalid, ip_proofs/src/lib.rs:22-25 */
-  RIPP_ERR_NO_DEVICE = -6
+  RIPP_ERR_NO_DEVICE = -6,
+  RIPP_ERR_NCCL = -7          /* NCCL could not be loaded, or a collective failed */
 } ripp_status;
 
 typedef struct ripp_ctx ripp_ctx;
@@ -134,6 +135,26 @@ int ripp_fr_fold_dev(ripp_ctx* ctx, const void* hi_dev, const void* lo_dev, cons
 int ripp_g1_scale_dev(ripp_ctx* ctx, const void* g1_aff_dev, const void* fr_dev, size_t n, void* g1_aff_out_dev);
 int ripp_g2_scale_dev(ripp_ctx* ctx, const void* g2_aff_dev, const void* fr_dev, size_t n, void* g2_aff_out_dev);
 
+/* ---- setup ----------------------------------------------------------- */
+/* The random draws of the reference's setups (Fr::rand / G::rand on the caller's Rng) stay with the caller; these
+ * entry points take the exponents, so the Rust shim keeps arkworks' own random stream (INTEGRATION.md "setup").
+ *
+ * ark-ec FixedBase::msm over ONE base as structured_generators_scalar_power uses it (tipa/mod.rs:384-389):
+ * out[i] = s[i] * base.  base: one affine point (host, Montgomery) or NULL for the standard generator; s: n Fr
+ * (device, Montgomery); out: n affine points (device).  With s[i] drawn by the caller this is also the key vector
+ * of random_generators (dh_commitments/src/lib.rs:59-61) for the synthetic keys of SURVEY.md §8d. */
+int ripp_fixed_base_msm_g1_dev(ripp_ctx* ctx, const void* base_g1_aff, const void* fr_dev, size_t n, void* g1_aff_out_dev);
+int ripp_fixed_base_msm_g2_dev(ripp_ctx* ctx, const void* base_g2_aff, const void* fr_dev, size_t n, void* g2_aff_out_dev);
+/* structured_generators_scalar_power (tipa/mod.rs:372-391): out[i] = s^i * base, i < num (num > 0 as :377 asserts).
+ * s: one Fr (host, Montgomery). */
+int ripp_structured_generators_g1_dev(ripp_ctx* ctx, const void* base_g1_aff, const void* s, size_t num, void* g1_aff_out_dev);
+int ripp_structured_generators_g2_dev(ripp_ctx* ctx, const void* base_g2_aff, const void* s, size_t num, void* g2_aff_out_dev);
+/* TIPA::setup (tipa/mod.rs:150-164) for given trapdoors alpha, beta (host Fr, Montgomery): the 2 size - 1 powers
+ * g^(alpha^i) and h^(beta^i) stay on the device (they are the long-lived SRS of the provers above), g^beta and
+ * h^alpha (the rest of VerifierSRS, tipa/mod.rs:120-127) come back to the host as affine points. */
+int ripp_tipa_setup_dev(ripp_ctx* ctx, const void* alpha, const void* beta, size_t size, void* srs_g1_out_dev,
+                        void* srs_g2_out_dev, void* g_beta_out, void* h_alpha_out);
+
 /* ---- L3: device-resident provers ------------------------------------------------------------ */
 /* Instantiations of GIPA<IP, LMC, RMC, IPC, Blake2b> (ip_proofs/src/gipa.rs:16-22); element types of
  * (left message A, right message B, left key v, right key w): */
@@ -159,6 +180,15 @@ typedef enum ripp_gipa_kind {
 int ripp_gipa_prove_dev(ripp_ctx* ctx, int kind, const void* a_dev, const void* b_dev, const void* v_dev,
                         const void* w_dev, size_t n, uint8_t* proof_out, size_t proof_cap, size_t* proof_len,
                         void* transcript_out, uint8_t* ck_base_out, size_t ck_cap, size_t* ck_len);
+
+/* GIPA::prove (gipa.rs:108-133), the CHECKED entry: recomputes IP(l, r), LMC::commit(ck_a, l) and RMC::commit(ck_b, r)
+ * on the device and compares them with the caller's statement before proving.  `com` is the statement in the
+ * verifier's layout (see ripp_gipa_verify_dev): com_a || com_b || com_t, no com_b for the *_SSM kinds.
+ * RIPP_ERR_INNER_PRODUCT = InnerProductArgumentError::InnerProductInvalid (wrong inner product, or a commitment
+ * that does not open to the message); RIPP_ERR_NOT_POW2 = MessageLengthInvalid -- checked in the reference's order. */
+int ripp_gipa_prove_checked_dev(ripp_ctx* ctx, int kind, const void* a_dev, const void* b_dev, const void* v_dev,
+                                const void* w_dev, size_t n, const uint8_t* com, size_t com_len, uint8_t* proof_out,
+                                size_t proof_cap, size_t* proof_len);
 
 /* The same prover continuing a transcript: prev_challenge (one Fr, host, Montgomery) is the challenge of the round
  * before the first one proved here (NULL = fresh transcript, i.e. ripp_gipa_prove_dev).  A sharded prover
@@ -216,6 +246,49 @@ int ripp_sipp_product_with_coeffs(ripp_ctx* ctx, const void* a_aff, const void* 
  * log2(n) pairs (z_l, z_r) in serialize_uncompressed form (Proof::gt_elems, lib.rs:32-34). */
 int ripp_sipp_prove(ripp_ctx* ctx, const void* a_aff, const void* b_aff, const void* r, size_t n,
                     const void* value_gt, uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink inside the library ------------------- */
+/* The reference is single-host rayon; this is what a host behind its traits calls to span the GPUs of one box.
+ * Bootstrap as NCCL itself: rank 0 calls ripp_comm_unique_id and hands the 128 bytes to every rank through whatever
+ * channel the host has (MPI, a torch.distributed store, a file); every rank then calls ripp_comm_init on its
+ * top-level context.  world must be a power of two.  NCCL is loaded at run time (libnccl.so.2; RIPP_B200_NCCL_LIB
+ * overrides), so single-GPU users never need it.  All collectives run on the context's stream. */
+int ripp_comm_unique_id(uint8_t* id128_out);
+int ripp_comm_init(ripp_ctx* ctx, const uint8_t* id128, int rank, int world);
+int ripp_comm_info(ripp_ctx* ctx, int* rank, int* world);
+int ripp_comm_destroy(ripp_ctx* ctx);
+/* all-gather of one `bytes`-sized device blob per rank (recv_dev: world * bytes, rank order) */
+int ripp_all_gather_dev(ripp_ctx* ctx, const void* send_dev, size_t bytes, void* recv_dev);
+
+/* Leaf inner products of ONE instance whose inputs are sharded by CONTIGUOUS slices (cfg_multi_pairing's chunks,
+ * inner_products/src/lib.rs:91-113, spread over GPUs instead of threads): every rank computes the partial of its
+ * slice (Miller value before the final exponentiation / one point), ONE all-gather of 576 / 96 / 192 bytes per
+ * rank, combination in rank order and (pairing) one final exponentiation on every rank.  Same result on all ranks,
+ * bit-identical to the single-GPU entry points. */
+int ripp_pairing_ip_sharded_dev(ripp_ctx* ctx, const void* g1_slice_dev, const void* g2_slice_dev, size_t n_local,
+                                void* gt_out_dev);
+int ripp_msm_g1_sharded_dev(ripp_ctx* ctx, const void* g1_slice_dev, const void* fr_slice_dev, size_t n_local,
+                            void* g1_aff_out_dev);
+int ripp_msm_g2_sharded_dev(ripp_ctx* ctx, const void* g2_slice_dev, const void* fr_slice_dev, size_t n_local,
+                            void* g2_aff_out_dev);
+
+/* GIPA::prove_with_aux (gipa.rs:162-312) for ONE instance whose four vectors are partitioned CYCLICALLY: rank k holds
+ * global indices j * world + k at local index j (n_local = n / world elements, a power of two).  Rounds run
+ * partitioned -- local products and folds, one all-gather of six partials per round -- while the global length exceeds
+ * tail_len (0 = default 2^12); the rest is gathered once and finished by the resident prover on every rank.  Outputs as
+ * ripp_gipa_prove_dev, identical on all ranks and to one GPU. */
+int ripp_gipa_prove_sharded_dev(ripp_ctx* ctx, int kind, const void* a_dev, const void* b_dev, const void* v_dev,
+                                const void* w_dev, size_t n_local, size_t tail_len, uint8_t* proof_out, size_t proof_cap,
+                                size_t* proof_len, void* transcript_out, uint8_t* ck_base_out, size_t ck_cap, size_t* ck_len);
+
+/* aggregate_proofs (groth16_aggregation.rs:77-160) for ONE batch of n_total proofs partitioned cyclically over the
+ * ranks: a, b, c are this rank's shares (n_total / world elements); the SRS (2 n_total - 1 powers each) is resident
+ * in full on every rank.  The two TIPA recursions advance in lock step (one all-gather of twelve partials per
+ * round), their latency-bound tails finish concurrently, the KZG opening MSMs are sharded by contiguous slices of the
+ * SRS powers.  Output: the AggregateProof bytes ripp_tipp_aggregate_dev emits, on every rank. */
+int ripp_tipp_aggregate_sharded_dev(ripp_ctx* ctx, const void* srs_g1_dev, const void* srs_g2_dev, const void* a_dev,
+                                    const void* b_dev, const void* c_dev, size_t n_total, size_t tail_len,
+                                    uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 
 /* ---- verifiers ----------------------------------------- */
 /* All arithmetic of the verifiers runs on the GPU (GT multi-exponentiation, MSMs, pairings); the host

@@ -15,6 +15,7 @@ RIPP_ERR_CUDA = -3
 RIPP_ERR_ARG = -4
 RIPP_ERR_INNER_PRODUCT = -5
 RIPP_ERR_NO_DEVICE = -6
+RIPP_ERR_NCCL = -7
 
 TEST_OPS = [
     "FQ_MUL", "FQ_ADD", "FQ_SUB", "FQ_INV", "FQ_HALF",
@@ -102,9 +103,11 @@ class DeviceBuffer:
         return out
 
     def free(self):
-        if self.ptr:
+        # a buffer that outlives its context (interpreter shutdown, a traceback holding a reference) has nothing left to
+        # free: ripp_ctx_destroy released the device and ripp_dev_free on a destroyed context would read freed memory
+        if self.ptr and self.ctx.handle:
             check(lib().ripp_dev_free(self.ctx.handle, _p(self.ptr)))
-            self.ptr = None
+        self.ptr = None
 
     def __del__(self):
         try:
@@ -230,6 +233,37 @@ class Context:
                                         ctypes.c_size_t(cap), ctypes.byref(plen), _p(tr), _p(ck), ctypes.c_size_t(1024),
                                         ctypes.byref(cklen)))
         return proof[: plen.value].tobytes(), tr, ck[: cklen.value].tobytes()
+
+    def gipa_prove_checked_dev(self, kind, a, b, v, w, n, com):
+        """GIPA::prove (gipa.rs:108-133): the statement `com` (bytes) is checked against the vectors first.  -> proof bytes"""
+        k = max(n.bit_length() - 1, 0)
+        cap = 64 + k * 6 * 600 + 2 * 600
+        proof = np.empty(cap, dtype=np.uint8)
+        plen = ctypes.c_size_t()
+        cb = self._bytes(com)
+        check(lib().ripp_gipa_prove_checked_dev(self.handle, int(kind), _p(a), _p(b), _p(v), _p(w), ctypes.c_size_t(n), _p(cb),
+                                                ctypes.c_size_t(len(cb)), _p(proof), ctypes.c_size_t(cap), ctypes.byref(plen)))
+        return proof[: plen.value].tobytes()
+
+    # ---- setup --------------------------------------------------------------------------------
+    def fixed_base_msm_dev(self, group, base, fr_dev, n, out_dev):
+        """out[i] = s[i] * base (base: packed affine words or None = generator)."""
+        fn = lib().ripp_fixed_base_msm_g1_dev if group == 1 else lib().ripp_fixed_base_msm_g2_dev
+        check(fn(self.handle, _p(base), _p(fr_dev), ctypes.c_size_t(n), _p(out_dev)))
+
+    def structured_generators_dev(self, group, base, s, num, out_dev):
+        """structured_generators_scalar_power (tipa/mod.rs:372-391): out[i] = s^i * base."""
+        fn = lib().ripp_structured_generators_g1_dev if group == 1 else lib().ripp_structured_generators_g2_dev
+        check(fn(self.handle, _p(base), _p(s), ctypes.c_size_t(num), _p(out_dev)))
+
+    def tipa_setup_dev(self, alpha, beta, size):
+        """TIPA::setup (tipa/mod.rs:150-164) for given trapdoors ((8,) uint32 Montgomery each).
+        -> (srs_g1 DeviceBuffer, srs_g2 DeviceBuffer, g_beta words, h_alpha words)"""
+        m = 2 * size - 1
+        s1, s2 = self.alloc(m * 96), self.alloc(m * 192)
+        gb, ha = np.zeros(24, dtype=np.uint32), np.zeros(48, dtype=np.uint32)
+        check(lib().ripp_tipa_setup_dev(self.handle, _p(alpha), _p(beta), ctypes.c_size_t(size), _p(s1), _p(s2), _p(gb), _p(ha)))
+        return s1, s2, gb, ha
 
     def gipa_prove_resume_dev(self, kind, a, b, v, w, n, prev_challenge):
         """As gipa_prove_dev, continuing a transcript whose last challenge is prev_challenge ((8,) uint32 Montgomery)."""

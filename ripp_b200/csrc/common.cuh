@@ -17,7 +17,7 @@ using namespace ripp;
 // ------------------------------------------------------------------------------------------------
 std::string& ripp_err_slot();
 
-#define RIPP_SCRATCH_SLOTS 24
+#define RIPP_SCRATCH_SLOTS 32
 #define RIPP_MAX_BATCH 8
 #define RIPP_MAX_CHILD 8
 // per-category device-time accounting (CUDA events on the context's stream; off by default)
@@ -41,7 +41,14 @@ struct ripp_ctx {
   // scratch (grown on demand)
   void* scratch[RIPP_SCRATCH_SLOTS];
   size_t scratch_bytes[RIPP_SCRATCH_SLOTS];
+  // page-locked host staging for the small per-round results (a pageable cudaMemcpyAsync goes through the driver's
+  // own staging buffer and blocks the calling thread)
+  uint8_t* pinned;
+  // multi-GPU (comm.cu): one process per GPU, an NCCL communicator owned by the top-level context
+  void* comm;  // ncclComm_t
+  int rank, world;
 };
+#define RIPP_PINNED_BYTES 16384
 
 static inline int fail(int code, const std::string& msg) {
   ripp_err_slot() = msg;
@@ -78,6 +85,12 @@ static inline int scratch(ripp_ctx* ctx, int slot, size_t bytes, void** out) {
 }
 
 
+static inline int pinned(ripp_ctx* ctx, uint8_t** out) {
+  if (!ctx->pinned) CU(cudaHostAlloc((void**)&ctx->pinned, RIPP_PINNED_BYTES, cudaHostAllocDefault));
+  *out = ctx->pinned;
+  return RIPP_OK;
+}
+
 struct TimeScope {
   ripp_ctx* c;
   long idx;
@@ -106,4 +119,7 @@ int ripp_final_exp_l6(ripp_ctx* ctx, const void* in, uint32_t T, void* out, int 
 int ripp_gt_multiexp_l6(ripp_ctx* ctx, const void* in, const void* sc, size_t n, void* out);
 int ripp_gt_check_l6(ripp_ctx* ctx, const void* in, size_t n, uint32_t* bad_dev, uint32_t flag);
 bool ripp_use_l6();
+// comm.cu: all-gather of one `bytes`-sized blob per rank on ctx's stream (recv = world * bytes, rank order); world == 1 copies
+int ripp_all_gather_internal(ripp_ctx* ctx, const void* send_dev, size_t bytes, void* recv_dev);
+void ripp_comm_release(ripp_ctx* ctx);
 int ripp_pairing6_init_device();  // per-device kernel attributes; called by ripp_ctx_create with the device current

@@ -282,7 +282,7 @@ RIPP_HD uint32_t* freg(const C& c, int r) { return c.sm + OFF_F + r * F12W; }
 // ---- Fq12 ops on smem registers (collective: all lanes of the group call with the same arguments) ---------
 // D = A * B on raw coefficient arrays (6 x Fq2, flat w-basis); D may alias A or B
 template <class C>
-RIPP_HD void mul_p(const C& c, uint32_t* D, const uint32_t* A, const uint32_t* B) {
+RIPP_HD void mul_p_body(const C& c, uint32_t* D, const uint32_t* A, const uint32_t* B) {
   typename AccOf<C>::type acc;
   acc_zero(acc);
 #pragma unroll 1
@@ -298,12 +298,22 @@ RIPP_HD void mul_p(const C& c, uint32_t* D, const uint32_t* A, const uint32_t* B
   st2(D + c.k * FQ2W, out);
   sync(c);
 }
+#if defined(__CUDA_ARCH__) && defined(RIPP_L6_CALL_W3)
+static __device__ __noinline__ void mul_p_w3(const CtxT<3>& c, uint32_t* D, const uint32_t* A, const uint32_t* B) { mul_p_body(c, D, A, B); }
+template <class C>
+RIPP_HD void mul_p(const C& c, uint32_t* D, const uint32_t* A, const uint32_t* B) {
+  if constexpr (C::W == 3) mul_p_w3(c, D, A, B); else mul_p_body(c, D, A, B);
+}
+#else
+template <class C>
+RIPP_HD void mul_p(const C& c, uint32_t* D, const uint32_t* A, const uint32_t* B) { mul_p_body(c, D, A, B); }
+#endif
 // dst = a * b;  dst may alias a or b
 template <class C>
 RIPP_HD void mul(const C& c, int dst, int a, int b) { mul_p(c, freg(c, dst), freg(c, a), freg(c, b)); }
 // dst = a^2: 21 distinct products over six coefficients (cross terms doubled)
 template <class C>
-RIPP_HD void sqr(const C& c, int dst, int a) {
+RIPP_HD void sqr_body(const C& c, int dst, int a) {
   const uint32_t* A = freg(c, a);
   typename AccOf<C>::type acc;
   acc_zero(acc);
@@ -339,7 +349,7 @@ RIPP_HD void sqr(const C& c, int dst, int a) {
 }
 // dst = a * (d0 + d1 w^2 + d4 w^3), line coefficients at OFF_LINE (the ark-ec `mul_by_014` shape)
 template <class C>
-RIPP_HD void mul_line(const C& c, int dst, int a) {
+RIPP_HD void mul_line_body(const C& c, int dst, int a) {
   const uint32_t* A = freg(c, a);
   const uint32_t* L = c.sm + OFF_LINE;
   int k = c.k;
@@ -426,7 +436,7 @@ RIPP_HD void inv(const C& c, int dst, int a, int t0, int t1, int t2) {
 // the outputs are  a0' = 3 t_even(A) - 2 a0,  a3' = 3 t_odd(A) + 2 a3,  a1' = 3 xi t_odd(C) + 2 a1,
 // a4' = 3 t_even(C) - 2 a4,  a2' = 3 t_even(B) - 2 a2,  a5' = 3 t_odd(B) + 2 a5   (A, B, C = pairs 0, 1, 2).
 template <class C>
-RIPP_HD void cyc_sqr(const C& c, int dst, int a) {
+RIPP_HD void cyc_sqr_body(const C& c, int dst, int a) {
   const uint32_t* A = freg(c, a);
   uint32_t* R = c.sm + OFF_R;
   const int k = c.k, pr = k % 3;
@@ -450,6 +460,26 @@ RIPP_HD void cyc_sqr(const C& c, int dst, int a) {
   st2(freg(c, dst) + k * FQ2W, out);
   sync(c);
 }
+
+// -DRIPP_L6_CALL_W3: the eighteen-lane shape's Fq12 operations as real calls (one copy each) instead of inlined.  ncu
+// shows 14 % of k_final_exp18's stall samples as "no instruction" (30 k instructions inlined), but the calls measured
+// no better: final exponentiation 1.39 -> 1.44 ms, k_miller18<1> 1.12 -> 1.21 ms (gpurun_out r2g).  Kept for A/B runs.
+#if defined(__CUDA_ARCH__) && defined(RIPP_L6_CALL_W3)
+#define RIPP_L6_OP(name, params, args)                                                              \
+  static __device__ __noinline__ void name##_w3(const Ctx3& c, params) { name##_body(c, args); }    \
+  template <class C>                                                                                \
+  RIPP_HD void name(const C& c, params) {                                                           \
+    if constexpr (C::W == 3) name##_w3(c, args); else name##_body(c, args);                         \
+  }
+#else
+#define RIPP_L6_OP(name, params, args) \
+  template <class C>                   \
+  RIPP_HD void name(const C& c, params) { name##_body(c, args); }
+#endif
+#define RIPP_L6_COMMA ,
+RIPP_L6_OP(sqr, int dst RIPP_L6_COMMA int a, dst RIPP_L6_COMMA a)
+RIPP_L6_OP(mul_line, int dst RIPP_L6_COMMA int a, dst RIPP_L6_COMMA a)
+RIPP_L6_OP(cyc_sqr, int dst RIPP_L6_COMMA int a, dst RIPP_L6_COMMA a)
 
 // a^x (x = -|x|) for a in the cyclotomic subgroup; dst != a; clobbers nothing else
 template <class C>

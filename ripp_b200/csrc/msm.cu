@@ -27,6 +27,7 @@ struct MsmPlan {
   uint32_t T;  // chunks per window
 };
 
+#define MSM_SMALL_N ((size_t)1 << 16)
 static MsmPlan msm_plan(size_t n, int bits = 255) {
   int lg = 0;
   while (((size_t)2 << lg) <= n) lg++;
@@ -37,8 +38,10 @@ static MsmPlan msm_plan(size_t n, int bits = 255) {
     const char* e = getenv("RIPP_B200_MSM_SHIFT");
     return e ? atoi(e) : 5;
   }();
-  p.c = lg - shift;
-  if (p.c < 4) p.c = 4;
+  // short inputs (the KZG openings and the MSM-type products of the GIPA rounds) are latency chains on an empty GPU:
+  // ~4 points per bucket keeps the per-bucket chain short; below 2^6 points the window only sets the Horner tail
+  p.c = lg - (n <= MSM_SMALL_N ? 2 : shift);
+  if (p.c < (n <= MSM_SMALL_N ? 6 : 4)) p.c = n <= MSM_SMALL_N ? 6 : 4;
   if (p.c > 16) p.c = 16;
   p.nw = (bits + p.c - 1) / p.c;
   p.B = 1u << p.c;
@@ -266,6 +269,46 @@ __global__ void __maxnreg__(255) k_msm_horner_x3(const Jac<XF>* __restrict__ sum
   Aff<XF> o = x3::to_affine(acc);
   if (threadIdx.x == 0) *out = o;
 }
+// Horner tail on lane teams (xt.cuh): phase 1, team w brings window sum w to affine form (one inversion each, all windows
+// in parallel) into shared memory; phase 2, the first team of warp 0 walks the (nw - 1) c doublings with mixed additions.
+// 115 doublings of a G1 tail: 1.19 ms on a three-warp team (k_msm_horner_x3, CTA barriers) -> lanes of one warp.
+template <class F>
+__global__ void __launch_bounds__(32 * 9) k_msm_horner_xt(const Jac<F>* __restrict__ sums, int nw, int c, Aff<F>* __restrict__ out) {
+  typedef xt::TeamOf<F> TO;
+  constexpr int AW = sizeof(Aff<F>) / 4;
+  extern __shared__ __align__(16) uint32_t hsm[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* aff = hsm;                                        // nw affine window sums
+  uint32_t* bus = hsm + ((nw * AW + 3) & ~3);                 // per team: 2 bus buffers
+  const int vl = lane % (TO::LANES * TO::PER_WARP), e = vl / TO::LANES;
+  xt::Team tm{vl % TO::LANES, bus + (warp * TO::PER_WARP + e) * 2 * TO::BUS_WORDS, 0, nullptr};
+  for (int w0 = 0; w0 < nw; w0 += warps * TO::PER_WARP) {  // warp-uniform trip count
+    int w = w0 + warp * TO::PER_WARP + e;
+    const bool live = w < nw && lane == vl;
+    if (w >= nw) w = nw - 1;
+    Aff<F> a = xt::to_affine<F>(tm, sums[w]);
+    if (live && tm.t == 0) xt::aff_st<F>(aff + w * AW, a);
+  }
+  __syncthreads();
+  if (warp) return;
+  Jac<F> acc = Jac<F>::from_affine(xt::aff_ld<F>(aff + (nw - 1) * AW));
+#pragma unroll 1
+  for (int w = nw - 2; w >= 0; w--) {
+#pragma unroll 1
+    for (int j = 0; j < c; j++) acc = xt::dbl<F>(tm, acc);
+    acc = xt::madd<F>(tm, acc, xt::aff_ld<F>(aff + w * AW));
+  }
+  Aff<F> o = xt::to_affine<F>(tm, acc);
+  if (threadIdx.x == 0) *out = o;
+}
+template <class F>
+static size_t horner_xt_smem(int nw) {
+  typedef xt::TeamOf<F> TO;
+  int warps = (nw + TO::PER_WARP - 1) / TO::PER_WARP;
+  if (warps > 9) warps = 9;
+  return (size_t)4 * (((nw * (sizeof(Aff<F>) / 4) + 3) & ~3) + warps * TO::PER_WARP * 2 * TO::BUS_WORDS);
+}
+
 template <class F> struct X3Of;
 template <> struct X3Of<Fq> { typedef Fq type; };
 template <> struct X3Of<Fq2> { typedef x3::Fq2x3 type; };
@@ -329,7 +372,8 @@ static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, 
   uint32_t* cursor = offsets + WB;
   cudaStream_t st = ctx->stream;
   // fat-bucket bookkeeping: at most nw*n/MSM_FAT fat buckets, nw*(n/CHUNK + n/FAT) chunk items
-  uint32_t max_fat = (uint32_t)((size_t)p.nw * n / MSM_FAT + p.nw + 1);
+  const uint32_t fat_min = n <= MSM_SMALL_N ? 16u : MSM_FAT;
+  uint32_t max_fat = (uint32_t)((size_t)p.nw * n / fat_min + p.nw + 1);
   uint32_t max_items = (uint32_t)((size_t)p.nw * n / MSM_FAT_CHUNK + max_fat + 1);
   void* fatbuf;
   OK(scratch(ctx, 15, 64 + (size_t)max_items * (sizeof(FatItem) + sizeof(Jac<F>)) + (size_t)max_fat * sizeof(FatBucket) + 1024, &fatbuf));
@@ -343,7 +387,7 @@ static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, 
   LAUNCHED(ctx);
   // "fat" = far above the mean bucket size (and never below MSM_FAT points)
   uint32_t fat_threshold = (uint32_t)(4 * (n >> p.c));
-  if (fat_threshold < MSM_FAT) fat_threshold = MSM_FAT;
+  if (fat_threshold < fat_min) fat_threshold = fat_min;
   k_msm_scan<<<p.nw, 256, 0, st>>>(counts, offsets, cursor, p.B, n, fat_counters, fat_items, fat_buckets, max_items,
                                    fat_threshold);
   LAUNCHED(ctx);
@@ -377,7 +421,12 @@ static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, 
     pb = t;
     T = To;
   }
-  if (fold_mode() <= 1) {
+  if (fold_mode() == 0) {
+    typedef xt::TeamOf<F> TO;
+    int warps = (p.nw + TO::PER_WARP - 1) / TO::PER_WARP;
+    if (warps > 9) warps = 9;
+    k_msm_horner_xt<F><<<1, 32 * warps, horner_xt_smem<F>(p.nw), st>>>(pa, p.nw, p.c, out);
+  } else if (fold_mode() == 1) {
     typedef typename X3Of<F>::type XF;
     k_msm_horner_x3<XF><<<1, 96, 0, st>>>((const Jac<XF>*)pa, p.nw, p.c, (Aff<XF>*)out);
   } else {

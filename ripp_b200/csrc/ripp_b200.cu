@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "x3.cuh"
 #include "endo.cuh"
+#include "xt.cuh"
 
 static thread_local std::string g_err;
 std::string& ripp_err_slot() { return g_err; }
@@ -20,6 +21,7 @@ extern "C" int ripp_ctx_create(int device, ripp_ctx** out) {
   ripp_ctx* c = new ripp_ctx();
   memset(c, 0, sizeof(*c));
   c->device = device;
+  c->world = 1;
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   c->recs = new std::vector<TimingRec>();
@@ -56,10 +58,12 @@ extern "C" void ripp_ctx_destroy(ripp_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < RIPP_MAX_CHILD; i++)
     if (ctx->child[i]) ripp_ctx_destroy(ctx->child[i]);
+  ripp_comm_release(ctx);
   cudaEventDestroy(ctx->ev);
   for (int i = 0; i < RIPP_SCRATCH_SLOTS; i++)
     if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   cudaStreamDestroy(ctx->own_stream);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->recs) {
     for (auto& r : *ctx->recs) {
       cudaEventDestroy(r.a);
@@ -227,12 +231,130 @@ __global__ void __launch_bounds__(64, 4) k_scale(const Aff<F>* __restrict__ pts,
   if (live) out[i] = r;
 }
 
+// Short vectors (the 2^12-element scalings a_i r^i / ck_i r^-i of aggregate_proofs were 4096 lone threads, 10.7 ms for G2):
+// one thread per (element, endomorphism part).  s P = sum_t d_t E^t(P) (endo.cuh) is m independent scalar
+// multiplications with 128-bit (G1, m = 2) / 64-bit (G2, m = 4) scalars: m times the parallelism at 1/m of the chain,
+// then one thread per element adds the m parts and normalises.  Lane teams (k_scale_xt below, kept for A/B runs) were
+// measured SLOWER here (8.8 ms): at 1366 warps the redundant glue of nine lanes per element is throughput, not latency.
+template <class F, bool GEN>
+__global__ void __launch_bounds__(64, 4) k_scale_parts(const Aff<F>* __restrict__ pts, const Fr* __restrict__ sc, size_t n, int m,
+                                                    Jac<F>* __restrict__ parts, Aff<F> gen) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // g = t n + i: a warp works on one part index (mostly)
+  const bool live = g < (size_t)m * n;
+  if (!live) g = (size_t)m * n - 1;
+  const int t = (int)(g / n);
+  const size_t i = g % n;
+  Fr s = sc[i].from_mont();
+  uint32_t digits[4][4];
+  int mm;
+  endo_digits<sizeof(F) == sizeof(Fq) ? 1 : 2>(s.v, digits, &mm);
+  Aff<F> p = GEN ? gen : pts[i];
+  {  // E^t(P): the chain of images as endo_mul_simt forms it, then a select (no data-dependent trip count)
+    Aff<F> b1 = endo_map(p), b2 = endo_map(b1), b3 = endo_map(b2);
+    p = t == 0 ? p : (t == 1 ? b1 : (t == 2 ? b2 : b3));
+  }
+  uint32_t d[4], pos[5] = {0, 0, 0, 0, 0}, neg[5] = {0, 0, 0, 0, 0};
+  for (int j = 0; j < 4; j++) d[j] = t == 0 ? digits[0][j] : (t == 1 ? digits[1][j] : (t == 2 ? digits[2][j] : digits[3][j]));
+  int nd = 0;
+  naf_bitmaps(d, 4, pos, neg, &nd);
+  for (int o = 16; o >= 1; o >>= 1) nd = max(nd, __shfl_xor_sync(0xffffffffu, nd, o));
+  nd = min(nd, 160);
+  const Aff<F> np = p.neg();
+  Jac<F> acc = Jac<F>::inf();
+  for (int j = nd - 1; j >= 0; j--) {
+    acc = Jac<F>::dbl_fn(acc);
+    const bool ps = (pos[j >> 5] >> (j & 31)) & 1, ng = (neg[j >> 5] >> (j & 31)) & 1;
+    Aff<F> q = ng ? np : p;
+    if (!(ps || ng)) q = Aff<F>::inf();
+    acc = Jac<F>::add_mixed_fn(acc, q);
+  }
+  if (live) parts[g] = acc;
+}
+template <class F>
+__global__ void __launch_bounds__(64, 4) k_scale_combine(const Jac<F>* __restrict__ parts, size_t n, int m, Aff<F>* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Jac<F> acc = parts[i];
+  for (int t = 1; t < m; t++) acc = acc.add(parts[(size_t)t * n + i]);
+  out[i] = acc.to_affine();
+}
+static size_t scale_parts_max_n() {
+  static const long v = [] {
+    const char* e = getenv("RIPP_B200_SCALE_PARTS_MAX");  // 0 = one thread per element everywhere (A/B runs)
+    return e ? atol(e) : 16384L;
+  }();
+  return (size_t)v;
+}
+
+// Lane teams (xt.cuh: 3 lanes per G1 element, 9 per G2 element) for vectors short enough that one element's dependent
+// chain, not the multiplier pipe, is the cost: the 2^12-element scalings of aggregate_proofs were 4096 lone threads.
+constexpr int SXT_WARPS = 2;
+template <class F, bool GEN>
+__global__ void __launch_bounds__(32 * SXT_WARPS) k_scale_xt(const Aff<F>* __restrict__ pts, const Fr* __restrict__ sc, size_t n,
+                                                            Aff<F>* __restrict__ out, Aff<F> gen) {
+  typedef xt::TeamOf<F> TO;
+  constexpr int AW4 = 4 * sizeof(Aff<F>) / 4;
+  __shared__ __align__(16) uint32_t bus[SXT_WARPS * TO::PER_WARP * (2 * TO::BUS_WORDS + AW4)];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vl = lane % (TO::LANES * TO::PER_WARP);
+  const int e = vl / TO::LANES;
+  size_t i = ((size_t)blockIdx.x * SXT_WARPS + warp) * TO::PER_WARP + e;
+  const bool live = i < n && lane == vl;
+  if (i >= n) i = n - 1;
+  uint32_t* scratch = bus + (warp * TO::PER_WARP + e) * (2 * TO::BUS_WORDS + AW4);
+  xt::Team tm{vl % TO::LANES, scratch, 0, nullptr};
+  Fr s = sc[i].from_mont();
+  EndoBits eb;
+  endo_decompose<sizeof(F) == sizeof(Fq) ? 1 : 2>(s.v, eb);
+  int nb = eb.nbits, mm = eb.m;
+  for (int o = 16; o >= 1; o >>= 1) {
+    nb = max(nb, __shfl_xor_sync(0xffffffffu, nb, o));
+    mm = max(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+  }
+  nb = min(nb, 160);
+  mm = min(mm, 4);
+  Jac<F> acc = xt::endo_mul_sel<F>(tm, GEN ? gen : pts[i], eb, mm, nb, scratch + 2 * TO::BUS_WORDS);
+  Aff<F> o = xt::to_affine<F>(tm, acc);
+  if (live && tm.t == 0) out[i] = o;
+}
+static size_t scale_xt_max_n(bool g2) {
+  static const long v = [] {
+    const char* e = getenv("RIPP_B200_SCALE_XT_MAX");  // 0 = one thread per element everywhere (A/B runs)
+    return e ? atol(e) : -1L;
+  }();
+  return v >= 0 ? (size_t)v : 0;  // off by default: see k_scale_parts
+}
+
 template <class F, class XF>
 static int scale_dev(ripp_ctx* ctx, const void* pts, const void* sc, size_t n, void* out, const Aff<F>& gen) {
   if (!ctx || (n && (!sc || !out))) return fail(RIPP_ERR_ARG, "null argument");
   if (n == 0) return RIPP_OK;
   CU(cudaSetDevice(ctx->device));
   TimeScope ts_(ctx, RIPP_T_SCALE);
+  if (n <= scale_parts_max_n()) {
+    const int m = sizeof(F) == sizeof(Fq) ? 2 : 4;
+    void* parts;
+    OK(scratch(ctx, 22, (size_t)m * n * sizeof(Jac<F>), &parts));
+    unsigned blocks = (unsigned)(((size_t)m * n + 63) / 64);
+    if (pts)
+      k_scale_parts<F, false><<<blocks, 64, 0, ctx->stream>>>((const Aff<F>*)pts, (const Fr*)sc, n, m, (Jac<F>*)parts, gen);
+    else
+      k_scale_parts<F, true><<<blocks, 64, 0, ctx->stream>>>(nullptr, (const Fr*)sc, n, m, (Jac<F>*)parts, gen);
+    LAUNCHED(ctx);
+    k_scale_combine<F><<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>((const Jac<F>*)parts, n, m, (Aff<F>*)out);
+    LAUNCHED(ctx);
+    return RIPP_OK;
+  }
+  if (n <= scale_xt_max_n(sizeof(F) != sizeof(Fq))) {
+    typedef xt::TeamOf<F> TO;
+    unsigned warps = (unsigned)((n + TO::PER_WARP - 1) / TO::PER_WARP), blocks = (warps + SXT_WARPS - 1) / SXT_WARPS;
+    if (pts)
+      k_scale_xt<F, false><<<blocks, 32 * SXT_WARPS, 0, ctx->stream>>>((const Aff<F>*)pts, (const Fr*)sc, n, (Aff<F>*)out, gen);
+    else
+      k_scale_xt<F, true><<<blocks, 32 * SXT_WARPS, 0, ctx->stream>>>(nullptr, (const Fr*)sc, n, (Aff<F>*)out, gen);
+    LAUNCHED(ctx);
+    return RIPP_OK;
+  }
   unsigned blocks = (unsigned)((n + 63) / 64);
   if (pts)
     k_scale<F, false><<<blocks, 64, 0, ctx->stream>>>((const Aff<F>*)pts, (const Fr*)sc, n, (Aff<F>*)out, gen);
@@ -240,6 +362,13 @@ static int scale_dev(ripp_ctx* ctx, const void* pts, const void* sc, size_t n, v
     k_scale<F, true><<<blocks, 64, 0, ctx->stream>>>(nullptr, (const Fr*)sc, n, (Aff<F>*)out, gen);
   LAUNCHED(ctx);
   return RIPP_OK;
+}
+// the same kernels on one caller-supplied base (setup.cu: the fixed-base table and the short-vector path)
+int ripp_scale_base_g1(ripp_ctx* ctx, const G1Aff* base_or_null, const void* sc, size_t n, void* out) {
+  return scale_dev<Fq, Fq>(ctx, nullptr, sc, n, out, base_or_null ? *base_or_null : g1_generator());
+}
+int ripp_scale_base_g2(ripp_ctx* ctx, const G2Aff* base_or_null, const void* sc, size_t n, void* out) {
+  return scale_dev<Fq2, x3::Fq2x3>(ctx, nullptr, sc, n, out, base_or_null ? *base_or_null : g2_generator());
 }
 extern "C" int ripp_g1_scale_dev(ripp_ctx* ctx, const void* pts, const void* sc, size_t n, void* out) {
   return scale_dev<Fq, Fq>(ctx, pts, sc, n, out, g1_generator());

@@ -210,5 +210,35 @@ RIPP_HD Jac<F> endo_mul(const Team& tm, const Aff<F>& p, const EndoBits& c, uint
   return acc;
 }
 
+// Same sum when every TEAM has its own scalar (element-wise scalings a_i r^i, ck_i r^-i of groth16_aggregation.rs:118-131,
+// SIPP's a_i r_i): all teams of a warp walk the same (bit, digit) slots -- `m` digits, `nbits` bits, the warp's maxima --
+// and a slot whose digit is zero adds the identity, so no team ever skips an exchange.
+template <class F>
+RIPP_HD Jac<F> endo_mul_sel(const Team& tm, const Aff<F>& p, const EndoBits& c, int m, int nbits, uint32_t* bases) {
+  constexpr int AW = sizeof(Aff<F>) / 4;
+  {
+    Aff<F> b = p;
+    for (int t = 0; t < m; t++) {
+      if (tm.t == 0) aff_st<F>(bases + t * AW, b);
+      if (t + 1 < m) b = endo_map(b);
+    }
+  }
+  sync(tm);
+  Jac<F> acc = Jac<F>::inf();
+#pragma unroll 1
+  for (int j = nbits - 1; j >= 0; j--) {
+    acc = dbl<F>(tm, acc);
+#pragma unroll 1
+    for (int t = 0; t < m; t++) {
+      const bool ps = (c.pos[t][j >> 5] >> (j & 31)) & 1, ng = (c.neg[t][j >> 5] >> (j & 31)) & 1;
+      Aff<F> q = aff_ld<F>(bases + t * AW);
+      if (ng) q = q.neg();
+      if (!(ps || ng)) q = Aff<F>::inf();
+      acc = madd<F>(tm, acc, q);
+    }
+  }
+  return acc;
+}
+
 }  // namespace xt
 }  // namespace ripp

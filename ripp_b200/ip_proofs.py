@@ -57,6 +57,24 @@ class GIPA:
     def __init__(self, kind, ctx=None):
         self.kind, self.ctx = kind, ctx or default_context()
 
+    def prove(self, values, ck, com):
+        """gipa.rs:108-133, the checked entry.  values = (m_a, m_b, ip); ck = (ck_a, ck_b or None, _); com = (com_a, com_b,
+        com_t) ((com_a, com_t) for the *_SSM kinds).  Raises InnerProductArgumentError("InnerProductInvalid") when the
+        inner product or a commitment does not match, MessageLengthInvalid for a length that is not a power of two."""
+        m_a, m_b = values[0], values[1]
+        n = len(m_a)
+        if len(m_b) != n:
+            raise _lib.LengthMismatch(_lib.RIPP_ERR_LEN_MISMATCH, "left length, right length: %d, %d" % (n, len(m_b)))
+        a, b, v, w = _upload(self.ctx, self.kind, (m_a, m_b, ck[0], ck[1]))
+        try:
+            return self.ctx.gipa_prove_checked_dev(self.kind, a, b, v, w, n, _ser_com(com))
+        except _lib.RippError as e:
+            if e.status == _lib.RIPP_ERR_INNER_PRODUCT:
+                raise InnerProductArgumentError("InnerProductInvalid") from e
+            if e.status == _lib.RIPP_ERR_NOT_POW2:
+                raise InnerProductArgumentError(str(e)) from e
+            raise
+
     def prove_with_aux(self, values, ck):
         """gipa.rs:162-178.  values = (m_a, m_b); ck = (ck_a, ck_b or None).  -> (proof bytes, transcript ints, ck_base bytes)"""
         m_a, m_b = values
@@ -87,6 +105,19 @@ class TIPA:
 
     def __init__(self, kind, ctx=None):
         self.kind, self.ctx = kind, ctx or default_context()
+
+    @staticmethod
+    def setup(alpha, beta, size, ctx=None):
+        """TIPA::setup (tipa/mod.rs:150-164) for given trapdoors (the reference draws them with Fr::rand; the caller
+        does that here).  -> (SRS dict(g_alpha_powers, h_beta_powers: DeviceBuffers of 2 size - 1 points; g_beta,
+        h_alpha: affine tuples), v_srs dict(g, h, g_beta, h_alpha))."""
+        ctx = ctx or default_context()
+        s1, s2, gb, ha = ctx.tipa_setup_dev(codec.fr_enc(alpha).copy(), codec.fr_enc(beta).copy(), size)
+        g_beta, h_alpha = codec.g1_dec(gb), codec.g2_dec(ha)
+        srs = {"g_alpha_powers": s1, "h_beta_powers": s2, "g_beta": g_beta, "h_alpha": h_alpha, "size": size}
+        g = codec.g1_vec_dec(s1.download((1, 24)))[0]  # power 0 of each tower: the generators (tipa/mod.rs:120-127)
+        h = codec.g2_vec_dec(s2.download((1, 48)))[0]
+        return srs, {"g": g, "h": h, "g_beta": g_beta, "h_alpha": h_alpha}
 
     def prove_with_srs_shift(self, srs, values, ck, r_shift=1):
         """tipa/mod.rs:176-231.  srs = (g_alpha_powers, h_beta_powers)."""
@@ -133,3 +164,13 @@ def verify_aggregate_proof(v_srs, vk, public_inputs, proof, ctx=None):
     assert len(vk["gamma_abc_g1"]) == m + 1  # :214
     inp = np.ascontiguousarray(np.stack([codec.fr_vec_enc(row) for row in public_inputs]).reshape(n, m, 8))
     return ctx.tipp_verify_aggregate(vsrs_enc(v_srs), np.ascontiguousarray(vk_enc(vk)), inp, proof)
+
+
+def structured_generators_scalar_power(num, g, s, group, ctx=None):
+    """tipa/mod.rs:372-391: [g * s^i for i < num] (g: affine tuple or None = the generator; group 1 / 2).  -> list of points"""
+    ctx = ctx or default_context()
+    out = ctx.alloc(num * (96 if group == 1 else 192))
+    base = None if g is None else (codec.g1_enc(g) if group == 1 else codec.g2_enc(g)).copy()
+    ctx.structured_generators_dev(group, base, codec.fr_enc(s).copy(), num, out)
+    ctx.sync()
+    return (codec.g1_vec_dec if group == 1 else codec.g2_vec_dec)(out.download((num, 24 if group == 1 else 48)))

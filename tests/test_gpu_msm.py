@@ -104,3 +104,26 @@ def test_folds(ctx, cbits):
     d_a, d_b = ctx.to_device(C.fr_vec_enc(a)), ctx.to_device(C.fr_vec_enc(b))
     ctx.fr_fold_dev(d_a, d_b, ch, n, d_b)
     assert C.fr_vec_dec(d_b.download((n, 8))) == [(x * c + y) % E.R for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize("n", [1, 3, 37])
+def test_scalings_match_oracle(ctx, n):
+    """out[i] = s[i] * P[i] with one scalar per element (groth16_aggregation.rs:118-131 a_r / ck_1_r; sipp/src/lib.rs:61-66):
+    the lane-team kernel (k_scale_xt), scalars 0 / 1 / r-1 / 128-bit, identity inputs, and the generator form (pts = NULL)."""
+    s = [rnd.randrange(E.R) for _ in range(n)]
+    for j, v in enumerate([0, 1, E.R - 1, rnd.randrange(1 << 128), 2]):
+        if j < n:
+            s[j] = v
+    p1, p2 = OS.g1_points("sc-p", n), OS.g2_points("sc-p", n)
+    if n > 5:
+        p1[5], p2[6] = None, None
+    ds = ctx.to_device(C.fr_vec_enc(s))
+    out = ctx.alloc(n * 192)
+    ctx.g1_scale_dev(ctx.to_device(C.g1_vec_enc(p1)), ds, n, out)
+    assert C.g1_vec_dec(out.download((n, 24))) == [E.g1_mul(p, k) for p, k in zip(p1, s)]
+    ctx.g2_scale_dev(ctx.to_device(C.g2_vec_enc(p2)), ds, n, out)
+    assert C.g2_vec_dec(out.download((n, 48))) == [E.g2_mul(p, k) for p, k in zip(p2, s)]
+    ctx.g1_scale_dev(None, ds, n, out)
+    assert C.g1_vec_dec(out.download((n, 24))) == [E.g1_mul(E.G1_GEN, k) for k in s]
+    ctx.g2_scale_dev(None, ds, n, out)
+    assert C.g2_vec_dec(out.download((n, 48))) == [E.g2_mul(E.G2_GEN, k) for k in s]
