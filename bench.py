@@ -49,8 +49,34 @@ LOG_PROOFS = 12
 LOG_PAIRS = 16
 LOG_MSM = 18
 LOG_GIPA = 18
-# per-launch DRAM traffic of the kernel classes measured once with `ncu --set full` (profiles/README.md)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {"fold": 150144, "miller": 19164928, "msm": 108558848, "final_exp": 711168}
+# kernel class -> (kernel named in the line, ncu capture of that kernel under profiles/: `ncu --set full ... --page raw --csv`)
+CLASS_KERNEL = {
+    "fold": ("k_fold_xt / k_fold_endo (A' = A_R c + A_L, gipa.rs:261-291)", "fold"),
+    "miller": ("k_miller6 / k_miller18 + Fq12 product tree (cfg_multi_pairing, inner_products/src/lib.rs:77-116)", "miller6"),
+    "final_exp": ("k_final_exp18", "fexp"),
+    "msm": ("variable-base MSM (k_msm_accumulate and its sort / reduce / Horner launches)", "msm_acc"),
+    "scale": ("k_scale_parts + k_scale_combine (a_i r^i, ck_i r^-i: groth16_aggregation.rs:118-131)", "scale"),
+}
+_UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def ncu_traffic(capture):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches) from the newest committed
+    `profiles/*_ncu_<capture>_raw.csv`; (None, None) when no capture of that kernel is committed."""
+    import csv
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_%s_raw.csv" % capture)))
+    if not files:
+        return None, None
+    try:
+        rows = list(csv.reader(open(files[-1])))
+        h = rows[0]
+        ir, iw = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+        vals = [float(r[ir]) * _UNIT[rows[1][ir]] + float(r[iw]) * _UNIT[rows[1][iw]] for r in rows[2:] if len(r) > max(ir, iw)]
+        return (sum(vals) / len(vals) if vals else None), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, os.path.relpath(files[-1], ROOT)
 METRIC = "tipp_groth16_aggregate_prove_seconds_at_2^12_proofs"
 DTYPE = "u32-limb Montgomery (BLS12-381 Fq 381-bit / Fr 255-bit)"
 
@@ -297,6 +323,11 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        # the library's own NCCL communicator (comm.cu): the sharded entry points run their all-gathers inside the C ABI
+        from ripp_b200.parallel import init_library_comm
+
+        init_library_comm(ctx)
     warmup = max(args.warmup, 3)
     n = 1 << args.logn
 
@@ -382,12 +413,8 @@ def main():
         result = torch.zeros(144, dtype=torch.int32, device="cuda")
 
         def pairing_step():
-            if world == 1:
-                ctx.pairing_ip_dev(pa, pb, npairs, result.data_ptr())
-            else:
-                ctx.miller_partial_dev(pa, pb, npairs, partial.data_ptr())
-                dist.all_gather_into_tensor(gathered, partial)
-                ctx.gt_combine_dev(gathered.data_ptr(), world, result.data_ptr())
+            # world == 1: the plain entry point; else Miller partial -> ncclAllGather (576 B / rank) -> product + final exp
+            ctx.pairing_ip_sharded_dev(pa, pb, npairs, result.data_ptr())
 
         def timed(fn, reps):
             for _ in range(3):
@@ -418,12 +445,7 @@ def main():
         res_pt = torch.zeros(24, dtype=torch.int32, device="cuda")
 
         def msm_step():
-            if world == 1:
-                ctx.msm_g1_dev(bases, sc, nmsm, res_pt.data_ptr())
-            else:
-                ctx.msm_g1_dev(bases, sc, nmsm, part_pt.data_ptr())
-                dist.all_gather_into_tensor(gath_pt, part_pt)
-                ctx.msm_g1_dev(gath_pt.data_ptr(), ones, world, res_pt.data_ptr())
+            ctx.msm_sharded_dev(1, bases, sc, nmsm, res_pt.data_ptr())
 
         ms = timed(msm_step, reps)
         sub["msm_g1_points_per_s"] = {"value": world * nmsm / (ms * 1e-3), "points_per_gpu": nmsm, "ms_per_step": ms}
@@ -452,19 +474,75 @@ def main():
             return t
 
         ga, gb, gv, gw = share("cfg3-a", 1), share("cfg3-b", 0), share("cfg3-v", 2), share("cfg3-w", 1)
-        sg = ShardedGIPA(_lib.GIPA_MULTIEXP_PEDERSEN, ctx, Comm())
-        gproof = sg.prove_with_aux_dev(ga, gb, gv, gw)[0]  # warm-up
+
+        def gipa_step():
+            # ripp_gipa_prove_sharded_dev: the round loop, its all-gathers (NCCL inside the library) and the resident tail
+            return ctx.gipa_prove_sharded_dev(_lib.GIPA_MULTIEXP_PEDERSEN, ga.data_ptr(), gb.data_ptr(), gv.data_ptr(),
+                                              gw.data_ptr(), nl, world)[0]
+
+        gproof = gipa_step()  # warm-up
         g_reps = 2
         barrier()
         t0 = time.perf_counter()
         for _ in range(g_reps):
-            gproof = sg.prove_with_aux_dev(ga, gb, gv, gw)[0]
+            gproof = gipa_step()
         torch.cuda.synchronize()
         g_s = max_over_ranks((time.perf_counter() - t0) / g_reps)
         sub["gipa_multiexp_prove_s"] = {"value": g_s, "elements_total": ng, "elements_per_gpu": nl, "scaling": "strong",
                                         "proof_blake2b": hashlib.blake2b(gproof, digest_size=16).hexdigest(),
                                         "proof_bytes": len(gproof)}
         del ga, gb, gv, gw
+
+        # ---- strong scaling of ONE instance over the N ranks, all through the library's sharded entry
+        # points: leaf products at sizes where a GPU is past its latency floor, and one batch of 2^16 proofs
+        def rand_fr(count, seed):
+            w = np.random.default_rng(seed).integers(0, 1 << 32, size=(count, 8), dtype=np.uint32)
+            w[:, 7] &= 0x0FFFFFFF  # < r: a valid Montgomery representative
+            return w
+
+        def gen(group, count, seed):
+            e = ctx.to_device(rand_fr(count, seed))
+            out = ctx.alloc(count * (96 if group == 1 else 192))
+            ctx.fixed_base_msm_dev(group, None, e, count, out)
+            ctx.sync()
+            e.free()
+            return out
+
+        strong = {}
+        lp, lm, la = 18, 22, 16
+        nlp = (1 << lp) // world
+        spa, spb = gen(1, nlp, 1000 + rank), gen(2, nlp, 2000 + rank)
+        ms = timed(lambda: ctx.pairing_ip_sharded_dev(spa, spb, nlp, result.data_ptr()), 3)
+        strong["pairing_ip_2^%d" % lp] = {"ms": ms, "pairs_per_s": (1 << lp) / (ms * 1e-3)}
+        spa.free()
+        spb.free()
+        nlm = (1 << lm) // world
+        smb, sms = gen(1, nlm, 3000 + rank), ctx.to_device(rand_fr(nlm, 4000 + rank))
+        ms = timed(lambda: ctx.msm_sharded_dev(1, smb, sms, nlm, res_pt.data_ptr()), 3)
+        strong["msm_g1_2^%d" % lm] = {"ms": ms, "points_per_s": (1 << lm) / (ms * 1e-3)}
+        smb.free()
+        sms.free()
+        strong["gipa_multiexp_2^%d" % LOG_GIPA] = {"s": g_s}
+        na = 1 << la
+        big = synth.tipp_instance_dev(ctx, na, seed=7)
+
+        def cyc(buf, words):
+            return ctx.to_device(np.ascontiguousarray(buf.download((na, words))[rank::world]))
+
+        if world == 1:
+            agg_step = lambda: ctx.tipp_aggregate_dev(big["srs_g1"], big["srs_g2"], big["a"], big["b"], big["c"], na)
+        else:
+            ca, cb, cc = cyc(big["a"], 24), cyc(big["b"], 48), cyc(big["c"], 24)
+            agg_step = lambda: ctx.tipp_aggregate_sharded_dev(big["srs_g1"], big["srs_g2"], ca, cb, cc, na)
+        aproof = agg_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            aproof = agg_step()
+        a_s = max_over_ranks((time.perf_counter() - t0) / 2)
+        strong["tipp_aggregate_2^%d" % la] = {"s": a_s, "proof_blake2b": hashlib.blake2b(aproof, digest_size=16).hexdigest()}
+        sub["strong_scaling_one_instance"] = strong
+        del big
 
     stop.set()
     th.join(timeout=2)
@@ -477,30 +555,38 @@ def main():
     dom = max((c for c in macs), key=lambda c: breakdown[c][0])
     dom_ms, dom_launches = breakdown[dom]
     achieved = macs[dom] / (dom_ms * 1e-3) if dom_ms else 0.0
+    traffic, traffic_src = ncu_traffic(CLASS_KERNEL[dom][1])
+    all_ms = sum(breakdown[c][0] for c in breakdown)
     roofline = {
         "bound": "int32 multiply pipe (IMAD.WIDE.U32: one 32x32+64 MAC per lane-instruction)",
-        "kernel": "%s kernels of one aggregation (%d timed scopes)" % (dom, dom_launches),
+        # the kernel class with the largest summed device time in one aggregation (CUDA events around every launch of
+        # the class, on the launching stream; classes overlap on several streams, so the sum over classes exceeds the step)
+        "kernel": CLASS_KERNEL[dom][0], "launches": dom_launches, "mean_ms": dom_ms / max(dom_launches, 1),
+        "share_of_summed_kernel_time": dom_ms / all_ms if all_ms else None,
         "achieved": achieved / 1e12, "peak": imad_peak / 1e12, "unit": "TMAC32/s", "frac": achieved / imad_peak,
-        # dram__bytes_read + write per launch of the dominant class from the committed `ncu --set full` capture
-        # (profiles/r1f_ncu_fold_raw.csv: 100 KB G1 / 201 KB G2 per late-round team-fold launch; Miller 2^16: 19 MB)
-        "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get(dom), "traffic_source": "profiles/r1f_ncu_*_raw.csv (static, from the committed ncu capture)",
-        "kernel_ms": dom_ms,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "note": ("2^12 proofs is a latency regime: the dominant class is %d launches of a few CTAs each (one dependent chain per "
+                 "element), so its fraction of the whole-GPU integer peak is small by construction; the throughput kernels "
+                 "the north star names are reported at their own sizes in miller_2^16 / msm_2^18" % dom_launches),
         "peak_source": "ripp_bench_imad in this run: independent IMAD.WIDE.U32 chains, all SMs",
         "peak_imad32_tmacs": imad32_peak / 1e12, "peak_carry_chain_tmacs": chain_peak / 1e12,
         "step_breakdown_ms": {c: round(breakdown[c][0], 3) for c in breakdown},
+        "step_launches": {c: breakdown[c][1] for c in breakdown},
         "step_frac_by_class": {c: (macs[c] / (breakdown[c][0] * 1e-3) / imad_peak if breakdown[c][0] else None) for c in macs},
         "whole_step_frac": sum(macs.values()) / value_s / imad_peak,
     }
     if miller_k_ms:
         m = (1 << LOG_PAIRS) * FQ_MUL_PER_MILLER_PAIR * MAC32_PER_FQ_MUL / (miller_k_ms * 1e-3)
-        roofline["miller_2^16"] = {"kernel": "k_miller + Fq12 product tree", "kernel_ms": miller_k_ms,
+        roofline["miller_2^16"] = {"kernel": "k_miller6<4,4> + Fq12 product tree", "kernel_ms": miller_k_ms,
+                                   "traffic": ncu_traffic("miller6")[0],
                                    "achieved": m / 1e12, "frac": m / imad_peak,
                                    "mac32_per_pair": FQ_MUL_PER_MILLER_PAIR * MAC32_PER_FQ_MUL}
 
     if "msm_g1_points_per_s" in sub:
         mm = sub["msm_g1_points_per_s"]
         m = world * mm["points_per_gpu"] * FQ_MUL_PER_G1_MSM_POINT * MAC32_PER_FQ_MUL / (mm["ms_per_step"] * 1e-3) / world
-        roofline["msm_2^18"] = {"kernel": "whole G1 MSM (13 launches: expand, prepare, scan, scatter, accumulate, fat buckets, reductions, Horner)",
+        roofline["msm_2^18"] = {"kernel": "whole G1 MSM (expand, prepare, scan, scatter, accumulate, fat buckets, reductions, Horner)",
+                                "traffic_accumulate_kernel": ncu_traffic("msm_acc")[0],
                                 "kernel_ms": mm["ms_per_step"], "achieved": m / 1e12, "frac": m / imad_peak,
                                 "mac32_per_point": FQ_MUL_PER_G1_MSM_POINT * MAC32_PER_FQ_MUL}
 
@@ -511,7 +597,9 @@ def main():
             "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": "TIPP aggregate_proofs of 2^%d Groth16 proofs per GPU, BLS12-381, Blake2b (BASELINE configs[3])" % args.logn,
                        "proofs_per_gpu": n, "l2": "flushed between steps (256 MiB memset)",
-                       "parallelism": "one 2^%d-proof aggregation per GPU (weak); leaf ops sharded by slices in sub_metrics" % args.logn},
+                       "parallelism": "one 2^%d-proof aggregation per GPU (weak); strong_scaling: ONE instance sharded over the N ranks "
+                                      "through the library's NCCL entry points (same bytes at every N)" % args.logn,
+                       "strong_scaling": sub.get("strong_scaling_one_instance")},
             "proofs_per_s": world * n / value_s,
             "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": n * 384, "d2h_bytes_per_step": len(host_proof)},
             "gpu_launches": launches,

@@ -245,6 +245,57 @@ class Context:
                                                 ctypes.c_size_t(len(cb)), _p(proof), ctypes.c_size_t(cap), ctypes.byref(plen)))
         return proof[: plen.value].tobytes()
 
+    # ---- multi-GPU: NCCL inside the library (comm.cu, sharded.cuh) ---------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes to hand to every rank (rank 0 calls this)."""
+        buf = np.zeros(128, dtype=np.uint8)
+        check(lib().ripp_comm_unique_id(_p(buf)))
+        return buf.tobytes()
+
+    def comm_init(self, unique_id, rank, world):
+        check(lib().ripp_comm_init(self.handle, _p(self._bytes(unique_id)), int(rank), int(world)))
+
+    def comm_info(self):
+        r, w = ctypes.c_int(), ctypes.c_int()
+        check(lib().ripp_comm_info(self.handle, ctypes.byref(r), ctypes.byref(w)))
+        return r.value, w.value
+
+    def comm_destroy(self):
+        check(lib().ripp_comm_destroy(self.handle))
+
+    def all_gather_dev(self, send_dev, nbytes, recv_dev):
+        check(lib().ripp_all_gather_dev(self.handle, _p(send_dev), ctypes.c_size_t(nbytes), _p(recv_dev)))
+
+    def pairing_ip_sharded_dev(self, g1_slice, g2_slice, n_local, out_dev):
+        check(lib().ripp_pairing_ip_sharded_dev(self.handle, _p(g1_slice), _p(g2_slice), ctypes.c_size_t(n_local), _p(out_dev)))
+
+    def msm_sharded_dev(self, group, bases_slice, fr_slice, n_local, out_dev):
+        fn = lib().ripp_msm_g1_sharded_dev if group == 1 else lib().ripp_msm_g2_sharded_dev
+        check(fn(self.handle, _p(bases_slice), _p(fr_slice), ctypes.c_size_t(n_local), _p(out_dev)))
+
+    def gipa_prove_sharded_dev(self, kind, a, b, v, w, n_local, world, tail_len=0):
+        """GIPA::prove_with_aux over cyclic shares.  -> (proof bytes, r_transcript (k, 8) uint32, ck_base bytes)."""
+        k = max((n_local * world).bit_length() - 1, 0)
+        cap = 64 + k * 6 * 600 + 2 * 600
+        proof = np.empty(cap, dtype=np.uint8)
+        plen, cklen = ctypes.c_size_t(), ctypes.c_size_t()
+        tr = np.zeros((k, 8), dtype=np.uint32)
+        ck = np.empty(1024, dtype=np.uint8)
+        check(lib().ripp_gipa_prove_sharded_dev(self.handle, int(kind), _p(a), _p(b), _p(v), _p(w), ctypes.c_size_t(n_local),
+                                                ctypes.c_size_t(tail_len), _p(proof), ctypes.c_size_t(cap), ctypes.byref(plen), _p(tr),
+                                                _p(ck), ctypes.c_size_t(1024), ctypes.byref(cklen)))
+        return proof[: plen.value].tobytes(), tr, ck[: cklen.value].tobytes()
+
+    def tipp_aggregate_sharded_dev(self, srs_g1, srs_g2, a, b, c, n_total, tail_len=0):
+        k = max(n_total.bit_length() - 1, 0)
+        cap = 8192 + 2 * (64 + k * 6 * 600 + 8 * 600)
+        proof = np.empty(cap, dtype=np.uint8)
+        plen = ctypes.c_size_t()
+        check(lib().ripp_tipp_aggregate_sharded_dev(self.handle, _p(srs_g1), _p(srs_g2), _p(a), _p(b), _p(c), ctypes.c_size_t(n_total),
+                                                    ctypes.c_size_t(tail_len), _p(proof), ctypes.c_size_t(cap), ctypes.byref(plen)))
+        return proof[: plen.value].tobytes()
+
     # ---- setup --------------------------------------------------------------------------------
     def fixed_base_msm_dev(self, group, base, fr_dev, n, out_dev):
         """out[i] = s[i] * base (base: packed affine words or None = generator)."""

@@ -470,3 +470,19 @@ def _lib_error(msg):
     from . import _lib
 
     return _lib.RippError(_lib.RIPP_ERR_INNER_PRODUCT, msg)
+
+
+def init_library_comm(ctx, group=None):
+    """Gives `ctx` the library's own NCCL communicator (comm.cu) over the ranks of a torch.distributed group: rank 0
+    draws the NCCL unique id, the bootstrap group (any backend) broadcasts its 128 bytes, every rank joins.  After this
+    the sharded entry points of the C ABI (ripp_*_sharded_dev) run their collectives inside the library."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        ctx.comm_init(b"\0" * 128, 0, 1)
+        return 0, 1
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init(box[0], rank, world)
+    return rank, world
