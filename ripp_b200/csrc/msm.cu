@@ -179,16 +179,25 @@ __global__ void __launch_bounds__(128) k_msm_fat_chunks(const Aff<F>* __restrict
     __syncthreads();
   }
 }
-// one thread per fat bucket: sum of its chunk partials
+// one block per fat bucket: strided sums of its chunk partials, then a shared-memory tree (a top window of a 128-bit
+// digit set holds one or two buckets of ~10^5 points = ~85 chunks: summed by ONE thread that was 0.83 ms of a 6.4 ms MSM)
 template <class F>
-__global__ void k_msm_fat_combine(const uint32_t* __restrict__ fat_counters, const FatBucket* __restrict__ fats,
-                                  const Jac<F>* __restrict__ partials, Jac<F>* __restrict__ buckets) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= fat_counters[1]) return;
-  FatBucket fb = fats[t];
-  Jac<F> acc = partials[fb.first_item];
-  for (uint32_t k = 1; k < fb.nchunks; k++) acc = acc.add(partials[fb.first_item + k]);
-  buckets[fb.bucket] = acc;
+__global__ void __launch_bounds__(64) k_msm_fat_combine(const uint32_t* __restrict__ fat_counters, const FatBucket* __restrict__ fats,
+                                                        const Jac<F>* __restrict__ partials, Jac<F>* __restrict__ buckets) {
+  __shared__ Jac<F> sh[64];
+  for (uint32_t t = blockIdx.x; t < fat_counters[1]; t += gridDim.x) {
+    FatBucket fb = fats[t];
+    Jac<F> acc = Jac<F>::inf();
+    for (uint32_t k = threadIdx.x; k < fb.nchunks; k += 64) acc = acc.add(partials[fb.first_item + k]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int st = 32; st >= 1; st >>= 1) {
+      if ((int)threadIdx.x < st) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + st]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) buckets[fb.bucket] = sh[0];
+    __syncthreads();
+  }
 }
 
 // one thread per (window, chunk of L buckets): sum_b b * bucket[b] restricted to the chunk
@@ -227,6 +236,25 @@ __global__ void __launch_bounds__(128) k_jac_reduce(const Jac<F>* __restrict__ i
   Jac<F> acc = in[(size_t)w * T + lo];
   for (uint32_t j = lo + 1; j < hi; j++) acc = acc.add(in[(size_t)w * T + j]);
   out[t] = acc;
+}
+
+// out[w] = sum_t in[w][t], t < T: one block per window
+template <class F> struct WSUM_THREADS { static constexpr int N = 256; };
+template <> struct WSUM_THREADS<Fq2> { static constexpr int N = 128; };  // 128 x 288 B of shared memory
+template <class F>
+__global__ void __launch_bounds__(WSUM_THREADS<F>::N) k_msm_window_sum(const Jac<F>* __restrict__ in, uint32_t T, Jac<F>* __restrict__ out) {
+  constexpr int NT = WSUM_THREADS<F>::N;
+  __shared__ Jac<F> sh[NT];
+  const Jac<F>* src = in + (size_t)blockIdx.x * T;
+  Jac<F> acc = Jac<F>::inf();
+  for (uint32_t t = threadIdx.x; t < T; t += NT) acc = acc.add(src[t]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = NT / 2; st >= 1; st >>= 1) {
+    if ((int)threadIdx.x < st) sh[threadIdx.x] = sh[threadIdx.x].add(sh[threadIdx.x + st]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
 }
 
 template <class F>
@@ -401,7 +429,7 @@ static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, 
     k_msm_fat_chunks<F><<<fat_grid, 128, 0, st>>>(bases, (const uint32_t*)idx, offsets, counts, fat_counters, fat_items,
                                                   fat_partials);
     LAUNCHED(ctx);
-    k_msm_fat_combine<F><<<(max_fat + 63) / 64, 64, 0, st>>>(fat_counters, fat_buckets, fat_partials, (Jac<F>*)bkt);
+    k_msm_fat_combine<F><<<max_fat < 256u ? max_fat : 256u, 64, 0, st>>>(fat_counters, fat_buckets, fat_partials, (Jac<F>*)bkt);
     LAUNCHED(ctx);
   }
   size_t WT = (size_t)p.nw * p.T;
@@ -409,18 +437,11 @@ static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, 
   Jac<F>* pb = pa + WT;
   k_msm_bucket_reduce<F><<<(unsigned)((WT + 127) / 128), 128, 0, st>>>((const Jac<F>*)bkt, p.B, p.L, p.T, pa, WT);
   LAUNCHED(ctx);
-  uint32_t T = p.T;
-  const uint32_t R = 8;
-  while (T > 1) {
-    uint32_t To = (T + R - 1) / R;
-    size_t tot = (size_t)p.nw * To;
-    k_jac_reduce<F><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(pa, T, R, To, pb, tot);
-    LAUNCHED(ctx);
-    Jac<F>* t = pa;
-    pa = pb;
-    pb = t;
-    T = To;
-  }
+  // window sums: one block per window (strided partial sums, then a shared-memory tree) instead of a ladder of
+  // log_8(T) launches of a few warps each
+  k_msm_window_sum<F><<<p.nw, WSUM_THREADS<F>::N, 0, st>>>(pa, p.T, pb);
+  LAUNCHED(ctx);
+  pa = pb;
   if (fold_mode() == 0) {
     typedef xt::TeamOf<F> TO;
     int warps = (p.nw + TO::PER_WARP - 1) / TO::PER_WARP;
