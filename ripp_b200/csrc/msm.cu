@@ -22,7 +22,7 @@ static bool use_endo() {
 struct MsmPlan {
   int c;       // window bits
   int nw;      // windows
-  uint32_t B;  // buckets per window (2^c, bucket 0 unused)
+  uint32_t B;  // buckets per window: 2^(c-1), slot i holds the points whose SIGNED digit has magnitude i + 1
   uint32_t L;  // buckets per reduction chunk
   uint32_t T;  // chunks per window
 };
@@ -42,9 +42,13 @@ static MsmPlan msm_plan(size_t n, int bits = 255) {
   // ~4 points per bucket keeps the per-bucket chain short; below 2^6 points the window only sets the Horner tail
   p.c = lg - (n <= MSM_SMALL_N ? 2 : shift);
   if (p.c < (n <= MSM_SMALL_N ? 6 : 4)) p.c = n <= MSM_SMALL_N ? 6 : 4;
-  if (p.c > 16) p.c = 16;
-  p.nw = (bits + p.c - 1) / p.c;
-  p.B = 1u << p.c;
+  if (p.c > 15) p.c = 15;
+  // signed digits d_w in (-2^(c-1), 2^(c-1)] (the negative of a point is free): half the buckets of an unsigned window
+  // for the same c, i.e. one more bit per window at equal bucket count.  The recoding may carry out of the top digit:
+  // one more bit of room.
+  p.c += 1;
+  p.nw = (bits + 1 + p.c - 1) / p.c;
+  p.B = 1u << (p.c - 1);
   p.L = p.B / 256;  // short chunks: the running-sum chains are latency, not throughput
   if (p.L < 2) p.L = 2;
   if (p.L > 8) p.L = 8;
@@ -60,6 +64,15 @@ __device__ __forceinline__ uint32_t msm_digit(const uint32_t* s, int w, int c) {
   return (uint32_t)(v >> sh) & ((1u << c) - 1);
 }
 
+// signed recoding, window by window with a running carry: returns the magnitude (0 .. 2^(c-1)) and the sign
+__device__ __forceinline__ uint32_t msm_sdigit(const uint32_t* s, int w, int c, uint32_t& carry, bool& neg) {
+  uint32_t raw = (w * c < 256 ? msm_digit(s, w, c) : 0u) + carry;  // <= 2^c
+  const uint32_t half = 1u << (c - 1);
+  neg = raw > half;
+  carry = neg ? 1u : 0u;
+  return neg ? (1u << c) - raw : raw;
+}
+
 // canonical scalars + per-(window, bucket) histogram
 __global__ void k_msm_prepare(const Fr* __restrict__ sc, size_t n, Fr* __restrict__ canon, uint32_t* __restrict__ counts,
                               int c, int nw, int is_mont) {
@@ -67,10 +80,11 @@ __global__ void k_msm_prepare(const Fr* __restrict__ sc, size_t n, Fr* __restric
   if (i >= n) return;
   Fr s = is_mont ? sc[i].from_mont() : sc[i];
   canon[i] = s;
-  uint32_t B = 1u << c;
+  uint32_t B = 1u << (c - 1), carry = 0;
   for (int w = 0; w < nw; w++) {
-    uint32_t d = msm_digit(s.v, w, c);
-    if (d) atomicAdd(&counts[(size_t)w * B + d], 1u);
+    bool neg;
+    uint32_t d = msm_sdigit(s.v, w, c, carry, neg);
+    if (d) atomicAdd(&counts[(size_t)w * B + d - 1], 1u);
   }
 }
 
@@ -132,26 +146,60 @@ __global__ void k_msm_scatter(const Fr* __restrict__ canon, size_t n, uint32_t* 
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fr s = canon[i];
-  uint32_t B = 1u << c;
+  uint32_t B = 1u << (c - 1), carry = 0;
   for (int w = 0; w < nw; w++) {
-    uint32_t d = msm_digit(s.v, w, c);
-    if (d) idx[atomicAdd(&cursor[(size_t)w * B + d], 1u)] = (uint32_t)i;
+    bool neg;
+    uint32_t d = msm_sdigit(s.v, w, c, carry, neg);
+    if (d) idx[atomicAdd(&cursor[(size_t)w * B + d - 1], 1u)] = (uint32_t)i | (neg ? 0x80000000u : 0u);  // bit 31: subtract
   }
 }
 
-// one thread per (window, bucket): sum of the bucket's points
+// ---- buckets sorted by size: a warp of the accumulate kernel then walks 32 buckets of (nearly) equal length ------
+// counting sort of the non-empty, non-fat bucket ids by descending point count (bins 1 .. fat_threshold)
+__global__ void k_msm_size_hist(const uint32_t* __restrict__ counts, size_t total, uint32_t fat_threshold, uint32_t* __restrict__ hist) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t cnt = counts[t];
+  if (cnt && cnt <= fat_threshold) atomicAdd(&hist[cnt], 1u);
+}
+// hist[s] -> start of size s in `order` (largest first); hist[0] <- number of sorted buckets
+__global__ void k_msm_size_scan(uint32_t* __restrict__ hist, uint32_t fat_threshold) {
+  if (threadIdx.x || blockIdx.x) return;
+  uint32_t run = 0;
+  for (uint32_t sz = fat_threshold; sz >= 1; sz--) {
+    uint32_t v = hist[sz];
+    hist[sz] = run;
+    run += v;
+  }
+  hist[0] = run;
+}
+__global__ void k_msm_size_scatter(const uint32_t* __restrict__ counts, size_t total, uint32_t fat_threshold,
+                                   uint32_t* __restrict__ hist, uint32_t* __restrict__ order) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  uint32_t cnt = counts[t];
+  if (cnt && cnt <= fat_threshold) order[atomicAdd(&hist[cnt], 1u)] = (uint32_t)t;
+}
+
+// one thread per non-empty bucket, in order of decreasing size (`order`, n_sorted = *n_sorted_dev entries): sum of the
+// bucket's points; bit 31 of an index entry = the point enters negated (signed window digits)
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_accumulate(const Aff<F>* __restrict__ bases, const uint32_t* __restrict__ idx,
                                                         const uint32_t* __restrict__ offsets,
                                                         const uint32_t* __restrict__ counts, Jac<F>* __restrict__ buckets,
-                                                        size_t total, uint32_t fat_threshold) {
+                                                        const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_sorted_dev) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  uint32_t start = offsets[t], cnt = counts[t];
-  if (cnt > fat_threshold) return;  // summed by k_msm_fat_*
+  if (t >= *n_sorted_dev) return;
+  const uint32_t b = order[t];
+  uint32_t start = offsets[b], cnt = counts[b];
   Jac<F> acc = Jac<F>::inf();
-  for (uint32_t j = 0; j < cnt; j++) acc = acc.add_mixed(bases[idx[start + j]]);
-  buckets[t] = acc;
+  for (uint32_t j = 0; j < cnt; j++) {
+    uint32_t e = idx[start + j];
+    Aff<F> p = bases[e & 0x7fffffffu];
+    if (e >> 31) p = p.neg();
+    acc = acc.add_mixed(p);
+  }
+  buckets[b] = acc;
 }
 
 // one block per (fat bucket, chunk): strided partial sums, then a shared-memory tree
@@ -168,7 +216,12 @@ __global__ void __launch_bounds__(128) k_msm_fat_chunks(const Aff<F>* __restrict
     uint32_t end = offsets[w.bucket] + counts[w.bucket];
     if (end > start + MSM_FAT_CHUNK) end = start + MSM_FAT_CHUNK;
     Jac<F> acc = Jac<F>::inf();
-    for (uint32_t j = start + threadIdx.x; j < end; j += 128) acc = acc.add_mixed(bases[idx[j]]);
+    for (uint32_t j = start + threadIdx.x; j < end; j += 128) {
+      uint32_t e = idx[j];
+      Aff<F> p = bases[e & 0x7fffffffu];
+      if (e >> 31) p = p.neg();
+      acc = acc.add_mixed(p);
+    }
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int s = 64; s >= 1; s >>= 1) {
@@ -213,12 +266,13 @@ __global__ void __launch_bounds__(128) k_msm_bucket_reduce(const Jac<F>* __restr
     run = run.add(buckets[(size_t)w * B + j0 + b]);
     if (b > 0) acc = acc.add(run);
   }
-  // acc = sum_b b_local * bucket, run = sum bucket; add j0 * run
-  if (j0 && !run.is_inf()) {
+  // acc = sum_b b_local * bucket, run = sum bucket; slot j0 + b_local carries weight j0 + b_local + 1: add (j0 + 1) run
+  if (!run.is_inf()) {
+    const uint32_t wgt = j0 + 1;
     Jac<F> m = Jac<F>::inf();
-    for (int bit = 31 - __clz(j0); bit >= 0; bit--) {
+    for (int bit = 31 - __clz(wgt); bit >= 0; bit--) {
       m = m.dbl();
-      if ((j0 >> bit) & 1) m = m.add(run);
+      if ((wgt >> bit) & 1) m = m.add(run);
     }
     acc = acc.add(m);
   }
@@ -414,15 +468,29 @@ static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, 
   k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, n, (Fr*)canon, counts, p.c, p.nw, is_mont);
   LAUNCHED(ctx);
   // "fat" = far above the mean bucket size (and never below MSM_FAT points)
-  uint32_t fat_threshold = (uint32_t)(4 * (n >> p.c));
+  uint32_t fat_threshold = (uint32_t)(4 * (n >> (p.c - 1)));  // 4 x the mean bucket size
   if (fat_threshold < fat_min) fat_threshold = fat_min;
   k_msm_scan<<<p.nw, 256, 0, st>>>(counts, offsets, cursor, p.B, n, fat_counters, fat_items, fat_buckets, max_items,
                                    fat_threshold);
   LAUNCHED(ctx);
   k_msm_scatter<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const Fr*)canon, n, cursor, (uint32_t*)idx, p.c, p.nw);
   LAUNCHED(ctx);
+  // buckets by decreasing size; empty ones stay the identity (all-zero Jacobian: Z = 0)
+  void* ordbuf;
+  OK(scratch(ctx, 30, (WB + fat_threshold + 8) * sizeof(uint32_t), &ordbuf));
+  uint32_t* size_hist = (uint32_t*)ordbuf;            // fat_threshold + 1 bins; [0] = number of sorted buckets
+  uint32_t* order = size_hist + fat_threshold + 8;
+  CU(cudaMemsetAsync(size_hist, 0, (fat_threshold + 1) * sizeof(uint32_t), st));
+  CU(cudaMemsetAsync(bkt, 0, WB * sizeof(Jac<F>), st));
+  k_msm_size_hist<<<(unsigned)((WB + 255) / 256), 256, 0, st>>>(counts, WB, fat_threshold, size_hist);
+  LAUNCHED(ctx);
+  k_msm_size_scan<<<1, 32, 0, st>>>(size_hist, fat_threshold);
+  LAUNCHED(ctx);
+  // the scan leaves the start of each size class in its bin: the scatter advances them, bin 0 keeps the total
+  k_msm_size_scatter<<<(unsigned)((WB + 255) / 256), 256, 0, st>>>(counts, WB, fat_threshold, size_hist, order);
+  LAUNCHED(ctx);
   k_msm_accumulate<F><<<(unsigned)((WB + 127) / 128), 128, 0, st>>>(bases, (const uint32_t*)idx, offsets, counts,
-                                                                   (Jac<F>*)bkt, WB, fat_threshold);
+                                                                   (Jac<F>*)bkt, order, size_hist);
   LAUNCHED(ctx);
   {
     unsigned fat_grid = max_items < 1184u ? max_items : 1184u;  // grid-stride over the item list; 8 blocks per SM
