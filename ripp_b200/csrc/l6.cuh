@@ -123,12 +123,7 @@ RIPP_HD void gather3(const C& c, const Fq& mine, Fq& t0, Fq& t1, Fq& t2) {
 // One out-of-line copy of the Fq2 product on the device (operands by value, in registers) instead of an inlined
 // copy per use: the Miller loop body drops from 24 k to 18 k instructions (2^16 pairs: 21.4 -> 21.1 ms, small
 // batches 3.0 -> 2.7 ms: fewer instruction-cache misses for the lone warps of the late GIPA rounds).
-RIPP_HD Fq2 f2mul_body(const Fq2& a, const Fq2& b) {
-  Fq t0 = fqmul(a.c0, b.c0);
-  Fq t1 = fqmul(a.c1, b.c1);
-  Fq t2 = fqmul(a.c0 + a.c1, b.c0 + b.c1);
-  return {t0 - t1, t2 - t0 - t1};
-}
+RIPP_HD Fq2 f2mul_body(const Fq2& a, const Fq2& b) { return fq2_mul_lazy(a, b); }  // two reductions, not three (tower.cuh)
 // the role's Karatsuba product of a b (W = 3); the caller exchanges the three and combines
 RIPP_HD Fq f2mul_part_body(const Fq2& a, const Fq2& b, int role) {
   return fqmul(sel3(role, a.c0, a.c1, a.c0 + a.c1), sel3(role, b.c0, b.c1, b.c0 + b.c1));
