@@ -382,7 +382,14 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
   Fq12 *src = (Fq12*)bufA, *dst = (Fq12*)bufB;
   uint32_t T;
   const size_t w18 = l18_max_warps();
-  if (total <= 4 * w18) {
+  // eighteen-lane warps with ONE pair each, up to l18_max_warps pairs (two warps per sub-partition); above that the
+  // six-lane shape wins -- measured (gpurun_out/r2o): six products of 256 / 512 pairs 3.80 / 5.68 ms with 2 / 4 pairs per
+  // eighteen-lane warp, 3.18 / 3.69 ms on six lanes; TIPP 2^12 93.5 -> 87.8 ms.  RIPP_B200_L18_KP = 2 / 4 re-enables them.
+  static const int l18_kp_max = [] {
+    const char* e = getenv("RIPP_B200_L18_KP");
+    return e ? atoi(e) : 1;
+  }();
+  if (total <= (size_t)l18_kp_max * w18) {
     // latency shape: one pair (or 2 / 4 sharing an accumulator) per eighteen-lane warp, four warps per CTA combined
     // in shared memory, then a tree of one-warp products and one warp per final exponentiation
     {

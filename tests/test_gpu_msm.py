@@ -36,7 +36,41 @@ def test_msm_g2_matches_oracle(ctx, n):
 
     pts = OS.g2_points("m-b", n, seed=n)
     sc = [rnd.randrange(E.R) for _ in range(n)]
+    if n >= 7:  # scalars 0 / 1 / r - 1 and the identity among the bases
+        sc[0], sc[1], sc[2] = 0, 1, E.R - 1
+        pts[3] = None
+    if n >= 64:  # repeated points (a doubling inside a bucket) and P, -P with equal scalars (a bucket that cancels)
+        pts[10] = pts[11]
+        sc[10] = sc[11]
+        pts[12] = E.g2_neg(pts[13])
+        sc[12] = sc[13]
+        sc[20] = (1 << 128) - 1  # one endomorphism digit only
     assert IP.inner_product(pts, sc, ctx) == E.msm(pts, sc, E.g2_add, E.g2_mul)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_msm_signed_digit_corner_scalars(ctx, group):
+    """Scalars chosen for the signed window recoding of msm.cu: every window digit at the carry boundary (2^(c-1),
+    2^(c-1) + 1, 2^c - 1 repeated), the all-ones scalar, r - 1, and many points sharing ONE scalar (a single fat bucket per
+    window, the size-sorted path with one giant class)."""
+    n = 600
+    pts = (OS.g1_points if group == 1 else OS.g2_points)("m-corner", n)
+    pats = []
+    for c in (7, 8, 13, 15, 16):
+        for d in ((1 << (c - 1)), (1 << (c - 1)) + 1, (1 << c) - 1):
+            pats.append(sum(d << (c * w) for w in range(255 // c)) % E.R)
+    sc = [pats[i % len(pats)] for i in range(n)]
+    sc[0], sc[1] = (1 << 254) - 1, E.R - 1
+    for i in range(300, 600):
+        sc[i] = sc[300]
+    d_p = ctx.to_device((C.g1_vec_enc if group == 1 else C.g2_vec_enc)(pts))
+    d_s = ctx.to_device(C.fr_vec_enc(sc))
+    out = ctx.alloc(192)
+    (ctx.msm_g1_dev if group == 1 else ctx.msm_g2_dev)(d_p, d_s, n, out)
+    ctx.sync()
+    add, mul = (E.g1_add, E.g1_mul) if group == 1 else (E.g2_add, E.g2_mul)
+    got = (C.g1_dec(out.download(24)) if group == 1 else C.g2_dec(out.download(48)))
+    assert got == E.msm(pts, sc, add, mul)
 
 
 def test_msm_linearity_at_scale(ctx):
