@@ -427,14 +427,44 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
     LAUNCHED(ctx);
     return RIPP_OK;
   }
-  // throughput shape.  Pairs per group: the largest of {4, 2, 1} that still leaves ~one wave of groups (148 SMs x 8 warps x 5)
-  int kp = total >= 4 * 5920 ? 4 : (total >= 2 * 5920 ? 2 : 1);
+  // throughput shape.  Pairs per group (they share the accumulator's squaring): all warps of a launch do equal work, so the
+  // launch takes ceil(warps / resident warps) waves of one warp's duration; per doubling step a warp spends ~2040 MAC32
+  // on the shared squaring and ~3096 per pair (point step + sparse line product).  Pick the kp in {1..4} with the
+  // cheapest waves x duration -- e.g. 12 288 pairs (TIPP 2^12, first round): kp = 2 is two waves, kp = 3 one.
+  int kp = 4;
+  {
+    cudaDeviceProp prop;
+    static int sms = 0;
+    if (!sms) {
+      CU(cudaGetDeviceProperties(&prop, ctx->device));
+      sms = prop.multiProcessorCount;
+    }
+    const size_t resident = (size_t)sms * 2 * M6_WARPS;  // two CTAs per SM (255 registers, ~100 KB of shared memory each)
+    double best = 0;
+    // many waves: CTAs are scheduled as others retire, the tail of the last wave is a small share -- most sharing wins
+    const bool many = (size_t)nseg * ((n + 19) / 20) >= 3 * resident;
+    for (int k = 1; k <= 4 && !many; k++) {
+      size_t warps = (size_t)nseg * ((n + 5 * k - 1) / (5 * k));
+      double t = (double)((warps + resident - 1) / resident) * (2040.0 + 3096.0 * k);
+      if (k == 1 || t <= best) {
+        best = t;
+        kp = k;
+      }
+    }
+    static const int force = [] {
+      const char* e = getenv("RIPP_B200_M6_KP");
+      return e ? atoi(e) : 0;
+    }();
+    if (force >= 1 && force <= 4) kp = force;
+  }
   const uint32_t R = 8;
   size_t nwarps = 0;
   {
     TimeScope ts_(ctx, RIPP_T_MILLER);
     if (kp == 4)
       OK(launch_miller6<4>(ctx, b, n, src, &nwarps));
+    else if (kp == 3)
+      OK(launch_miller6<3>(ctx, b, n, src, &nwarps));
     else if (kp == 2)
       OK(launch_miller6<2>(ctx, b, n, src, &nwarps));
     else
@@ -482,6 +512,7 @@ int ripp_pairing6_init_device() {
   CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
   CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 1) * 4));
   CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 2) * 4));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 3) * 4));
   CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 4) * 4));
   return RIPP_OK;
 }

@@ -1,6 +1,5 @@
-O=gpurun_out; T=r2o
-for cfg in "4 1184" "1 1184" "1 1776" "1 2368" "1 3552"; do set -- $cfg
-echo "== L18_KP=$1 L18_WARPS=$2"
-RIPP_B200_L18_KP=$1 RIPP_B200_L18_WARPS=$2 python tools/time_round.py 2>&1 | sed -n 6,13p
-RIPP_B200_L18_KP=$1 RIPP_B200_L18_WARPS=$2 python tools/time_tipp.py 12 5 2>&1 | tail -2 | head -1
-done
+O=gpurun_out; T=r2r
+python -m pytest tests/test_gpu_pairing.py tests/test_gpu_fullsize.py tests/test_gpu_protocols.py -m gpu -q -x > $O/${T}_pytest.log 2>&1; tail -3 $O/${T}_pytest.log
+python tools/time_round.py 2>&1 | tail -6
+python tools/time_tipp.py 12 6 2>&1 | tail -2
+for lg in 14 15 16 18; do python tools/time_pairing.py $lg 2>&1 | tail -1; done
