@@ -178,8 +178,9 @@ def run_reference(args):
 
 def run_config5(args):
     """BASELINE configs[4]: scaling sweep of the two leaf inner products.  Each point is ONE instance of n elements
-    sharded by contiguous slices over the ranks: per-rank partial (Miller product without final exponentiation / MSM
-    point), one all-gather, combine on every rank.  CUDA events on the shared stream, max over ranks."""
+    sharded by contiguous slices over the ranks through the library's own entry points (ripp_pairing_ip_sharded_dev /
+    ripp_msm_g1_sharded_dev: per-rank partial, one ncclAllGather, combine on every rank).  CUDA events on the shared
+    stream, max over ranks."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -197,6 +198,10 @@ def run_config5(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        from ripp_b200.parallel import init_library_comm
+
+        init_library_comm(ctx)  # the sharded entry points run their all-gathers inside the library (comm.cu)
     imad_peak, _ = ctx.bench_imad(0, 4096)
     max_p, max_m = 20, 22
 
@@ -232,12 +237,7 @@ def run_config5(args):
         nl = n // world
 
         def pairing():
-            if world == 1:
-                ctx.pairing_ip_dev(a, b, nl, res.data_ptr())
-            else:
-                ctx.miller_partial_dev(a, b, nl, part.data_ptr())
-                dist.all_gather_into_tensor(gath, part)
-                ctx.gt_combine_dev(gath.data_ptr(), world, res.data_ptr())
+            ctx.pairing_ip_sharded_dev(a, b, nl, res.data_ptr())
 
         ms = timed(pairing)
         emit({"config": "BASELINE configs[4]", "op": "PairingInnerProduct", "log_n": lg, "n_gpus": world, "scaling": "strong",
@@ -256,12 +256,7 @@ def run_config5(args):
         nl = n // world
 
         def msm():
-            if world == 1:
-                ctx.msm_g1_dev(bases, sc, nl, rpt.data_ptr())
-            else:
-                ctx.msm_g1_dev(bases, sc, nl, ppt.data_ptr())
-                dist.all_gather_into_tensor(gpt, ppt)
-                ctx.seg_sum_dev(1, gpt.data_ptr(), world, 1, rpt.data_ptr())
+            ctx.msm_sharded_dev(1, bases, sc, nl, rpt.data_ptr())
 
         ms = timed(msm)
         emit({"config": "BASELINE configs[4]", "op": "MultiexponentiationInnerProduct<G1>", "log_n": lg, "n_gpus": world,

@@ -27,9 +27,10 @@ constexpr int OFF_F = OFF_LINE + 3 * FQ2W;  // Fq12 registers F0..F(nreg-1), the
 // per-pair block (a group can walk several pairs that share one accumulator, ark-ec's multi_miller_loop shape)
 constexpr int PB_T = 0;                   // running point T: x, y, z
 constexpr int PB_P = PB_T + 3 * FQ2W;     // xP, yP (Fq each)
-constexpr int PB_Q = PB_P + FQ2W;         // xQ, yQ
-constexpr int PB_VALID = PB_Q + 2 * FQ2W; // 1 = finite pair, 0 = contributes the constant line 1
-constexpr int PAIR_WORDS = PB_VALID + 8;
+constexpr int PB_QPTR = PB_P + FQ2W;      // address of Q (affine, global memory): read at the start and by the five
+                                          // addition steps only -- 192 B of shared memory per pair bought a third CTA per SM
+constexpr int PB_VALID = PB_QPTR + 2;     // 1 = finite pair, 0 = contributes the constant line 1
+constexpr int PAIR_WORDS = PB_QPTR + 8;   // 104 words
 RIPP_HD constexpr int group_words(int nreg, int npairs) { return OFF_F + nreg * F12W + npairs * PAIR_WORDS; }
 
 // W = 1: the coefficient's lane does the whole Fq2 arithmetic (throughput shape: five groups per warp).
@@ -225,6 +226,16 @@ RIPP_HD Fq2 f2_finish(const C& c, Acc1& A) {
   return {t0 - t1, t2 - t0 - t1};
 }
 
+// Q of a pair block (pointer stored as two words)
+RIPP_HD const uint32_t* pair_q(const uint32_t* pb) {
+  uint64_t a = (uint64_t)pb[PB_QPTR] | ((uint64_t)pb[PB_QPTR + 1] << 32);
+  return reinterpret_cast<const uint32_t*>(a);
+}
+RIPP_HD void set_pair_q(uint32_t* pb, const void* q) {
+  uint64_t a = (uint64_t)reinterpret_cast<uintptr_t>(q);
+  pb[PB_QPTR] = (uint32_t)a;
+  pb[PB_QPTR + 1] = (uint32_t)(a >> 32);
+}
 RIPP_HD Fq2 f2sel(bool c, const Fq2& a, const Fq2& b) {  // c ? a : b, branch-free
   Fq2 r;
 #pragma unroll
@@ -593,7 +604,8 @@ RIPP_HD void add_step(const C& c, uint32_t* pb) {
   uint32_t* R = c.sm + OFF_R;
   const int k = c.k;
   Fq2 x = ld2(T), y = ld2(T + FQ2W), z = ld2(T + 2 * FQ2W);
-  Fq2 qx = ld2(pb + PB_Q), qy = ld2(pb + PB_Q + FQ2W);
+  const uint32_t* Q = pair_q(pb);
+  Fq2 qx = ld2(Q), qy = ld2(Q + FQ2W);
   // round 1: R0 = qy z, R1 = qx z
   st2(R + k * FQ2W, f2mul(c, f2sel(k == 0, qy, qx), z));
   sync(c);
@@ -646,8 +658,9 @@ RIPP_HD void miller(const C& c, uint32_t* pairs, int npairs) {
   if (c.k == 0) {
     for (int j = 0; j < npairs; j++) {
       uint32_t* pb = pairs + j * PAIR_WORDS;
-      st2(pb + PB_T, ld2(pb + PB_Q));
-      st2(pb + PB_T + FQ2W, ld2(pb + PB_Q + FQ2W));
+      const uint32_t* Q = pair_q(pb);
+      st2(pb + PB_T, ld2(Q));
+      st2(pb + PB_T + FQ2W, ld2(Q + FQ2W));
       st2(pb + PB_T + 2 * FQ2W, Fq2::one());
     }
   }

@@ -19,6 +19,11 @@ struct Miller6Batch {
 constexpr int M6_NREG = 2;
 constexpr int M6_WARPS = 4;
 
+// the generator of G2 in global memory: Q of masked pairs (identities / padding) -- per device, written by
+// ripp_pairing6_init_device
+__device__ G2Aff g_g2_gen;
+__global__ void k_init_g2_gen() { g_g2_gen = g2_generator(); }
+
 // KP pairs per six-lane group share one accumulator (one Fq12 squaring per bit instead of KP):
 // KP = 1 minimises latency (late GIPA rounds), KP = 4 maximises throughput (long vectors).
 template <int WARPS, int KP>
@@ -26,8 +31,11 @@ __global__ void __launch_bounds__(32 * WARPS) k_miller6(Miller6Batch b, Fq12* __
   extern __shared__ __align__(16) uint32_t smem[];
   constexpr int GW = group_words(M6_NREG, KP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane / 6;
-  uint32_t* wsm = smem + warp * 6 * GW;  // five groups + one junk slot for lanes 30, 31
+  // five groups per warp; lanes 30, 31 MIRROR lanes 24, 25 (coefficients 0, 1 of group 4: same addresses, same values),
+  // so no sixth scratch slot is needed: 18.4 KB of shared memory per warp at KP = 4.  (Three CTAs per SM then fit, but the
+  // 168-register build that needs spills: Miller 2^16 19.5 -> 25.3 ms, measured; the room goes to more pairs per group.)
+  const int g = lane < 30 ? lane / 6 : 4;
+  uint32_t* wsm = smem + warp * 5 * GW;
   Ctx c{lane % 6, wsm + g * GW};
   uint32_t* pairs = c.sm + OFF_F + M6_NREG * F12W;
   const uint32_t gw = blockIdx.x * WARPS + warp;
@@ -37,12 +45,12 @@ __global__ void __launch_bounds__(32 * WARPS) k_miller6(Miller6Batch b, Fq12* __
     for (int j = 0; j < KP; j++) {
       const uint32_t i = (wl * 5 + g) * KP + j;
       G1Aff P = g1_generator();
-      G2Aff Q = g2_generator();
+      const G2Aff* Q = &g_g2_gen;
       uint32_t valid = 0;
-      if (g < 5 && seg < (uint32_t)b.nseg && i < b.n) {
+      if (seg < (uint32_t)b.nseg && i < b.n) {
         G1Aff p = b.p[seg][i];
-        G2Aff q = b.q[seg][i];
-        if (!p.is_inf() && !q.is_inf()) {
+        const G2Aff* q = &b.q[seg][i];
+        if (!p.is_inf() && !q->is_inf()) {
           P = p;
           Q = q;
           valid = 1;
@@ -50,8 +58,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_miller6(Miller6Batch b, Fq12* __
       }
       uint32_t* pb = pairs + j * PAIR_WORDS;
       st2(pb + PB_P, Fq2{P.x, P.y});
-      st2(pb + PB_Q, Q.x);
-      st2(pb + PB_Q + FQ2W, Q.y);
+      set_pair_q(pb, Q);
       pb[PB_VALID] = valid;
     }
   }
@@ -172,12 +179,12 @@ __global__ void __launch_bounds__(32 * M18_WARPS) k_miller18(Miller6Batch b, Fq1
     for (int j = 0; j < KP; j++) {
       const uint32_t i = wl * KP + j;
       G1Aff P = g1_generator();
-      G2Aff Q = g2_generator();
+      const G2Aff* Q = &g_g2_gen;
       uint32_t valid = 0;
       if (i < b.n) {
         G1Aff p = b.p[seg][i];
-        G2Aff q = b.q[seg][i];
-        if (!p.is_inf() && !q.is_inf()) {
+        const G2Aff* q = &b.q[seg][i];
+        if (!p.is_inf() && !q->is_inf()) {
           P = p;
           Q = q;
           valid = 1;
@@ -185,8 +192,7 @@ __global__ void __launch_bounds__(32 * M18_WARPS) k_miller18(Miller6Batch b, Fq1
       }
       uint32_t* pb = pairs + j * PAIR_WORDS;
       st2(pb + PB_P, Fq2{P.x, P.y});
-      st2(pb + PB_Q, Q.x);
-      st2(pb + PB_Q + FQ2W, Q.y);
+      set_pair_q(pb, Q);
       pb[PB_VALID] = valid;
     }
   }
@@ -346,7 +352,7 @@ int ripp_gt_multiexp_l6(ripp_ctx* ctx, const void* in, const void* sc, size_t n,
 
 template <int KP>
 static int launch_miller6(ripp_ctx* ctx, Miller6Batch& b, size_t n, Fq12* dst, size_t* nwarps_out) {
-  constexpr int SM = M6_WARPS * 6 * group_words(M6_NREG, KP) * 4;
+  constexpr int SM = M6_WARPS * 5 * group_words(M6_NREG, KP) * 4;
   b.wps = (uint32_t)((n + 5 * KP - 1) / (5 * KP));
   size_t nwarps = (size_t)b.wps * b.nseg;
   unsigned blocks = (unsigned)((nwarps + M6_WARPS - 1) / M6_WARPS);
@@ -439,14 +445,17 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
       CU(cudaGetDeviceProperties(&prop, ctx->device));
       sms = prop.multiProcessorCount;
     }
-    const size_t resident = (size_t)sms * 2 * M6_WARPS;  // two CTAs per SM (255 registers, ~100 KB of shared memory each)
+    const size_t resident = (size_t)sms * 2 * M6_WARPS;  // two CTAs per SM (255 registers)
     double best = 0;
     // many waves: CTAs are scheduled as others retire, the tail of the last wave is a small share -- most sharing wins
+    // (six or eight pairs per group fit the shared memory since Q left the pair block, but measured no better: 2^18 pairs
+    // 77.3 ms at kp = 4, 80.2 at 6, 78.9 at 8; 2^16: 19.7 / 19.4 / 23.8 ms)
     const bool many = (size_t)nseg * ((n + 19) / 20) >= 3 * resident;
     for (int k = 1; k <= 4 && !many; k++) {
+      const int ci = k - 1;
       size_t warps = (size_t)nseg * ((n + 5 * k - 1) / (5 * k));
       double t = (double)((warps + resident - 1) / resident) * (2040.0 + 3096.0 * k);
-      if (k == 1 || t <= best) {
+      if (ci == 0 || t <= best) {
         best = t;
         kp = k;
       }
@@ -508,11 +517,13 @@ int ripp_final_exp_l6(ripp_ctx* ctx, const void* in, uint32_t T, void* out, int 
 // Opt-in shared-memory sizes of the six-lane kernels: function attributes are per device, set once per context
 // creation (ripp_ctx_create) -- never from the launch paths, which run concurrently on several host threads.
 int ripp_pairing6_init_device() {
+  k_init_g2_gen<<<1, 1>>>();
+  CU(cudaGetLastError());
   CU(cudaFuncSetAttribute(k_reduce6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * R6_GROUP_WORDS * 4));
   CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
-  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 1) * 4));
-  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 2) * 4));
-  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 3) * 4));
-  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * group_words(M6_NREG, 4) * 4));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 5 * group_words(M6_NREG, 1) * 4));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 5 * group_words(M6_NREG, 2) * 4));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 5 * group_words(M6_NREG, 3) * 4));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 5 * group_words(M6_NREG, 4) * 4));
   return RIPP_OK;
 }

@@ -165,10 +165,8 @@ static void l6_miller(const uint32_t* p, const uint32_t* q, const int* valid, in
       for (int j = 0; j < npairs; j++) {
         uint32_t* pb = pairs + j * l6::PAIR_WORDS;
         G1Aff P = ld<G1Aff>(p + 24 * j);
-        G2Aff Q = ld<G2Aff>(q + 48 * j);
         l6::st2(pb + l6::PB_P, Fq2{P.x, P.y});
-        l6::st2(pb + l6::PB_Q, Q.x);
-        l6::st2(pb + l6::PB_Q + 24, Q.y);
+        l6::set_pair_q(pb, q + 48 * j);  // Q is read through its address (same words as a packed G2Aff)
         pb[l6::PB_VALID] = valid[j];
       }
     }
