@@ -58,9 +58,9 @@ int ripp_ctx_set_stream(ripp_ctx* ctx, void* cuda_stream);
 uint64_t ripp_ctx_launch_count(ripp_ctx* ctx);
 
 /* Per-category device-time accounting with CUDA events on the context's stream (off by default).
- * Categories: 0 Miller loops (+ Fq12 product tree), 1 final exponentiations, 2 MSMs, 3 folds,
- * 4 element-wise scalar muls, 5 other.  ripp_ctx_timing synchronises, returns the sums since the
- * last call (arrays of 6) and resets them. */
+ * Categories: 0 Miller loops (+ Fq12 product tree), 1 final exponentiations, 2 MSM bucket accumulation, 3 folds,
+ * 4 element-wise scalar muls, 5 other, 6 MSM digit recoding / sort, 7 MSM bucket reduction + window sums + Horner tail.
+ * ripp_ctx_timing synchronises, returns the sums since the last call (arrays of 8) and resets them. */
 int ripp_ctx_set_timing(ripp_ctx* ctx, int on);
 int ripp_ctx_timing(ripp_ctx* ctx, double* ms_by_cat, uint64_t* count_by_cat);
 

@@ -138,15 +138,15 @@ class Context:
     def set_stream(self, cuda_stream):
         check(lib().ripp_ctx_set_stream(self.handle, ctypes.c_void_p(int(cuda_stream) if cuda_stream else 0)))
 
-    TIMING_CATS = ("miller", "final_exp", "msm", "fold", "scale", "other")
+    TIMING_CATS = ("miller", "final_exp", "msm", "fold", "scale", "other", "msm_sort", "msm_reduce")
 
     def set_timing(self, on):
         check(lib().ripp_ctx_set_timing(self.handle, int(on)))
 
     def timing(self):
         """-> {category: (ms, scopes)} since the last call (synchronises)."""
-        ms = (ctypes.c_double * 6)()
-        cnt = (ctypes.c_uint64 * 6)()
+        ms = (ctypes.c_double * 8)()
+        cnt = (ctypes.c_uint64 * 8)()
         check(lib().ripp_ctx_timing(self.handle, ms, cnt))
         return {c: (ms[i], int(cnt[i])) for i, c in enumerate(self.TIMING_CATS)}
 

@@ -21,7 +21,10 @@ std::string& ripp_err_slot();
 #define RIPP_MAX_BATCH 8
 #define RIPP_MAX_CHILD 8
 // per-category device-time accounting (CUDA events on the context's stream; off by default)
-enum { RIPP_T_MILLER = 0, RIPP_T_FINAL_EXP, RIPP_T_MSM, RIPP_T_FOLD, RIPP_T_SCALE, RIPP_T_OTHER, RIPP_T_NCAT };
+// RIPP_T_MSM = the bucket accumulation kernels of an MSM (the algorithmic work); its sort and its reduction / Horner tail
+// are kernels of their own kind and are accounted separately
+enum { RIPP_T_MILLER = 0, RIPP_T_FINAL_EXP, RIPP_T_MSM, RIPP_T_FOLD, RIPP_T_SCALE, RIPP_T_OTHER, RIPP_T_MSM_SORT, RIPP_T_MSM_REDUCE,
+       RIPP_T_NCAT };
 struct TimingRec {
   int cat;
   cudaEvent_t a, b;
@@ -122,4 +125,7 @@ bool ripp_use_l6();
 // comm.cu: all-gather of one `bytes`-sized blob per rank on ctx's stream (recv = world * bytes, rank order); world == 1 copies
 int ripp_all_gather_internal(ripp_ctx* ctx, const void* send_dev, size_t bytes, void* recv_dev);
 void ripp_comm_release(ripp_ctx* ctx);
+// msm.cu: the (up to four) folds of one GIPA round in ONE launch when the vectors are short enough for lane teams
+int ripp_fold4_internal(ripp_ctx* ctx, const int* types, const void* const* hi, const void* const* lo, const void* const* cs, size_t n,
+                        void* const* out, int* fused);
 int ripp_pairing6_init_device();  // per-device kernel attributes; called by ripp_ctx_create with the device current

@@ -232,6 +232,41 @@ static void gipa_challenge(const Fr& prev, const Val* com, Fr* c, Fr* c_inv) {
   }
 }
 
+// gipa.rs:261-291 for one round: A <- A_R c + A_L, B <- B_R c^-1 + B_L, v <- v_R c^-1 + v_L, w <- w_R c + w_L, in place over
+// the lower halves.  Short vectors: ONE fused launch on ctx's stream; long ones: four kernels on four streams.
+static int fold_typed(ripp_ctx* ctx, int t, char* base, size_t split, const Fr& c);
+static int fold_round(ripp_ctx* ctx, const int* types, char* const* bases, size_t split, const Fr& c, const Fr& c_inv) {
+  const void *hi[4], *lo[4], *cs[4];
+  void* out[4];
+  int ty[4];
+  const Fr* sc[4] = {&c, &c_inv, &c_inv, &c};
+  for (int i = 0; i < 4; i++) {
+    ty[i] = (types[i] == VT_NONE || !bases[i]) ? 0 : (types[i] == VT_G1 ? 1 : (types[i] == VT_G2 ? 2 : 3));
+    lo[i] = bases[i];
+    hi[i] = bases[i] ? bases[i] + split * vt_size(types[i]) : nullptr;
+    out[i] = bases[i];
+    cs[i] = sc[i]->v;
+  }
+  int fused = 0;
+  OK(ripp_fold4_internal(ctx, ty, hi, lo, cs, split, out, &fused));
+  if (fused) return RIPP_OK;
+  ripp_ctx* k1 = ripp_child(ctx, 0);
+  ripp_ctx* k2 = ripp_child(ctx, 1);
+  ripp_ctx* k3 = ripp_child(ctx, 2);
+  if (!k1 || !k2 || !k3) return fail(RIPP_ERR_CUDA, "child context");
+  OK(ripp_fork(ctx, k1));
+  OK(ripp_fork(ctx, k2));
+  OK(ripp_fork(ctx, k3));
+  OK(fold_typed(ctx, types[0], bases[0], split, c));
+  OK(fold_typed(k1, types[1], bases[1], split, c_inv));
+  OK(fold_typed(k2, types[2], bases[2], split, c_inv));
+  OK(fold_typed(k3, types[3], bases[3], split, c));
+  OK(ripp_join(ctx, k1));
+  OK(ripp_join(ctx, k2));
+  OK(ripp_join(ctx, k3));
+  return RIPP_OK;
+}
+
 static int fold_typed(ripp_ctx* ctx, int t, char* base, size_t split, const Fr& c) {
   if (t == VT_NONE || !base) return RIPP_OK;  // HomomorphicPlaceholderValue: no-op (identity/mod.rs:18-30)
   char* hi = base + split * vt_size(t);
@@ -309,20 +344,9 @@ static int gipa_prove(ripp_ctx* ctx, const GipaSpec& sp, const void* a_in, const
     gipa_challenge(transcript.empty() ? (prev0 ? *prev0 : Fr::zero()) : transcript.back(), com.data(), &c, &c_inv);
     // gipa.rs:261-291 -- rescale
     {
-      ripp_ctx* k1 = ripp_child(ctx, 0);
-      ripp_ctx* k2 = ripp_child(ctx, 1);
-      ripp_ctx* k3 = ripp_child(ctx, 2);
-      if (!k1 || !k2 || !k3) return fail(RIPP_ERR_CUDA, "child context");
-      OK(ripp_fork(ctx, k1));
-      OK(ripp_fork(ctx, k2));
-      OK(ripp_fork(ctx, k3));
-      OK(fold_typed(ctx, sp.a, A, split, c));
-      OK(fold_typed(k1, sp.b, B, split, c_inv));
-      OK(fold_typed(k2, sp.v, V, split, c_inv));
-      OK(fold_typed(k3, sp.w, W, split, c));
-      OK(ripp_join(ctx, k1));
-      OK(ripp_join(ctx, k2));
-      OK(ripp_join(ctx, k3));
+      const int types[4] = {sp.a, sp.b, sp.v, sp.w};
+      char* const bases[4] = {A, B, V, W};
+      OK(fold_round(ctx, types, bases, split, c, c_inv));
     }
     steps.push_back(com);
     transcript.push_back(c);

@@ -4,6 +4,8 @@
 // (inner_products/src/lib.rs:123-142), PedersenCommitment::commit (pedersen/mod.rs:24-26), the KZG
 // opening MSMs (tipa/mod.rs:333-334), and the "rescale" maps of GIPA/SIPP (gipa.rs:261-291,
 // sipp/src/lib.rs:87-100; scalar-mul primitive `mul_helper`, ip_proofs/src/lib.rs:15-19).
+#include <optional>
+
 #include "common.cuh"
 #include "x3.cuh"
 #include "xt.cuh"
@@ -426,7 +428,6 @@ static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, A
     CU(cudaMemsetAsync(out, 0, sizeof(Aff<F>), ctx->stream));
     return RIPP_OK;
   }
-  TimeScope ts_(ctx, RIPP_T_MSM);
   if (!use_endo()) return msm_core<F>(ctx, bases, sc, n, out, 255, 1);
   const int m = sizeof(F) == sizeof(Fq) ? 2 : 4;
   void* ex;
@@ -434,8 +435,11 @@ static int msm_dev(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, A
   OK(scratch(ctx, 16, pts_bytes + (size_t)m * n * sizeof(Fr) + 256, &ex));
   Aff<F>* bases2 = (Aff<F>*)ex;
   Fr* canon2 = (Fr*)((char*)ex + pts_bytes);
-  k_msm_endo_expand<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(bases, sc, n, bases2, canon2, m);
-  LAUNCHED(ctx);
+  {
+    TimeScope ts_(ctx, RIPP_T_MSM_SORT);
+    k_msm_endo_expand<F><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(bases, sc, n, bases2, canon2, m);
+    LAUNCHED(ctx);
+  }
   return msm_core<F>(ctx, bases2, canon2, (size_t)m * n, out, m == 2 ? 128 : 64, 0);
 }
 
@@ -463,6 +467,8 @@ static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, 
   Jac<F>* fat_partials = (Jac<F>*)((char*)fatbuf + 64);
   FatItem* fat_items = (FatItem*)(fat_partials + max_items);
   FatBucket* fat_buckets = (FatBucket*)(fat_items + max_items);
+  std::optional<TimeScope> ts_;  // one accounting scope per kernel group: sort, accumulate, reduce
+  ts_.emplace(ctx, RIPP_T_MSM_SORT);
   CU(cudaMemsetAsync(fat_counters, 0, 64, st));
   CU(cudaMemsetAsync(counts, 0, WB * sizeof(uint32_t), st));
   k_msm_prepare<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, n, (Fr*)canon, counts, p.c, p.nw, is_mont);
@@ -489,6 +495,8 @@ static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, 
   // the scan leaves the start of each size class in its bin: the scatter advances them, bin 0 keeps the total
   k_msm_size_scatter<<<(unsigned)((WB + 255) / 256), 256, 0, st>>>(counts, WB, fat_threshold, size_hist, order);
   LAUNCHED(ctx);
+  ts_.reset();
+  ts_.emplace(ctx, RIPP_T_MSM);
   k_msm_accumulate<F><<<(unsigned)((WB + 127) / 128), 128, 0, st>>>(bases, (const uint32_t*)idx, offsets, counts,
                                                                    (Jac<F>*)bkt, order, size_hist);
   LAUNCHED(ctx);
@@ -500,6 +508,8 @@ static int msm_core(ripp_ctx* ctx, const Aff<F>* bases, const Fr* sc, size_t n, 
     k_msm_fat_combine<F><<<max_fat < 256u ? max_fat : 256u, 64, 0, st>>>(fat_counters, fat_buckets, fat_partials, (Jac<F>*)bkt);
     LAUNCHED(ctx);
   }
+  ts_.reset();
+  ts_.emplace(ctx, RIPP_T_MSM_REDUCE);
   size_t WT = (size_t)p.nw * p.T;
   Jac<F>* pa = (Jac<F>*)parts;
   Jac<F>* pb = pa + WT;
@@ -709,6 +719,104 @@ static size_t xt_max_n() {
     return e ? atol(e) : 2048L;
   }();
   return (size_t)v;
+}
+
+// ---- the folds of ONE GIPA round in ONE launch (gipa.rs:261-291: A, B, v, w rescaled together) ------------------
+// Up to four jobs (G1 / G2 on lane teams, Fr one thread per element); blocks [first_block, first_block + blocks) of the
+// grid belong to a job, so a block runs exactly one of the three bodies.  Same arithmetic as k_fold_xt / k_fr_fold.
+struct FoldJob {
+  int type;  // 0 = none, 1 = G1, 2 = G2, 3 = Fr
+  const void* hi;
+  const void* lo;
+  void* out;
+  uint32_t n, first_block;
+  EndoBits c;  // G1 / G2
+  Fr s;        // Fr
+};
+struct FoldJobs {
+  FoldJob j[4];
+};
+template <class F>
+__device__ __forceinline__ void fold_xt_body(uint32_t* bus, const FoldJob& job, uint32_t block) {
+  typedef xt::TeamOf<F> TO;
+  constexpr int AW4 = 4 * sizeof(Aff<F>) / 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vl = lane % (TO::LANES * TO::PER_WARP);
+  const int e = vl / TO::LANES;
+  size_t i = ((size_t)block * XT_WARPS + warp) * TO::PER_WARP + e;
+  const bool live = i < job.n && lane == vl;
+  if (i >= job.n) i = job.n - 1;
+  uint32_t* scratch = bus + (warp * TO::PER_WARP + e) * (2 * TO::BUS_WORDS + AW4);
+  xt::Team tm{vl % TO::LANES, scratch, 0, nullptr};
+  Jac<F> acc = xt::endo_mul<F>(tm, ((const Aff<F>*)job.hi)[i], job.c, scratch + 2 * TO::BUS_WORDS);
+  acc = xt::madd<F>(tm, acc, ((const Aff<F>*)job.lo)[i]);
+  Aff<F> o = xt::to_affine<F>(tm, acc);
+  if (live && tm.t == 0) ((Aff<F>*)job.out)[i] = o;
+}
+constexpr int FOLD4_BUS_WORDS_G1 = XT_WARPS * xt::TeamOf<Fq>::PER_WARP * (2 * xt::TeamOf<Fq>::BUS_WORDS + 4 * 24);
+constexpr int FOLD4_BUS_WORDS_G2 = XT_WARPS * xt::TeamOf<Fq2>::PER_WARP * (2 * xt::TeamOf<Fq2>::BUS_WORDS + 4 * 48);
+__global__ void __launch_bounds__(32 * XT_WARPS) k_fold4_xt(const FoldJobs jobs) {
+  __shared__ __align__(16) uint32_t bus[FOLD4_BUS_WORDS_G1 > FOLD4_BUS_WORDS_G2 ? FOLD4_BUS_WORDS_G1 : FOLD4_BUS_WORDS_G2];
+  int k = 0;
+#pragma unroll
+  for (int t = 1; t < 4; t++)
+    if (jobs.j[t].type && blockIdx.x >= jobs.j[t].first_block) k = t;
+  const FoldJob& job = jobs.j[k];
+  const uint32_t block = blockIdx.x - job.first_block;
+  if (job.type == 1) {
+    fold_xt_body<Fq>(bus, job, block);
+  } else if (job.type == 2) {
+    fold_xt_body<Fq2>(bus, job, block);
+  } else if (job.type == 3) {
+    size_t i = (size_t)block * blockDim.x + threadIdx.x;
+    if (i < job.n) ((Fr*)job.out)[i] = ((const Fr*)job.hi)[i] * job.s + ((const Fr*)job.lo)[i];
+  }
+}
+// types[t] in {0 none, 1 G1, 2 G2, 3 Fr}; out[t][i] = hi[t][i] * c[t] + lo[t][i].  Returns RIPP_OK and *fused = 1 when the
+// fused launch was used (all vectors short enough for lane teams), *fused = 0 when the caller should fold one by one.
+int ripp_fold4_internal(ripp_ctx* ctx, const int* types, const void* const* hi, const void* const* lo, const void* const* cs, size_t n,
+                        void* const* out, int* fused) {
+  *fused = 0;
+  if (fold_mode() != 0 || n == 0 || n > xt_max_n()) return RIPP_OK;
+  CU(cudaSetDevice(ctx->device));
+  FoldJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  uint32_t nblocks = 0;
+  int nj = 0;
+  for (int t = 0; t < 4; t++) {
+    if (!types[t] || !hi[t]) continue;
+    FoldJob& j = jobs.j[nj++];
+    j.type = types[t];
+    j.hi = hi[t];
+    j.lo = lo[t];
+    j.out = out[t];
+    j.n = (uint32_t)n;
+    j.first_block = nblocks;
+    uint32_t blocks;
+    if (types[t] == 1) {
+      j.c = endo_bits<Fq>(cs[t]);
+      uint32_t warps = (uint32_t)((n + xt::TeamOf<Fq>::PER_WARP - 1) / xt::TeamOf<Fq>::PER_WARP);
+      blocks = (warps + XT_WARPS - 1) / XT_WARPS;
+    } else if (types[t] == 2) {
+      j.c = endo_bits<Fq2>(cs[t]);
+      uint32_t warps = (uint32_t)((n + xt::TeamOf<Fq2>::PER_WARP - 1) / xt::TeamOf<Fq2>::PER_WARP);
+      blocks = (warps + XT_WARPS - 1) / XT_WARPS;
+    } else {
+      memcpy(j.s.v, cs[t], sizeof(Fr));
+      blocks = (uint32_t)((n + 32 * XT_WARPS - 1) / (32 * XT_WARPS));
+    }
+    nblocks += blocks;
+  }
+  if (!nj) {
+    *fused = 1;
+    return RIPP_OK;
+  }
+  // jobs are packed at the front of the array in launch order: unused slots keep type 0
+  TimeScope ts_(ctx, RIPP_T_FOLD);
+  k_fold4_xt<<<nblocks, 32 * XT_WARPS, 0, ctx->stream>>>(jobs);
+  LAUNCHED(ctx);
+  *fused = 1;
+  return RIPP_OK;
 }
 
 template <class F, class XF>

@@ -193,18 +193,11 @@ static int sharded_rounds(ripp_ctx* ctx, ShardedInst* in, int ninst, size_t m, s
       gipa_challenge(in[i].transcript.empty() ? Fr::zero() : in[i].transcript.back(), com.data(), &c, &c_inv);
       ripp_ctx* cx = in[i].cx;
       OK(ripp_fork(ctx, cx));
-      ripp_ctx *k1 = ripp_child(cx, 0), *k2 = ripp_child(cx, 1), *k3 = ripp_child(cx, 2);
-      if (!k1 || !k2 || !k3) return fail(RIPP_ERR_CUDA, "child context");
-      OK(ripp_fork(cx, k1));
-      OK(ripp_fork(cx, k2));
-      OK(ripp_fork(cx, k3));
-      OK(fold_typed(cx, sp.a, in[i].A, split, c));
-      OK(fold_typed(k1, sp.b, in[i].B, split, c_inv));
-      OK(fold_typed(k2, sp.v, in[i].V, split, c_inv));
-      OK(fold_typed(k3, sp.w, in[i].W, split, c));
-      OK(ripp_join(cx, k1));
-      OK(ripp_join(cx, k2));
-      OK(ripp_join(cx, k3));
+      {
+        const int types[4] = {sp.a, sp.b, sp.v, sp.w};
+        char* const bases[4] = {in[i].A, in[i].B, in[i].V, in[i].W};
+        OK(fold_round(cx, types, bases, split, c, c_inv));
+      }
       OK(ripp_join(ctx, cx));
       in[i].steps.push_back(com);
       in[i].transcript.push_back(c);

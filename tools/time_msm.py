@@ -13,4 +13,4 @@ for logn in [int(x) for x in sys.argv[1:]] or [18]:
         dt = time.time() - t0
     ctx.set_timing(True); ctx.timing(); l0 = ctx.launches
     ctx.msm_g1_dev(bases, sc, n, out); tm = ctx.timing(); ctx.set_timing(False)
-    print("msm g1 n=2^%d: %.2f ms wall, %.2f ms device, %d launches" % (logn, 1e3 * dt, tm["msm"][0], ctx.launches - l0))
+    print("msm g1 n=2^%d: %.2f ms wall, %.2f ms device, %d launches" % (logn, 1e3 * dt, sum(tm[k][0] for k in ("msm", "msm_sort", "msm_reduce")), ctx.launches - l0))
