@@ -56,7 +56,9 @@ CLASS_KERNEL = {
     "msm_sort": ("k_msm_endo_expand / prepare / scan / scatter / size sort", "msm_sort"),
     "msm_reduce": ("k_msm_bucket_reduce + k_msm_window_sum + k_msm_horner_xt (bucket reduction and Horner tail)", "msm_reduce"),
     "fold": ("k_fold4_xt (the four folds of a round in one launch: A' = A_R c + A_L, ..., gipa.rs:261-291) / k_fold_endo", "fold"),
-    "miller": ("k_miller6 / k_miller18 + Fq12 product tree (cfg_multi_pairing, inner_products/src/lib.rs:77-116)", "miller6"),
+    # the class's most frequent launch in the 2^12 aggregation is k_miller18<1> (18 of 26): its capture gives `traffic`;
+    # the throughput kernel k_miller6<4,4> at 2^16 pairs has its own capture under roofline["miller_2^16"]
+    "miller": ("k_miller18 / k_miller6 + Fq12 product tree (cfg_multi_pairing, inner_products/src/lib.rs:77-116)", "miller18"),
     "final_exp": ("k_final_exp18", "fexp"),
     "msm": ("k_msm_accumulate + fat-bucket kernels (bucket accumulation of the variable-base MSM)", "msm_acc"),
     "scale": ("k_scale_parts + k_scale_combine (a_i r^i, ck_i r^-i: groth16_aggregation.rs:118-131)", "scale"),

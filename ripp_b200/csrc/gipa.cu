@@ -864,12 +864,23 @@ extern "C" int ripp_sipp_prove(ripp_ctx* ctx, const void* a_aff, const void* b_a
     Fr x = rng.next_u128();          // lib.rs:85
     Fr x_inv = x.inv();
     // lib.rs:87-100: a <- a_R x + a_L ; b <- b_R x^-1 + b_L   (on two streams)
-    ripp_ctx* kid = ripp_child(ctx, 0);
-    if (!kid) return fail(RIPP_ERR_CUDA, "child context");
-    OK(ripp_fork(ctx, kid));
-    OK(ripp_g1_fold_dev(ctx, Av + len * 96, Av, x.v, len, Av));
-    OK(ripp_g2_fold_dev(kid, Bv + len * 192, Bv, x_inv.v, len, Bv));
-    OK(ripp_join(ctx, kid));
+    {
+      const int ty[4] = {1, 2, 0, 0};
+      const void* hi[4] = {Av + len * 96, Bv + len * 192, nullptr, nullptr};
+      const void* lo[4] = {Av, Bv, nullptr, nullptr};
+      const void* cs[4] = {x.v, x_inv.v, nullptr, nullptr};
+      void* outp[4] = {Av, Bv, nullptr, nullptr};
+      int fused = 0;
+      OK(ripp_fold4_internal(ctx, ty, hi, lo, cs, len, outp, &fused));  // both folds in one launch when short enough
+      if (!fused) {
+        ripp_ctx* kid = ripp_child(ctx, 0);
+        if (!kid) return fail(RIPP_ERR_CUDA, "child context");
+        OK(ripp_fork(ctx, kid));
+        OK(ripp_g1_fold_dev(ctx, Av + len * 96, Av, x.v, len, Av));
+        OK(ripp_g2_fold_dev(kid, Bv + len * 192, Bv, x_inv.v, len, Bv));
+        OK(ripp_join(ctx, kid));
+      }
+    }
   }
   CU(cudaStreamSynchronize(ctx->stream));
   return copy_out(proof, proof_out, proof_cap, proof_len);
