@@ -290,6 +290,23 @@ int ripp_tipp_aggregate_sharded_dev(ripp_ctx* ctx, const void* srs_g1_dev, const
                                     const void* b_dev, const void* c_dev, size_t n_total, size_t tail_len,
                                     uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
 
+/* ---- BLS12-377: the reference's own SIPP instantiation ------------------------------------- */
+/* `SIPP<Bls12_377, Blake2s>` (sipp/src/lib.rs:228-254, sipp/examples/scaling-ipp.rs:10) on the second parameter set
+ * (csrc/bls377.cuh: Fq2 non-residue -5, xi = u, D-type twist, x > 0; ark-ec's default little-endian point
+ * serialisation in the Fiat-Shamir seed).  Same conventions as the BLS12-381 entry points: host pointers, Montgomery
+ * limbs (12 x 32 bits for the 377-bit Fq, 8 x 32 for the 253-bit Fr), affine points packed x | y (G1 96 B, G2 192 B,
+ * identity = all zero), GT = 576 B in arkworks' tower order; proof = log2(n) pairs (z_l, z_r), serialize_uncompressed.
+ * One thread per pairing / element: the correctness port of the curve (bit-exact against oracle/bls12_377.py); the
+ * lane-role throughput engines are specialised on BLS12-381. */
+int ripp377_pairing_ip_affine(ripp_ctx* ctx, const void* g1_aff, size_t n_left, const void* g2_aff, size_t n_right,
+                              void* gt_out);
+int ripp377_sipp_product_with_coeffs(ripp_ctx* ctx, const void* a_aff, const void* b_aff, const void* r, size_t n,
+                                     void* gt_out);
+int ripp377_sipp_prove(ripp_ctx* ctx, const void* a_aff, const void* b_aff, const void* r, size_t n, const void* value_gt,
+                       uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+int ripp377_sipp_verify(ripp_ctx* ctx, const void* a_aff, const void* b_aff, const void* r, size_t n, const void* value_gt,
+                        const uint8_t* proof, size_t proof_len, int* accept);
+
 /* ---- verifiers ----------------------------------------- */
 /* All arithmetic of the verifiers runs on the GPU (GT multi-exponentiation, MSMs, pairings); the host
  * recomputes the Fiat-Shamir chain from the proof bytes.  Inputs are arkworks serialize_uncompressed

@@ -444,6 +444,33 @@ class Context:
                                      ctypes.c_size_t(len(proof)), ctypes.byref(acc)))
         return bool(acc.value)
 
+    # ---- BLS12-377 (csrc/sipp377.cu): SIPP on the reference's own curve ----------------------------
+    def pairing_ip_affine_377(self, g1, g2):
+        out = np.empty(144, dtype=np.uint32)
+        check(lib().ripp377_pairing_ip_affine(self.handle, _p(g1), ctypes.c_size_t(len(g1)), _p(g2), ctypes.c_size_t(len(g2)), _p(out)))
+        return out
+
+    def sipp_product_with_coeffs_377(self, a, b, r):
+        out = np.empty(144, dtype=np.uint32)
+        check(lib().ripp377_sipp_product_with_coeffs(self.handle, _p(a), _p(b), _p(r), ctypes.c_size_t(len(a)), _p(out)))
+        return out
+
+    def sipp_prove_377(self, a, b, r, value):
+        n = len(a)
+        cap = max(n.bit_length() - 1, 0) * 1152 + 16
+        proof = np.empty(cap, dtype=np.uint8)
+        plen = ctypes.c_size_t()
+        check(lib().ripp377_sipp_prove(self.handle, _p(a), _p(b), _p(r), ctypes.c_size_t(n), _p(value), _p(proof),
+                                       ctypes.c_size_t(cap), ctypes.byref(plen)))
+        return proof[: plen.value].tobytes()
+
+    def sipp_verify_377(self, a, b, r, value, proof):
+        acc = ctypes.c_int(0)
+        pb = self._bytes(proof)
+        check(lib().ripp377_sipp_verify(self.handle, _p(a), _p(b), _p(r), ctypes.c_size_t(len(a)), _p(value), _p(pb),
+                                        ctypes.c_size_t(len(proof)), ctypes.byref(acc)))
+        return bool(acc.value)
+
     # ---- diagnostics ----------------------------------------------------------------------
     def test_elementwise(self, op, a, b, out_words):
         a = np.ascontiguousarray(a, dtype=np.uint32)
