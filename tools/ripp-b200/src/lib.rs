@@ -9,6 +9,7 @@
 //!   `TIPA::prove_with_srs_shift`, `TIPAWithSSM::prove_with_structured_scalar_message`, `aggregate_proofs`,
 //!   `verify_aggregate_proof`, `TIPA::setup` for given trapdoors.
 //! * [`sipp`] -- `SIPP::prove` / `verify` / `product_of_pairings_with_coeffs` (`sipp/src/lib.rs`; BLS12-381 + Blake2s).
+//! * [`sipp377`] -- the same three on the reference's own curve, `SIPP<Bls12_377, Blake2s>` (`sipp/src/lib.rs:228-254`).
 //!
 //! Every value crosses the C ABI as the Montgomery limbs arkworks already holds (`Fp.0 .0`: little-endian `u64`
 //! limbs, R = 2^(64 N) -- the same bytes as the ABI's 32-bit limbs on a little-endian host) or as arkworks' own
@@ -20,6 +21,7 @@ pub mod inner_products;
 pub mod pack;
 pub mod resident;
 pub mod sipp;
+pub mod sipp377;
 
 use ripp_b200_sys as sys;
 use std::ffi::CStr;
