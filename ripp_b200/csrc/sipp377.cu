@@ -262,8 +262,13 @@ extern "C" int ripp377_sipp_prove(ripp_ctx* ctx, const void* a_aff, const void* 
   while (len != 1) {
     len /= 2;
     // lib.rs:77-78: z_l = prod e(a_R, b_L), z_r = prod e(a_L, b_R)
+    // the two products run concurrently (second one on a child context: own stream and scratch)
+    ripp_ctx* kid = ripp_child(ctx, 0);
+    if (!kid) return fail(RIPP_ERR_CUDA, "child context");
+    OK(ripp_fork(ctx, kid));
+    OK(pairing_product(kid, (const G1A7*)Av, (const G2A7*)(Bv + len * 192), len, res + 576));
     OK(pairing_product(ctx, (const G1A7*)(Av + len * 96), (const G2A7*)Bv, len, res));
-    OK(pairing_product(ctx, (const G1A7*)Av, (const G2A7*)(Bv + len * 192), len, res + 576));
+    OK(ripp_join(ctx, kid));
     uint8_t z[2 * 576];
     CU(cudaMemcpyAsync(z, res, 2 * 576, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
