@@ -64,3 +64,57 @@ def test_sipp_round_trip_and_tamper():
     bad = list(proof)
     bad[1] = (bad[1][1], bad[1][0])
     assert not S.sipp_verify(a, b, r, z, bad)
+
+
+# ---- the BLS12-377 device headers compiled for the host (tests/hostsim/hostsim377.cpp) against this oracle ----------
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def hs377():
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim377.cpp")
+    so = os.path.join(ROOT, "tests", "hostsim", "_hostsim377.so")
+    csrc = os.path.join(ROOT, "ripp_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
+    return ctypes.CDLL(so)
+
+
+def _call(lib, fn, *args, out):
+    o = np.zeros(out, dtype=np.uint32)
+    keep = [np.ascontiguousarray(a, dtype=np.uint32) if isinstance(a, np.ndarray) else a for a in args]
+    cargs = [ctypes.c_void_p(a.ctypes.data) if isinstance(a, np.ndarray) else a for a in keep]
+    getattr(lib, fn)(*cargs, ctypes.c_void_p(o.ctypes.data))
+    return o
+
+
+def test_device_headers_on_host_match_oracle(hs377):
+    """Miller loop on the D-type twist + final exponentiation, the Granger-Scott squaring, both scalar multiplications and
+    the Fr inversion of bls377.cuh, executed on the CPU with the emulated carry flag, equal the big-int oracle."""
+    from ripp_b200 import sipp_377 as G
+
+    p, q = E.g1_mul(E.G1_GEN, 12345), E.g2_mul(E.G2_GEN, 6789)
+    ep, eq = G.g1_vec_enc([p])[0], G.g2_vec_enc([q])[0]
+    assert G.gt_dec(_call(hs377, "hs377_pairing", ep, eq, 1, out=144)) == E.pairing(p, q)
+    m = G.gt_dec(_call(hs377, "hs377_pairing", ep, eq, 0, out=144))
+    assert E.final_exponentiation(m) == E.pairing(p, q)  # Miller values may differ by subfield factors; the pairing may not
+    s = rnd.randrange(E.R)
+    sw = np.frombuffer(s.to_bytes(32, "little"), dtype=np.uint32)
+    got = _call(hs377, "hs377_g1_mul", ep, sw, out=24)
+    assert (G.fq_dec(got[:12]), G.fq_dec(got[12:])) == E.g1_mul(p, s)
+    got = _call(hs377, "hs377_g2_mul", eq, sw, out=48)
+    assert ((G.fq_dec(got[:12]), G.fq_dec(got[12:24])), (G.fq_dec(got[24:36]), G.fq_dec(got[36:]))) == E.g2_mul(q, s)
+    z = E.pairing(p, q)  # in the cyclotomic subgroup
+    both = _call(hs377, "hs377_cyc_sqr", G.gt_enc(z), out=288)
+    assert G.gt_dec(both[:144]) == G.gt_dec(both[144:]) == E.f12_sqr(z)
+    a = rnd.randrange(1, E.R)
+    inv = _call(hs377, "hs377_fr_inv", np.frombuffer((a * (1 << 256) % E.R).to_bytes(32, "little"), dtype=np.uint32), out=8)
+    assert int.from_bytes(inv.tobytes(), "little") * pow(1 << 256, -1, E.R) % E.R == pow(a, -1, E.R)
