@@ -27,8 +27,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_variant_paths(env):
     sel = ["tests/test_gpu_msm.py::test_folds", "tests/test_gpu_msm.py::test_scalings_match_oracle",
            "tests/test_gpu_msm.py::test_msm_g1_matches_oracle", "tests/test_gpu_pairing.py::test_pairing_ip_matches_oracle",
-           "tests/test_gpu_protocols.py::test_aggregate_proofs_bytes_match_oracle",
-           "tests/test_gpu_fullsize.py::test_pairing_product_engine_shapes_match_cpu_oracle"]
+           "tests/test_gpu_protocols.py::test_aggregate_proofs_bytes_match_oracle"]
+    if any(k.startswith("RIPP_B200_L18") for k in env):  # the pairing engine's shape thresholds: the sizes that cross them
+        sel.append("tests/test_gpu_fullsize.py::test_pairing_product_engine_shapes_match_cpu_oracle")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu"] + sel, cwd=ROOT, env=dict(os.environ, **env),
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
