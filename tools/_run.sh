@@ -1,3 +1,4 @@
-O=gpurun_out; T=r2y; N=$1
-python -m pytest tests/test_gpu_multi.py -m gpu -q > $O/${T}_pytest_mgpu_${N}.log 2>&1; tail -3 $O/${T}_pytest_mgpu_${N}.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus $N --steps 5 --warmup 3 > $O/${T}_bench_${N}gpu.json 2> $O/${T}_bench_${N}gpu.err; tail -c 700 $O/${T}_bench_${N}gpu.json; tail -2 $O/${T}_bench_${N}gpu.err
+O=gpurun_out; T=r2z; N=$1
+if [ "$N" = "1" ]; then python bench.py --config5 > $O/${T}_config5_1gpu.jsonl 2> $O/${T}_config5_1gpu.err; else
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus $N --config5 > $O/${T}_config5_${N}gpu.jsonl 2> $O/${T}_config5_${N}gpu.err; fi
+tail -3 $O/${T}_config5_${N}gpu.jsonl | cut -c1-250; tail -2 $O/${T}_config5_${N}gpu.err
