@@ -79,3 +79,31 @@ def test_sipp(golden):
     assert S.ser_gt(z) == golden["sipp_n8_value"]
     if "sipp_n8_proof" in golden:
         assert O.ser_sipp_proof(O.sipp_prove(a, b, r, z)) == golden["sipp_n8_proof"]
+
+
+def test_sipp_bls12_377(golden):
+    """The reference's own SIPP curve.  The goldens carry arkworks' two generators; inputs are scalar(tag, i) * generator."""
+    from oracle import bls12_377 as E7
+    from oracle import sipp_377 as S7
+
+    if "bls12_377_sipp_n8_value" not in golden:
+        pytest.skip("golden file predates the BLS12-377 section of tools/ark_golden")
+
+    def fq(b):
+        return int.from_bytes(b, "little")
+
+    g1b, g2b = golden["bls12_377_g1_generator"], golden["bls12_377_g2_generator"]
+    g1 = (fq(g1b[:48]), fq(g1b[48:95] + bytes([g1b[95] & 0x3F])))
+    g2 = ((fq(g2b[:48]), fq(g2b[48:96])), (fq(g2b[96:144]), fq(g2b[144:191] + bytes([g2b[191] & 0x3F]))))
+    assert E7.g1_is_on_curve(g1) and E7.g2_is_on_curve(g2)
+    assert E7.ser_g1(g1) == g1b and E7.ser_g2(g2) == g2b  # the flag convention of ark-ec's default serialisation
+    assert g1 == E7.G1_GEN  # the derived generator is arkworks' generator
+    sc = lambda tag: [OS.scalar(tag, i) % E7.R for i in range(N)]
+    a = [E7.g1_mul(g1, s) for s in sc("s377-a")]
+    b = [E7.g2_mul(g2, s) for s in sc("s377-b")]
+    r = sc("s377-r")
+    assert E7.ser_g1(a[0]) == golden["bls12_377_g1_s377-a_0"] and E7.ser_g2(b[0]) == golden["bls12_377_g2_s377-b_0"]
+    z = S7.product_of_pairings_with_coeffs(a, b, r)
+    assert E7.ser_gt(z) == golden["bls12_377_sipp_n8_value"]
+    if "bls12_377_sipp_n8_proof" in golden:
+        assert S7.ser_proof(S7.sipp_prove(a, b, r, z)) == golden["bls12_377_sipp_n8_proof"]

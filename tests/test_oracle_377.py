@@ -27,7 +27,8 @@ def test_generators_and_twist():
     assert E.g2_is_on_curve(E.G2_GEN) and E._mul_raw(E.G2_GEN, E.R, E.g2_add) is None
     assert E.f2_mul(E.B2, E.XI) == E.F2_ONE  # D-type twist: b' = b / xi
     # the derived G1 generator is the one arkworks uses for BLS12-377 (x coordinate recalled from ark-bls12-377)
-    assert hex(E.G1_GEN[0]).startswith("0x8848defe740a67c8fc6225bf87ff5485951e2caa9d41bb188282c8bd37cb5cd5481512ffcd394eeab9b16eb21be9ef")
+    assert E.G1_GEN[0] == 0x008848DEFE740A67C8FC6225BF87FF5485951E2CAA9D41BB188282C8BD37CB5CD5481512FFCD394EEAB9B16EB21BE9EF
+    assert E.G1_GEN[1] == 0x01914A69C5102EFF1F674F5D30AFEEC4BD7FB348CA3E52D96D182AD44FB82305C2FE3D3634A9591AFD82DE55559C8EA6
 
 
 def test_pairing_bilinear_nondegenerate_order_r():

@@ -146,6 +146,44 @@ fn main() {
         out.push(("sipp_n8_proof".into(), pb.iter().map(|x| format!("{:02x}", x)).collect()));
     }
 
+    // SIPP on the reference's OWN curve, BLS12-377 + Blake2s (sipp/src/lib.rs:228-254).  The goldens are self-describing:
+    // the two generators are dumped, the inputs are scalar(tag, i) * generator with the same 31-byte scalars.
+    {
+        use ark_bls12_377::{Bls12_377, Fr as Fr7, G1Projective as G17, G2Projective as G27};
+        let sc7 = |tag: &str, n: usize| -> Vec<Fr7> {
+            (0..n as u64)
+                .map(|i| {
+                    let mut h = Blake2b::new();
+                    h.update(b"ripp-b200/");
+                    h.update(tag.as_bytes());
+                    h.update(&0u64.to_le_bytes());
+                    h.update(&i.to_le_bytes());
+                    Fr7::from_le_bytes_mod_order(&h.finalize()[..31])
+                })
+                .collect()
+        };
+        out.push(("bls12_377_g1_generator".into(), hex(&G17::generator().into_affine())));
+        out.push(("bls12_377_g2_generator".into(), hex(&G27::generator().into_affine())));
+        let a7: Vec<_> = sc7("s377-a", N).iter().map(|s| (G17::generator() * s).into_affine()).collect();
+        let b7: Vec<_> = sc7("s377-b", N).iter().map(|s| (G27::generator() * s).into_affine()).collect();
+        let r7 = sc7("s377-r", N);
+        out.push(("bls12_377_g1_s377-a_0".into(), hex(&a7[0])));
+        out.push(("bls12_377_g2_s377-b_0".into(), hex(&b7[0])));
+        let z7 = product_of_pairings_with_coeffs::<Bls12_377>(&a7, &b7, &r7);
+        out.push(("bls12_377_sipp_n8_value".into(), hex(&z7)));
+        let proof7 = SIPP::<Bls12_377, Blake2s>::prove(&a7, &b7, &r7, z7).unwrap();
+        assert!(SIPP::<Bls12_377, Blake2s>::verify(&a7, &b7, &r7, z7, &proof7).unwrap());
+        #[cfg(feature = "sipp-proof")]
+        {
+            let mut pb = Vec::new();
+            for (l, r) in proof7.gt_elems.iter() {
+                l.serialize_uncompressed(&mut pb).unwrap();
+                r.serialize_uncompressed(&mut pb).unwrap();
+            }
+            out.push(("bls12_377_sipp_n8_proof".into(), pb.iter().map(|x| format!("{:02x}", x)).collect()));
+        }
+    }
+
     // AggregateProof has private fields and no CanonicalSerialize (groth16_aggregation.rs:58-66): its parts are
     // covered by the two TIPA goldens above; add `#[derive(CanonicalSerialize)]` upstream to dump it whole.
     println!("{{");
