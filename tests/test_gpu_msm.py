@@ -161,3 +161,29 @@ def test_scalings_match_oracle(ctx, n):
     assert C.g1_vec_dec(out.download((n, 24))) == [E.g1_mul(E.G1_GEN, k) for k in s]
     ctx.g2_scale_dev(None, ds, n, out)
     assert C.g2_vec_dec(out.download((n, 48))) == [E.g2_mul(E.G2_GEN, k) for k in s]
+
+
+def test_msm_random_small_instances(ctx):
+    """Randomised differential test of the MSM plan (signed digits, size-sorted buckets, fat path, lane-team Horner):
+    a dozen G1 instances of random length with duplicated points, P / -P pairs, zero / one / r - 1 / short scalars and
+    identities sprinkled in, each compared with the oracle's sum of scalar multiplications."""
+    r2 = random.Random(20261017)
+    base = OS.g1_points("m-rand", 40)
+    for it in range(12):
+        n = r2.choice([1, 2, 3, 7, 31, 32, 33, 64, 100, 157, 200])
+        pts, sc = [], []
+        for i in range(n):
+            p = base[r2.randrange(len(base))]
+            kind = r2.randrange(10)
+            if kind == 0:
+                p = None
+            elif kind == 1:
+                p = E.g1_neg(p)
+            s = r2.choice([0, 1, E.R - 1, r2.randrange(1 << 64), r2.randrange(1 << 128), r2.randrange(E.R), r2.randrange(E.R)])
+            pts.append(p)
+            sc.append(s)
+        d_p, d_s = ctx.to_device(C.g1_vec_enc(pts)), ctx.to_device(C.fr_vec_enc(sc))
+        out = ctx.alloc(96)
+        ctx.msm_g1_dev(d_p, d_s, n, out)
+        ctx.sync()
+        assert C.g1_dec(out.download(24)) == E.msm(pts, sc, E.g1_add, E.g1_mul), "instance %d (n = %d)" % (it, n)
