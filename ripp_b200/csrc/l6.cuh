@@ -41,6 +41,8 @@ RIPP_HD constexpr int group_words(int nreg, int npairs) { return OFF_F + nreg * 
 // the final exponentiation and the verifier's GT powers this is a ~2.5x shorter chain at no extra pipe time.
 // The three lanes of a coefficient hold identical Fq2 state; partial products are exchanged through `bus`.
 constexpr int BUS_WORDS = 6 * 3 * 12;  // one Fq per (coefficient, role); two buffers are used alternately
+constexpr int BUS_ZERO = 2 * BUS_WORDS;   // twelve words that stay zero: the padding operand of the address-driven sums below
+constexpr int BUS_TOTAL = BUS_ZERO + 16;  // what a W = 3 group reserves behind its registers
 template <int W_>
 struct CtxT {
   static constexpr int W = W_;
@@ -48,7 +50,7 @@ struct CtxT {
   uint32_t* sm;   // group scratch
   void* bar;      // host build (tests/hostsim): barrier object; unused on the device
   int role;       // W = 3: Karatsuba role of this lane, 0..2
-  uint32_t* bus;  // W = 3: 2 * BUS_WORDS words of the group's scratch
+  uint32_t* bus;  // W = 3: BUS_TOTAL words of the group's scratch (zero slot cleared by whoever builds the context)
   mutable int par;  // W = 3: which bus buffer the next exchange uses
 };
 using Ctx = CtxT<1>;
@@ -121,13 +123,25 @@ RIPP_HD void gather3(const C& c, const Fq& mine, Fq& t0, Fq& t1, Fq& t2) {
   t1 = ld1(b + 12);
   t2 = ld1(b + 24);
 }
+// c0 + c1 over the integers (< 2p < 2^382): operand of the Karatsuba cross product
+RIPP_HD void add_unreduced(uint32_t* s, const Fq& a, const Fq& b) {
+  using namespace limb;
+  add_cc(s[0], a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) addc_cc(s[i], a.v[i], b.v[i]);
+  addc(s[11], a.v[11], b.v[11]);
+}
 // One out-of-line copy of the Fq2 product on the device (operands by value, in registers) instead of an inlined
 // copy per use: the Miller loop body drops from 24 k to 18 k instructions (2^16 pairs: 21.4 -> 21.1 ms, small
 // batches 3.0 -> 2.7 ms: fewer instruction-cache misses for the lone warps of the late GIPA rounds).
 RIPP_HD Fq2 f2mul_body(const Fq2& a, const Fq2& b) { return fq2_mul_lazy(a, b); }  // two reductions, not three (tower.cuh)
 // the role's Karatsuba product of a b (W = 3); the caller exchanges the three and combines
+// (the cross operands stay unreduced, < 2p each: the product is < 4 p^2 / R + p < 2p, which the final subtraction handles)
 RIPP_HD Fq f2mul_part_body(const Fq2& a, const Fq2& b, int role) {
-  return fqmul(sel3(role, a.c0, a.c1, a.c0 + a.c1), sel3(role, b.c0, b.c1, b.c0 + b.c1));
+  Fq sa, sb;
+  add_unreduced(sa.v, a.c0, a.c1);
+  add_unreduced(sb.v, b.c0, b.c1);
+  return fqmul(sel3(role, a.c0, a.c1, sa), sel3(role, b.c0, b.c1, sb));
 }
 #if defined(__CUDA_ARCH__) && !defined(RIPP_L6_INLINE_F2MUL)
 static __device__ __noinline__ Fq2 f2mul_fn(Fq2 a, Fq2 b) { return f2mul_body(a, b); }
@@ -166,14 +180,6 @@ RIPP_HD void acc_zero(Acc3& A) {
 RIPP_HD void acc_zero(Acc1& A) {
 #pragma unroll
   for (int i = 0; i < 24; i++) A.s[i] = 0;
-}
-// c0 + c1 over the integers (< 2p < 2^382): operand of the Karatsuba cross product
-RIPP_HD void add_unreduced(uint32_t* s, const Fq& a, const Fq& b) {
-  using namespace limb;
-  add_cc(s[0], a.v[0], b.v[0]);
-#pragma unroll
-  for (int i = 1; i < 11; i++) addc_cc(s[i], a.v[i], b.v[i]);
-  addc(s[11], a.v[11], b.v[11]);
 }
 template <class C>
 RIPP_HD void f2_mac(const C&, Acc3& A, const Fq2& a, const Fq2& b) {
@@ -435,6 +441,197 @@ RIPP_HD void inv(const C& c, int dst, int a, int t0, int t1, int t2) {
   mul(c, dst, t0, t2);
 }
 
+// ---- address-driven lazy sums (W = 3) --------------------------------------------------------------
+// On the eighteen-lane shape the modular additions around a product, not the product, are the chain: the
+// Granger-Scott squaring below spent 31 of them (~37 instructions each: carry chain, trial subtraction, select) and
+// twelve 24-word selects on one 330-instruction product.  Here a lane forms a SUM of values read from lane-dependent
+// shared-memory ADDRESSES (padding slots read twelve zero words), carries it unreduced in 12 or 13 limbs
+// (2^384 = 9.84 p), and reduces once: operands of a product only need (bound of u) x (bound of v) < 9.84 p^2 for the
+// Montgomery product to come out below 2p; results are brought to [0, p) by one quotient estimate.
+RIPP_DEFCONST(FQ_2P, 12, 0xffff5556u, 0x73fdffffu, 0x62a7ffffu, 0x3d57fffdu, 0xed61ec48u, 0xce61a541u, 0xe70a257eu, 0xc8ee9709u, 0x869759aeu, 0x96374f6cu, 0x72ffcd34u, 0x340223d4u)
+RIPP_DEFCONST(FQ_4P, 12, 0xfffeaaacu, 0xe7fbffffu, 0xc54ffffeu, 0x7aaffffau, 0xdac3d890u, 0x9cc34a83u, 0xce144afdu, 0x91dd2e13u, 0x0d2eb35du, 0x2c6e9ed9u, 0xe5ff9a69u, 0x680447a8u)
+RIPP_DEFCONST(FQ_5P, 12, 0xfffe5557u, 0xa1faffffu, 0x76a3fffeu, 0x995bfff9u, 0xd174ceb4u, 0x03f41d24u, 0xc1995dbdu, 0xf6547998u, 0x507a6034u, 0x778a468fu, 0x1f7f8103u, 0x82055993u)
+template <int K>
+RIPP_HD uint32_t fq_kp(int i) {
+  static_assert(K == 1 || K == 2 || K == 4 || K == 5, "tabulated multiples of p");
+  return K == 1 ? FqParams::p(i) : (K == 2 ? FQ_2P(i) : (K == 4 ? FQ_4P(i) : FQ_5P(i)));
+}
+// acc (12 limbs) += x;  the caller's bound keeps the sum below 2^384
+RIPP_HD void lz_add12(uint32_t* acc, const Fq& x) {
+  using namespace limb;
+  add_cc(acc[0], acc[0], x.v[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) addc_cc(acc[i], acc[i], x.v[i]);
+  addc(acc[11], acc[11], x.v[11]);
+}
+RIPP_HD void lz_sub12(uint32_t* acc, const Fq& x) {
+  using namespace limb;
+  sub_cc(acc[0], acc[0], x.v[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) subc_cc(acc[i], acc[i], x.v[i]);
+  subc(acc[11], acc[11], x.v[11]);
+}
+template <int K>
+RIPP_HD void lz_addk12(uint32_t* acc) {  // acc += K p
+  using namespace limb;
+  add_cc(acc[0], acc[0], fq_kp<K>(0));
+#pragma unroll
+  for (int i = 1; i < 11; i++) addc_cc(acc[i], acc[i], fq_kp<K>(i));
+  addc(acc[11], acc[11], fq_kp<K>(11));
+}
+// v >= K p ? v - K p : v
+template <int K>
+RIPP_HD void lz_csub12(uint32_t* v) {
+  using namespace limb;
+  uint32_t t[12], borrow;
+  sub_cc(t[0], v[0], fq_kp<K>(0));
+#pragma unroll
+  for (int i = 1; i < 12; i++) subc_cc(t[i], v[i], fq_kp<K>(i));
+  subc(borrow, 0, 0);
+#pragma unroll
+  for (int i = 0; i < 12; i++) v[i] = borrow ? v[i] : t[i];
+}
+// 13-limb accumulator (values below 32 p < 2^386)
+RIPP_HD void lz_add13(uint32_t* acc, const uint32_t* x, uint32_t x12) {
+  using namespace limb;
+  add_cc(acc[0], acc[0], x[0]);
+#pragma unroll
+  for (int i = 1; i < 12; i++) addc_cc(acc[i], acc[i], x[i]);
+  addc(acc[12], acc[12], x12);
+}
+RIPP_HD void lz_sub13(uint32_t* acc, const uint32_t* x) {
+  using namespace limb;
+  sub_cc(acc[0], acc[0], x[0]);
+#pragma unroll
+  for (int i = 1; i < 12; i++) subc_cc(acc[i], acc[i], x[i]);
+  subc(acc[12], acc[12], 0);
+}
+// T (13 limbs, T < 32 p) -> T mod p.  h = floor(T / 2^376) < 1024 and p / 2^376 = 26.0042..., so
+// q = floor(h * 2520 / 2^16) (2520 / 2^16 = 1 / 26.0063) is floor(T / p) or one less for every such T (checked
+// exhaustively over h in tests/test_hostsim.py); T - q p < 2p fits 12 limbs and one trial subtraction finishes.
+RIPP_HD Fq lz_reduce13(const uint32_t* T) {
+  using namespace limb;
+  const uint32_t h = (T[12] << 8) | (T[11] >> 24);
+  const uint32_t q = (h * 2520u) >> 16;
+  uint32_t lo[12], hi[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    uint64_t m = mul_wide(q, FqParams::p(i));
+    lo[i] = (uint32_t)m;
+    hi[i] = (uint32_t)(m >> 32);
+  }
+  Fq r;
+  sub_cc(r.v[0], T[0], lo[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) subc_cc(r.v[i], T[i], lo[i]);
+  subc(r.v[11], T[11], lo[11]);
+  sub_cc(r.v[1], r.v[1], hi[0]);
+#pragma unroll
+  for (int i = 2; i < 11; i++) subc_cc(r.v[i], r.v[i], hi[i - 1]);
+  subc(r.v[11], r.v[11], hi[10]);
+  detail::final_sub<FqParams>(r.v);
+  return r;
+}
+
+// Granger-Scott squaring on eighteen lanes (same formulas as cyc_sqr_body below).  Lane (k, role) multiplies ONE pair of
+// operand sums u v -- role 0: u0 v0, role 1: u1 v1, role 2: (u0 + u1)(v0 + v1) of this coefficient's Fq2 product, with
+// (u, v) = (ra, rb) for k < 3 and (ra + rb, ra + xi rb) for k >= 3 -- and after the exchange forms ONE component
+// (role 1: c1, roles 0 and 2: c0) of its output coefficient straight from the six raw Karatsuba parts
+// p0 p1 p2 (product ra rb) and x0 x1 x2 (cross product) of its source pair:
+//   t_even = (x0 - x1 - 3 p0 + p1 + p2,  x2 - x0 - x1 - 2 p2 + p0 + 3 p1)
+//   t_odd  = (2 p0 - 2 p1,  2 p2 - 2 p0 - 2 p1),      xi t_odd = (4 p0 - 2 p2,  2 p2 - 4 p1)
+//   out = 3 t -+ 2 own        (t_even, -: k = 0, 2, 4;  t_odd, +: k = 3, 5;  xi t_odd, +: k = 1)
+// as S = 5p + (five added slots) - (four subtracted slots) in [p, 10p), T = 3 S + 2 own_added - 2 own_subtracted < 32 p.
+template <class C>
+RIPP_HD void cyc_sqr_w3_body(const C& c, int dst, int a) {
+  const uint32_t* A = freg(c, a);
+  const uint32_t* Z = c.bus + BUS_ZERO;
+  const int k = c.k, pr = k % 3, role = c.role;
+  const bool hi = k >= 3;
+  const uint32_t *ra0 = A + pr * FQ2W, *ra1 = ra0 + 12, *rb0 = A + (pr + 3) * FQ2W, *rb1 = rb0 + 12;
+  // u:  k < 3: ra0 | ra1 | ra0 + ra1;   k >= 3: ra0 + rb0 | ra1 + rb1 | ra0 + ra1 + rb0 + rb1      (< 4p, then < 2p)
+  // v:  k < 3: rb0 | rb1 | rb0 + rb1;   k >= 3: ra0 + rb0 - rb1 | ra1 + rb0 + rb1 | ra0 + ra1 + 2 rb0   (+ p; < 5p, then < 4p)
+  const uint32_t* U1 = role == 1 ? ra1 : ra0;
+  const uint32_t* U2 = role == 2 ? ra1 : Z;
+  const uint32_t* U3 = hi ? (role == 1 ? rb1 : rb0) : Z;
+  const uint32_t* U4 = (hi && role == 2) ? rb1 : Z;
+  const uint32_t* V1 = hi ? (role == 1 ? ra1 : ra0) : (role == 1 ? rb1 : rb0);
+  const uint32_t* V2 = hi ? rb0 : (role == 2 ? rb1 : Z);
+  const uint32_t* V3 = hi ? (role == 0 ? Z : (role == 1 ? rb1 : ra1)) : Z;
+  const uint32_t* V4 = (hi && role == 2) ? rb0 : Z;
+  const uint32_t* N1 = (hi && role == 0) ? rb1 : Z;
+  Fq u = ld1(U1), v = ld1(V1);
+  lz_add12(u.v, ld1(U2));
+  lz_add12(u.v, ld1(U3));
+  lz_add12(u.v, ld1(U4));
+  lz_csub12<2>(u.v);
+  lz_add12(v.v, ld1(V2));
+  lz_add12(v.v, ld1(V3));
+  lz_add12(v.v, ld1(V4));
+  lz_addk12<1>(v.v);
+  lz_sub12(v.v, ld1(N1));
+  lz_csub12<4>(v.v);
+  uint32_t* b = c.bus + c.par * BUS_WORDS;
+  c.par ^= 1;
+  st1(b + k * 36 + role * 12, fqmul(u, v));  // < (2p)(4p) / R + p < 2p before the product's own final subtraction
+  sync(c);
+  // source pair of this coefficient's output: a0, a3 <- pair 0; a2, a5 <- pair 1; a1, a4 <- pair 2
+  const int src = pr == 0 ? 0 : (pr == 2 ? 1 : 2);
+  const uint32_t *p0 = b + src * 36, *p1 = p0 + 12, *p2 = p0 + 24;
+  const uint32_t *x0 = b + (src + 3) * 36, *x1 = x0 + 12, *x2 = x0 + 24;
+  const bool c1 = role == 1;
+  const bool tE = (k & 1) == 0, tX = k == 1;  // else t_odd (k = 3, 5)
+  const uint32_t *P1, *P2, *P3, *P4, *P5, *M1, *M2, *M3, *M4;
+  //            even, c0        even, c1        xi odd, c0   xi odd, c1   odd, c0      odd, c1
+  // added      x0 p1 p2 .  .   x2 p0 p1 p1 p1  p0 p0 p0 p0  p2 p2 . . .  p0 p0 . . .  p2 p2 . . .
+  // subtracted x1 p0 p0 p0     x0 x1 p2 p2     p2 p2 .  .   p1 p1 p1 p1  p1 p1 .  .   p0 p0 p1 p1
+  P1 = tE ? (c1 ? x2 : x0) : (c1 ? p2 : p0);
+  P2 = tE ? (c1 ? p0 : p1) : (c1 ? p2 : p0);
+  P3 = tE ? (c1 ? p1 : p2) : ((tX && !c1) ? p0 : Z);
+  P4 = (tE && c1) ? p1 : ((tX && !c1) ? p0 : Z);
+  P5 = (tE && c1) ? p1 : Z;
+  M1 = tE ? (c1 ? x0 : x1) : (tX ? (c1 ? p1 : p2) : (c1 ? p0 : p1));
+  M2 = tE ? (c1 ? x1 : p0) : (tX ? (c1 ? p1 : p2) : (c1 ? p0 : p1));
+  M3 = tE ? (c1 ? p2 : p0) : (c1 ? p1 : Z);
+  M4 = tE ? (c1 ? p2 : p0) : (c1 ? p1 : Z);
+  const uint32_t* own = A + k * FQ2W + (c1 ? 12 : 0);
+  const uint32_t* ownP = tE ? Z : own;
+  const uint32_t* ownM = tE ? own : Z;
+  uint32_t S[13];
+#pragma unroll
+  for (int i = 0; i < 12; i++) S[i] = fq_kp<5>(i);
+  S[12] = 0;
+  {
+    Fq t;
+    t = ld1(P1); lz_add13(S, t.v, 0);
+    t = ld1(P2); lz_add13(S, t.v, 0);
+    t = ld1(P3); lz_add13(S, t.v, 0);
+    t = ld1(P4); lz_add13(S, t.v, 0);
+    t = ld1(P5); lz_add13(S, t.v, 0);
+    t = ld1(M1); lz_sub13(S, t.v);
+    t = ld1(M2); lz_sub13(S, t.v);
+    t = ld1(M3); lz_sub13(S, t.v);
+    t = ld1(M4); lz_sub13(S, t.v);
+  }
+  uint32_t T[13];
+#pragma unroll
+  for (int i = 0; i < 13; i++) T[i] = S[i];
+  lz_add13(T, S, S[12]);
+  lz_add13(T, S, S[12]);
+  {
+    Fq t = ld1(ownP);
+    lz_add13(T, t.v, 0);
+    lz_add13(T, t.v, 0);
+    t = ld1(ownM);
+    lz_sub13(T, t.v);
+    lz_sub13(T, t.v);
+  }
+  Fq out = lz_reduce13(T);
+  sync(c);  // every lane has read `a` (dst may be the same register) before anyone overwrites it
+  if (role != 2) st1(freg(c, dst) + k * FQ2W + (c1 ? 12 : 0), out);
+  sync(c);
+}
+
 // dst = a^2 for a in the cyclotomic subgroup (Granger-Scott): ONE Fq2 product per coefficient.
 // In the flat basis the three Fq4 pairs are (a0, a3), (a1, a4), (a2, a5); coefficient k < 3 forms a_k a_{k+3},
 // coefficient k >= 3 forms (a_{k-3} + a_k)(a_{k-3} + xi a_k), and with
@@ -485,7 +682,21 @@ RIPP_HD void cyc_sqr_body(const C& c, int dst, int a) {
 #define RIPP_L6_COMMA ,
 RIPP_L6_OP(sqr, int dst RIPP_L6_COMMA int a, dst RIPP_L6_COMMA a)
 RIPP_L6_OP(mul_line, int dst RIPP_L6_COMMA int a, dst RIPP_L6_COMMA a)
+#if defined(__CUDA_ARCH__) && defined(RIPP_L6_CALL_W3)
 RIPP_L6_OP(cyc_sqr, int dst RIPP_L6_COMMA int a, dst RIPP_L6_COMMA a)
+#else
+// -DRIPP_L6_CYC_EAGER: the eighteen-lane shape on the generic body (the round-2 baseline, kept for A/B runs)
+template <class C>
+RIPP_HD void cyc_sqr(const C& c, int dst, int a) {
+#if !defined(RIPP_L6_CYC_EAGER)
+  if constexpr (C::W == 3) {
+    cyc_sqr_w3_body(c, dst, a);
+    return;
+  }
+#endif
+  cyc_sqr_body(c, dst, a);
+}
+#endif
 
 // a^x (x = -|x|) for a in the cyclotomic subgroup; dst != a; clobbers nothing else
 template <class C>

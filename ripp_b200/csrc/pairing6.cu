@@ -158,11 +158,13 @@ __global__ void __launch_bounds__(32) k_gt_pow6(const Fq12* __restrict__ in, con
 // ------------------------------------------------------------------------------------------------
 static __device__ __forceinline__ Ctx3 ctx18(uint32_t* wsm, int group_words_no_bus) {
   const int vl = (threadIdx.x & 31) % 18;  // lanes 18..31 mirror lanes 0..13: same addresses, same values
+  if ((threadIdx.x & 31) < 12) wsm[group_words_no_bus + BUS_ZERO + (threadIdx.x & 31)] = 0;  // l6.cuh's padding operand
+  __syncwarp();
   return Ctx3{vl / 3, wsm, nullptr, vl % 3, wsm + group_words_no_bus, 0};
 }
 constexpr int M18_WARPS = 4;
 template <int KP>
-RIPP_HD constexpr int m18_group_words() { return group_words(M6_NREG, KP) + 2 * BUS_WORDS; }
+RIPP_HD constexpr int m18_group_words() { return group_words(M6_NREG, KP) + BUS_TOTAL; }
 
 // grid (ceil(wps / 4), nseg): warp w of segment s walks pairs [w KP, w KP + KP); the CTA's four Miller values are
 // multiplied in shared memory; one partial per CTA at partials[s * gridDim.x + blockIdx.x].
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(32 * M18_WARPS) k_miller18(Miller6Batch b, Fq1
 }
 
 // out[s][j] = prod in[s][j*R .. min(T, j*R+R)); one warp per output
-constexpr int R18_GROUP_WORDS = group_words(2, 0) + 2 * BUS_WORDS;
+constexpr int R18_GROUP_WORDS = group_words(2, 0) + BUS_TOTAL;
 __global__ void __launch_bounds__(32 * M18_WARPS) k_reduce18(const Fq12* __restrict__ in, uint32_t T, uint32_t R, uint32_t To,
                                                             Fq12* __restrict__ out, uint32_t total) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(32 * M18_WARPS) k_reduce18(const Fq12* __restr
 }
 
 // out[s] = final_exponentiation(prod_j in[s][j]), j < T; one warp (one CTA) per value
-constexpr int FE18_GROUP_WORDS = group_words(FE_NREG, 0) + 2 * BUS_WORDS;
+constexpr int FE18_GROUP_WORDS = group_words(FE_NREG, 0) + BUS_TOTAL;
 __global__ void __launch_bounds__(32) k_final_exp18(const Fq12* __restrict__ in, uint32_t T, Fq12* __restrict__ out) {
   extern __shared__ __align__(16) uint32_t smem[];
   Ctx3 c = ctx18(smem, group_words(FE_NREG, 0));
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(32) k_final_exp18(const Fq12* __restrict__ in,
 }
 
 // out[i] = in[i]^sc[i], one warp per element (k_gt_pow6 on eighteen lanes)
-constexpr int GP18_GROUP_WORDS = group_words(GP_NREG, 0) + 2 * BUS_WORDS;
+constexpr int GP18_GROUP_WORDS = group_words(GP_NREG, 0) + BUS_TOTAL;
 __global__ void __launch_bounds__(32) k_gt_pow18(const Fq12* __restrict__ in, const Fr* __restrict__ sc, uint32_t n,
                                                  Fq12* __restrict__ out) {
   extern __shared__ __align__(16) uint32_t smem[];
@@ -288,7 +290,7 @@ static size_t l18_max_warps() {
 // (Scott, ePrint 2021/1130; oracle: gt_in_subgroup_fast, checked there against f^r == 1).  One group per element;
 // a failing element ORs `flag` into *bad.
 constexpr int GC_NREG = 3;
-constexpr int GC_GROUP_WORDS = group_words(GC_NREG, 0) + 2 * BUS_WORDS;
+constexpr int GC_GROUP_WORDS = group_words(GC_NREG, 0) + BUS_TOTAL;
 __global__ void __launch_bounds__(32) k_gt_check18(const Fq12* __restrict__ in, uint32_t n, uint32_t* __restrict__ bad,
                                                    uint32_t flag) {
   extern __shared__ __align__(16) uint32_t smem[];

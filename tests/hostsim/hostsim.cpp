@@ -67,6 +67,8 @@ void hs_fq_dot_redc(const uint32_t* a, const uint32_t* b, int k, int subs, uint3
   }
   detail::redc_wide<FqParams>(r, acc, subs);
 }
+// l6.cuh's lazy sums: T (13 limbs, < 32 p) -> T mod p
+void hs_lz_reduce13(const uint32_t* T, uint32_t* r) { st(r, l6::lz_reduce13(T)); }
 uint64_t hs_mul_count(int which) { return detail::mul_count_[which]; }
 void hs_mul_count_reset() { detail::mul_count_[0] = detail::mul_count_[1] = 0; }
 // k * P through the GLV / GLS decomposition (endo.cuh); k = 8 canonical words
@@ -93,7 +95,7 @@ static inline int tower_slot(int k) { return (k & 1) * 3 + (k >> 1); }
 // W lanes per coefficient: 6 (W = 1) or 18 (W = 3) host threads per group
 template <int W, class Fn>
 static void run_group(Fn fn, int nreg = 8) {
-  std::vector<uint32_t> sm(l6::group_words(nreg, 4) + 2 * l6::BUS_WORDS, 0);
+  std::vector<uint32_t> sm(l6::group_words(nreg, 4) + l6::BUS_TOTAL, 0);
   pthread_barrier_t bar;
   pthread_barrier_init(&bar, nullptr, 6 * W);
   std::vector<std::thread> th;

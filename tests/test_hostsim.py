@@ -160,6 +160,42 @@ def test_l6_six_lane_fq12(hostsim, eng):
         assert op(9, ea, ew) == E.f12_pow(a, e)
 
 
+def test_l18_lazy_sums(hostsim):
+    """l6.cuh's address-driven lazy sums behind the eighteen-lane Granger-Scott squaring: the single-quotient reduction
+    of a 13-limb value below 32p (exhaustive over the 10 bits the estimate reads, both ends of every bucket), and the
+    squaring against the six-lane body on inputs that drive every unreduced sum to its bound."""
+    import numpy as np
+
+    def words13(t):
+        return np.array([(t >> (32 * i)) & 0xFFFFFFFF for i in range(13)], dtype=np.uint32)
+
+    radix = 1 << 384
+    h = 0
+    while (h << 376) < 32 * E.P:
+        lo, hi = h << 376, min(((h + 1) << 376), 32 * E.P) - 1
+        q_est = (h * 2520) >> 16
+        for t in (lo, hi):
+            assert 0 <= t // E.P - q_est <= 1
+        h += 1
+    assert h <= 1024
+    cases = [0, 1, E.P - 1, E.P, E.P + 1, 2 * E.P - 1, 2 * E.P, 31 * E.P, 32 * E.P - 1]
+    cases += [k * E.P + d for k in range(1, 32) for d in (-1, 0, 1)]
+    cases += [rnd.randrange(32 * E.P) for _ in range(300)]
+    for t in cases:
+        got = C._int(hostsim.call("hs_lz_reduce13", words13(t), out=12))
+        assert got == t % E.P, hex(t)
+    # the squaring as a polynomial map (any Fq12 input, not only cyclotomic ones): extreme coefficient patterns
+    big, mont = E.P - 1, lambda x: x * pow(radix, -1, E.P) % E.P  # mont(x): the value whose Montgomery form is the word pattern x
+    pats = [tuple((mont(big), mont(big)) for _ in range(6)), tuple((0, 0) for _ in range(6)),
+            tuple((mont(big), 0) if k < 3 else (0, mont(big)) for k in range(6)),
+            tuple((mont(big - k), mont(k)) for k in range(6))] + [rf12() for _ in range(6)]
+    for a in pats:
+        ea = C.gt_enc(a)
+        new = hostsim.call("hs_l18_op", 8, ea, ea, out=144)
+        ref = hostsim.call("hs_l6_op", 8, ea, ea, out=144)
+        assert (new == ref).all()
+
+
 @pytest.mark.parametrize("eng", ["l6", "l18"])
 def test_l6_miller_and_final_exp(hostsim, eng):
     p, q = E.g1_mul(E.G1_GEN, 123), E.g2_mul(E.G2_GEN, 456)
