@@ -26,7 +26,7 @@ constexpr int OFF_LINE = OFF_R + F12W;    // line coefficients d0, d1, d4
 constexpr int OFF_F = OFF_LINE + 3 * FQ2W;  // Fq12 registers F0..F(nreg-1), then the per-pair blocks
 // per-pair block (a group can walk several pairs that share one accumulator, ark-ec's multi_miller_loop shape)
 constexpr int PB_T = 0;                   // running point T: x, y, z
-constexpr int PB_P = PB_T + 3 * FQ2W;     // xP, yP (Fq each)
+constexpr int PB_P = PB_T + 3 * FQ2W;     // xP, -yP (Fq each; stage_pair_p)
 constexpr int PB_QPTR = PB_P + FQ2W;      // address of Q (affine, global memory): read at the start and by the five
                                           // addition steps only -- 192 B of shared memory per pair bought a third CTA per SM
 constexpr int PB_VALID = PB_QPTR + 2;     // 1 = finite pair, 0 = contributes the constant line 1
@@ -52,6 +52,7 @@ struct CtxT {
   int role;       // W = 3: Karatsuba role of this lane, 0..2
   uint32_t* bus;  // W = 3: BUS_TOTAL words of the group's scratch (zero slot cleared by whoever builds the context)
   mutable int par;  // W = 3: which bus buffer the next exchange uses
+  const uint32_t* zero;  // Miller loop: twelve words that stay zero (padding operand of lz_pass); W = 3: bus + BUS_ZERO
 };
 using Ctx = CtxT<1>;
 using Ctx3 = CtxT<3>;
@@ -449,12 +450,13 @@ RIPP_HD void inv(const C& c, int dst, int a, int t0, int t1, int t2) {
 // (2^384 = 9.84 p), and reduces once: operands of a product only need (bound of u) x (bound of v) < 9.84 p^2 for the
 // Montgomery product to come out below 2p; results are brought to [0, p) by one quotient estimate.
 RIPP_DEFCONST(FQ_2P, 12, 0xffff5556u, 0x73fdffffu, 0x62a7ffffu, 0x3d57fffdu, 0xed61ec48u, 0xce61a541u, 0xe70a257eu, 0xc8ee9709u, 0x869759aeu, 0x96374f6cu, 0x72ffcd34u, 0x340223d4u)
+RIPP_DEFCONST(FQ_3P, 12, 0xffff0001u, 0x2dfcffffu, 0x13fbffffu, 0x5c03fffcu, 0xe412e26cu, 0x359277e2u, 0xda8f383eu, 0x2d65e28eu, 0xc9e30686u, 0xe152f722u, 0xac7fb3ceu, 0x4e0335beu)
 RIPP_DEFCONST(FQ_4P, 12, 0xfffeaaacu, 0xe7fbffffu, 0xc54ffffeu, 0x7aaffffau, 0xdac3d890u, 0x9cc34a83u, 0xce144afdu, 0x91dd2e13u, 0x0d2eb35du, 0x2c6e9ed9u, 0xe5ff9a69u, 0x680447a8u)
 RIPP_DEFCONST(FQ_5P, 12, 0xfffe5557u, 0xa1faffffu, 0x76a3fffeu, 0x995bfff9u, 0xd174ceb4u, 0x03f41d24u, 0xc1995dbdu, 0xf6547998u, 0x507a6034u, 0x778a468fu, 0x1f7f8103u, 0x82055993u)
 template <int K>
 RIPP_HD uint32_t fq_kp(int i) {
-  static_assert(K == 1 || K == 2 || K == 4 || K == 5, "tabulated multiples of p");
-  return K == 1 ? FqParams::p(i) : (K == 2 ? FQ_2P(i) : (K == 4 ? FQ_4P(i) : FQ_5P(i)));
+  static_assert(K >= 1 && K <= 5, "tabulated multiples of p");
+  return K == 1 ? FqParams::p(i) : (K == 2 ? FQ_2P(i) : (K == 3 ? FQ_3P(i) : (K == 4 ? FQ_4P(i) : FQ_5P(i))));
 }
 // acc (12 limbs) += x;  the caller's bound keeps the sum below 2^384
 RIPP_HD void lz_add12(uint32_t* acc, const Fq& x) {
@@ -506,7 +508,7 @@ RIPP_HD void lz_sub13(uint32_t* acc, const uint32_t* x) {
   for (int i = 1; i < 12; i++) subc_cc(acc[i], acc[i], x[i]);
   subc(acc[12], acc[12], 0);
 }
-// T (13 limbs, T < 32 p) -> T mod p.  h = floor(T / 2^376) < 1024 and p / 2^376 = 26.0042..., so
+// T (13 limbs, T < 2^386 = 39.4 p) -> T mod p.  h = floor(T / 2^376) < 1024 and p / 2^376 = 26.0042..., so
 // q = floor(h * 2520 / 2^16) (2520 / 2^16 = 1 / 26.0063) is floor(T / p) or one less for every such T (checked
 // exhaustively over h in tests/test_hostsim.py); T - q p < 2p fits 12 limbs and one trial subtraction finishes.
 RIPP_HD Fq lz_reduce13(const uint32_t* T) {
@@ -531,6 +533,55 @@ RIPP_HD Fq lz_reduce13(const uint32_t* T) {
   subc(r.v[11], r.v[11], hi[10]);
   detail::final_sub<FqParams>(r.v);
   return r;
+}
+
+// One lane's share of a "pass": out = MUL * (sum of NP slots - sum of NM slots) [/ 2] mod p, fully reduced.  The slots
+// are twelve-word canonical values at lane-dependent shared-memory addresses (unused ones point at the zero slot), so
+// lanes producing DIFFERENT derived values run one instruction stream; NP + NM + 1 <= 9 keeps the sum in 12 limbs.
+RIPP_HD uint32_t shr_pair(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
+}
+template <int NP, int NM, int MUL, bool HALF>
+RIPP_HD Fq lz_pass(const uint32_t* base, const int* P, const int* M, bool half) {
+  static_assert(NP + NM + 1 <= 9 && (MUL == 1 || (MUL == 12 && NP + NM <= 3 && !HALF)), "bounds: 2^384 = 9.84 p, 2^386 = 39.4 p");
+  using namespace limb;
+  uint32_t S[13];
+  {
+    Fq t = ld1(base + P[0]);
+    lz_addk12<NM>(t.v);  // + NM p: the subtractions below cannot go negative
+#pragma unroll
+    for (int i = 0; i < 12; i++) S[i] = t.v[i];
+  }
+#pragma unroll
+  for (int j = 1; j < NP; j++) lz_add12(S, ld1(base + P[j]));
+#pragma unroll
+  for (int j = 0; j < NM; j++) lz_sub12(S, ld1(base + M[j]));
+  if (HALF) {  // (S + (S odd ? p : 0)) / 2 for the lanes that halve
+    const uint32_t m = (half && (S[0] & 1u)) ? 0xffffffffu : 0u, sh = half ? 1u : 0u;
+    add_cc(S[0], S[0], FqParams::p(0) & m);
+#pragma unroll
+    for (int i = 1; i < 11; i++) addc_cc(S[i], S[i], FqParams::p(i) & m);
+    addc(S[11], S[11], FqParams::p(11) & m);
+#pragma unroll
+    for (int i = 0; i < 11; i++) S[i] = shr_pair(S[i], S[i + 1], sh);
+    S[11] >>= sh;
+  }
+  S[12] = 0;
+  if (MUL == 12) {
+    uint32_t T[13];
+#pragma unroll
+    for (int i = 0; i < 13; i++) T[i] = S[i];
+    lz_add13(T, S, 0);
+    lz_add13(T, S, 0);
+#pragma unroll
+    for (int i = 12; i >= 1; i--) S[i] = (T[i] << 2) | (T[i - 1] >> 30);
+    S[0] = T[0] << 2;
+  }
+  return lz_reduce13(S);
 }
 
 // Granger-Scott squaring on eighteen lanes (same formulas as cyc_sqr_body below).  Lane (k, role) multiplies ONE pair of
@@ -761,49 +812,74 @@ RIPP_HD void final_exp(const C& c) {
 }
 
 // ---- Miller loop --------------------------------------------------------------------------------
-// smem: T = (x, y, z) at OFF_T, P = (xP, yP) at OFF_P, Q = (xQ, yQ) at OFF_Q, accumulator in register 0.
-// One doubling step: two rounds of at most six parallel Fq2 products.
+// smem: T = (x, y, z) at PB_T, (xP, -yP) at PB_P, accumulator in register 0.
+RIPP_HD void stage_pair_p(uint32_t* pb, const G1Aff& P) { st2(pb + PB_P, Fq2{P.x, -P.y}); }
+template <class C>
+RIPP_HD int lane_index(const C& c) { return C::W == 1 ? c.k : c.k * 3 + c.role; }
+template <class C>
+RIPP_HD bool lane_stores(const C& c) { return C::W == 1 || c.role == 0; }  // W = 3: the triple holds one value
+
+// One doubling step (ark-ec's homogeneous-projective formulas): two rounds of six parallel Fq2 products, every operand
+// read from a lane-dependent ADDRESS, and between / after them three lz_pass rounds in which each lane forms one Fq
+// component of one derived value.  (The first version had every lane compute every intermediate and select its own:
+// 48 modular additions and ~22 24-word selects per step -- 2300 of the ~9100 instructions of a Miller-loop bit.)
+//   round 1:  R0 = x y, R1 = y^2 (= b), R2 = z^2, R3 = y z, R4 = x^2
+//   pass E:   E = 12 xi R2                        (e = 4 xi 3 z^2; f = 3 E)                        -> slot R5
+//   pass B:   BFh = (R1 - 3E) / 2,  G = (R1 + 3E) / 2,  H = 2 R3 (= h = (y + z)^2 - y^2 - z^2)     -> the line slots
+//   round 2:  x' = R0 BFh,  R2 = G^2,  z' = R1 H,  R3 = E^2,  R4 = R4 xP,  d4 = H (-yP)
+//   pass F:   y' = R2 - 3 R3,  d0 = E - R1,  d1 = 3 R4         (masked pair: the line is the constant 1)
 template <class C>
 RIPP_HD void dbl_step(const C& c, uint32_t* pb) {
-  uint32_t* T = pb + PB_T;
-  uint32_t* R = c.sm + OFF_R;
-  const int k = c.k;
-  Fq2 x = ld2(T), y = ld2(T + FQ2W), z = ld2(T + 2 * FQ2W);
-  // round 1: R0 = x y, R1 = y^2, R2 = z^2, R3 = (y + z)^2, R4 = x^2, R5 = unused
-  Fq2 yz = f2add(y, z);
-  Fq2 u = f2sel(k == 0 || k == 4, x, f2sel(k == 3, yz, f2sel(k == 2, z, y)));
-  Fq2 v = f2sel(k == 0 || k == 1, y, f2sel(k == 3, yz, f2sel(k == 2, z, x)));
-  st2(R + k * FQ2W, f2mul(c, u, v));
-  sync(c);
-  Fq2 a = f2half(ld2(R)), b = ld2(R + FQ2W), cc = ld2(R + 2 * FQ2W), d = ld2(R + 3 * FQ2W), j = ld2(R + 4 * FQ2W);
-  Fq2 e = f2dbl(f2dbl(f2xi(f2add(f2dbl(cc), cc))));  // 4 xi * 3 z^2
-  Fq2 f = f2add(f2dbl(e), e);
-  Fq2 g = f2half(f2add(b, f));
-  Fq2 h = f2sub(d, f2add(b, cc));
-  Fq2 j3 = f2add(f2dbl(j), j);
-  sync(c);
-  // round 2: R0 = a (b - f), R1 = g^2, R2 = b h, R3 = e^2, R4 = 3j * xP, R5 = -h * yP
-  Fq xp = ld2(pb + PB_P).c0, yp = ld2(pb + PB_P).c1;
+  const int k = c.k, li = lane_index(c);
+  uint32_t* sm = c.sm;
+  const int oT = (int)(pb - sm) + PB_T, oP = (int)(pb - sm) + PB_P, oZ = (int)(c.zero - sm);
+  constexpr int oR = OFF_R, oL = OFF_LINE, oE = OFF_R + 5 * FQ2W;
   const bool valid = pb[PB_VALID] != 0;
-  Fq2 sxp = {xp, Fq::zero()}, syp = {yp, Fq::zero()};
-  u = f2sel(k == 0, a, f2sel(k == 1, g, f2sel(k == 2, b, f2sel(k == 3, e, f2sel(k == 4, j3, f2neg(h))))));
-  v = f2sel(k == 0, f2sub(b, f), f2sel(k == 1, g, f2sel(k == 2, h, f2sel(k == 3, e, f2sel(k == 4, sxp, syp)))));
-  st2(R + k * FQ2W, f2mul(c, u, v));
-  sync(c);
-  // new T and the line (d0, d1, d4) = (e - b, 3j xP, -h yP)
-  Fq2 e2 = ld2(R + 3 * FQ2W);
-  Fq2 nx = ld2(R), ny = f2sub(ld2(R + FQ2W), f2add(f2dbl(e2), e2)), nz = ld2(R + 2 * FQ2W);
-  Fq2 d1 = ld2(R + 4 * FQ2W), d4 = ld2(R + 5 * FQ2W);
-  sync(c);
-  if (k == 0) {
-    st2(T, nx);
-    st2(T + FQ2W, ny);
-    st2(T + 2 * FQ2W, nz);
+  {
+    const int ua = oT + ((k == 0 || k >= 4) ? 0 : (k == 2 ? 2 : 1)) * FQ2W;
+    const int va = oT + (k <= 1 ? 1 : (k <= 3 ? 2 : 0)) * FQ2W;
+    Fq2 r = f2mul(c, ld2(sm + ua), ld2(sm + va));
+    if (lane_stores(c)) st2(sm + oR + k * FQ2W, r);
   }
-  if (k == 1) {  // masked pairs multiply the accumulator by the constant line 1
-    st2(c.sm + OFF_LINE, f2sel(valid, f2sub(e, b), Fq2::one()));
-    st2(c.sm + OFF_LINE + FQ2W, f2sel(valid, d1, Fq2::zero()));
-    st2(c.sm + OFF_LINE + 2 * FQ2W, f2sel(valid, d4, Fq2::zero()));
+  sync(c);
+  {
+    const int cc = li & 1;
+    const int P[2] = {oR + 2 * FQ2W, cc ? oR + 2 * FQ2W + 12 : oZ}, M[1] = {cc ? oZ : oR + 2 * FQ2W + 12};
+    Fq e = lz_pass<2, 1, 12, false>(sm, P, M, false);
+    if (li < 2) st1(sm + oE + 12 * cc, e);
+  }
+  sync(c);
+  {
+    const int ci = li % 6, vi = ci >> 1, cc = 12 * (ci & 1);
+    const int r1 = oR + FQ2W + cc, r3 = oR + 3 * FQ2W + cc, e = oE + cc;
+    const int P[4] = {vi == 2 ? r3 : r1, vi == 0 ? oZ : (vi == 1 ? e : r3), vi == 1 ? e : oZ, vi == 1 ? e : oZ};
+    const int m = vi == 0 ? e : oZ;
+    const int M[3] = {m, m, m};
+    Fq v = lz_pass<4, 3, 1, true>(sm, P, M, vi != 2);
+    if (li < 6) st1(sm + oL + vi * FQ2W + cc, v);
+  }
+  sync(c);
+  {
+    const int ua = k == 0 ? oR : (k == 1 ? oL + FQ2W : (k == 2 ? oR + FQ2W : (k == 3 ? oE : (k == 4 ? oR + 4 * FQ2W : oL + 2 * FQ2W))));
+    const int v0 = k == 0 ? oL : (k == 1 ? oL + FQ2W : (k == 2 ? oL + 2 * FQ2W : (k == 3 ? oE : (k == 4 ? oP : oP + 12))));
+    const int v1 = k < 4 ? v0 + 12 : oZ;
+    Fq2 u = ld2(sm + ua), v = {ld1(sm + v0), ld1(sm + v1)};
+    sync(c);  // every operand is in registers before a product lands on its slot
+    Fq2 r = f2mul(c, u, v);
+    r = f2sel(valid || k < 4, r, Fq2::zero());  // masked pair: d4 = 0 (d1 is zeroed in pass F)
+    const int dst = k == 0 ? oT : (k == 1 ? oR + 2 * FQ2W : (k == 2 ? oT + 2 * FQ2W : (k == 3 ? oR + 3 * FQ2W : (k == 4 ? oR + 4 * FQ2W : oL + 2 * FQ2W))));
+    if (lane_stores(c)) st2(sm + dst, r);
+  }
+  sync(c);
+  {
+    const int ci = li % 6, vi = ci >> 1, cc = 12 * (ci & 1);
+    const int r1 = oR + FQ2W + cc, r2 = oR + 2 * FQ2W + cc, r3 = oR + 3 * FQ2W + cc, r4 = oR + 4 * FQ2W + cc, e = oE + cc;
+    const int P[3] = {vi == 0 ? r2 : (vi == 1 ? e : r4), vi == 2 ? r4 : oZ, vi == 2 ? r4 : oZ};
+    const int M[3] = {vi == 0 ? r3 : (vi == 1 ? r1 : oZ), vi == 0 ? r3 : oZ, vi == 0 ? r3 : oZ};
+    Fq v = lz_pass<3, 3, 1, false>(sm, P, M, false);
+    if (vi != 0 && !valid) v = (vi == 1 && cc == 0) ? Fq::one() : Fq::zero();
+    const int dst = vi == 0 ? oT + FQ2W + cc : (vi == 1 ? oL + cc : oL + FQ2W + cc);
+    if (li < 6) st1(sm + dst, v);
   }
   sync(c);
 }
@@ -837,11 +913,11 @@ RIPP_HD void add_step(const C& c, uint32_t* pb) {
   Fq2 e = ld2(R), f = ld2(R + FQ2W), g = ld2(R + 2 * FQ2W);
   Fq2 h = f2sub(f2add(e, f), f2dbl(g));
   sync(c);
-  // round 4: R0 = lambda h, R1 = theta (g - h), R2 = e y, R3 = z e, R4 = -theta xP, R5 = lambda yP
-  Fq xp = ld2(pb + PB_P).c0, yp = ld2(pb + PB_P).c1;
+  // round 4: R0 = lambda h, R1 = theta (g - h), R2 = e y, R3 = z e, R4 = -theta xP, R5 = (-lambda) (-yP)
+  Fq xp = ld2(pb + PB_P).c0, myp = ld2(pb + PB_P).c1;  // xP, -yP
   const bool valid = pb[PB_VALID] != 0;
-  Fq2 sxp = {xp, Fq::zero()}, syp = {yp, Fq::zero()};
-  u = f2sel(k == 0, lambda, f2sel(k == 1, theta, f2sel(k == 2, e, f2sel(k == 3, z, f2sel(k == 4, f2neg(theta), lambda)))));
+  Fq2 sxp = {xp, Fq::zero()}, syp = {myp, Fq::zero()};
+  u = f2sel(k == 0, lambda, f2sel(k == 1, theta, f2sel(k == 2, e, f2sel(k == 3, z, f2neg(f2sel(k == 4, theta, lambda))))));
   v = f2sel(k == 0, h, f2sel(k == 1, f2sub(g, h), f2sel(k == 2, y, f2sel(k == 3, e, f2sel(k == 4, sxp, syp)))));
   st2(R + k * FQ2W, f2mul(c, u, v));
   sync(c);

@@ -18,6 +18,7 @@ struct Miller6Batch {
 
 constexpr int M6_NREG = 2;
 constexpr int M6_WARPS = 4;
+RIPP_HD constexpr int m6_smem_bytes(int kp) { return (M6_WARPS * 5 * group_words(M6_NREG, kp) + 16) * 4; }
 
 // the generator of G2 in global memory: Q of masked pairs (identities / padding) -- per device, written by
 // ripp_pairing6_init_device
@@ -37,6 +38,9 @@ __global__ void __launch_bounds__(32 * WARPS) k_miller6(Miller6Batch b, Fq12* __
   const int g = lane < 30 ? lane / 6 : 4;
   uint32_t* wsm = smem + warp * 5 * GW;
   Ctx c{lane % 6, wsm + g * GW};
+  c.zero = smem + WARPS * 5 * GW;  // l6.cuh's padding operand: sixteen words behind the groups, one slot per CTA
+  if (threadIdx.x < 12) smem[WARPS * 5 * GW + threadIdx.x] = 0;
+  __syncthreads();
   uint32_t* pairs = c.sm + OFF_F + M6_NREG * F12W;
   const uint32_t gw = blockIdx.x * WARPS + warp;
   const uint32_t seg = gw / b.wps, wl = gw % b.wps;
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(32 * WARPS) k_miller6(Miller6Batch b, Fq12* __
         }
       }
       uint32_t* pb = pairs + j * PAIR_WORDS;
-      st2(pb + PB_P, Fq2{P.x, P.y});
+      stage_pair_p(pb, P);
       set_pair_q(pb, Q);
       pb[PB_VALID] = valid;
     }
@@ -160,7 +164,7 @@ static __device__ __forceinline__ Ctx3 ctx18(uint32_t* wsm, int group_words_no_b
   const int vl = (threadIdx.x & 31) % 18;  // lanes 18..31 mirror lanes 0..13: same addresses, same values
   if ((threadIdx.x & 31) < 12) wsm[group_words_no_bus + BUS_ZERO + (threadIdx.x & 31)] = 0;  // l6.cuh's padding operand
   __syncwarp();
-  return Ctx3{vl / 3, wsm, nullptr, vl % 3, wsm + group_words_no_bus, 0};
+  return Ctx3{vl / 3, wsm, nullptr, vl % 3, wsm + group_words_no_bus, 0, wsm + group_words_no_bus + BUS_ZERO};
 }
 constexpr int M18_WARPS = 4;
 template <int KP>
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(32 * M18_WARPS) k_miller18(Miller6Batch b, Fq1
         }
       }
       uint32_t* pb = pairs + j * PAIR_WORDS;
-      st2(pb + PB_P, Fq2{P.x, P.y});
+      stage_pair_p(pb, P);
       set_pair_q(pb, Q);
       pb[PB_VALID] = valid;
     }
@@ -354,7 +358,7 @@ int ripp_gt_multiexp_l6(ripp_ctx* ctx, const void* in, const void* sc, size_t n,
 
 template <int KP>
 static int launch_miller6(ripp_ctx* ctx, Miller6Batch& b, size_t n, Fq12* dst, size_t* nwarps_out) {
-  constexpr int SM = M6_WARPS * 5 * group_words(M6_NREG, KP) * 4;
+  constexpr int SM = m6_smem_bytes(KP);
   b.wps = (uint32_t)((n + 5 * KP - 1) / (5 * KP));
   size_t nwarps = (size_t)b.wps * b.nseg;
   unsigned blocks = (unsigned)((nwarps + M6_WARPS - 1) / M6_WARPS);
@@ -523,9 +527,9 @@ int ripp_pairing6_init_device() {
   CU(cudaGetLastError());
   CU(cudaFuncSetAttribute(k_reduce6<M6_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 6 * R6_GROUP_WORDS * 4));
   CU(cudaFuncSetAttribute(k_final_exp6, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 6 * FE_GROUP_WORDS * 4));
-  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 5 * group_words(M6_NREG, 1) * 4));
-  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 5 * group_words(M6_NREG, 2) * 4));
-  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 5 * group_words(M6_NREG, 3) * 4));
-  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_WARPS * 5 * group_words(M6_NREG, 4) * 4));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, m6_smem_bytes(1)));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, m6_smem_bytes(2)));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, m6_smem_bytes(3)));
+  CU(cudaFuncSetAttribute(k_miller6<M6_WARPS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, m6_smem_bytes(4)));
   return RIPP_OK;
 }

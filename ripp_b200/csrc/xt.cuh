@@ -97,18 +97,40 @@ RIPP_HD void mul3(const Team& tm, const Fq& u0, const Fq& v0, const Fq& u1, cons
 RIPP_HD void mul3(const Team& tm, const Fq2& u0, const Fq2& v0, const Fq2& u1, const Fq2& v1, const Fq2& u2, const Fq2& v2,
                   Fq2& p0, Fq2& p1, Fq2& p2) {
   uint32_t* b = tm.bus + tm.par * TeamOf<Fq2>::BUS_WORDS;
-  tm.par ^= 1;
+  uint32_t* b2 = tm.bus + (tm.par ^ 1) * TeamOf<Fq2>::BUS_WORDS;  // two exchanges per level: the parity is unchanged after it
   const int u = tm.t / 3, r = tm.t % 3;
   Fq2 x = sel3(u, u0, u1, u2), y = sel3(u, v0, v1, v2);
-  // Karatsuba part r of x * y
-  bus_st(b + tm.t * 12, fqmul(sel3(r, x.c0, x.c1, x.c0 + x.c1), sel3(r, y.c0, y.c1, y.c0 + y.c1)));
-  sync(tm);
-  Fq2* out[3] = {&p0, &p1, &p2};
+  // Karatsuba part r of x * y; the cross operands stay unreduced (< 2p each: the product is < 4 p^2 / R + p < 2p,
+  // which its final subtraction handles)
+  Fq sx, sy;
+  {
+    using namespace limb;
+    add_cc(sx.v[0], x.c0.v[0], x.c1.v[0]);
 #pragma unroll
-  for (int j = 0; j < 3; j++) {
-    Fq t0 = bus_ld(b + (3 * j) * 12), t1 = bus_ld(b + (3 * j + 1) * 12), t2 = bus_ld(b + (3 * j + 2) * 12);
-    *out[j] = {t0 - t1, t2 - t0 - t1};
+    for (int i = 1; i < 11; i++) addc_cc(sx.v[i], x.c0.v[i], x.c1.v[i]);
+    addc(sx.v[11], x.c0.v[11], x.c1.v[11]);
+    add_cc(sy.v[0], y.c0.v[0], y.c1.v[0]);
+#pragma unroll
+    for (int i = 1; i < 11; i++) addc_cc(sy.v[i], y.c0.v[i], y.c1.v[i]);
+    addc(sy.v[11], y.c0.v[11], y.c1.v[11]);
   }
+  bus_st(b + tm.t * 12, fqmul(sel3(r, x.c0, x.c1, sx), sel3(r, y.c0, y.c1, sy)));
+  sync(tm);
+  // Second exchange: lane t < 6 recombines ONE component of one product (lanes 6..8 repeat lanes 0..2) instead of
+  // every lane recombining all six -- nine modular subtractions on each lane's chain become two.
+  {
+    const int t6 = tm.t % 6, j = t6 >> 1;
+    const bool c1 = t6 & 1;
+    const uint32_t* q = b + (3 * j) * 12;
+    Fq t0 = bus_ld(q), t1 = bus_ld(q + 12), t2 = bus_ld(q + 24);
+    Fq d = sel3(c1 ? 1 : 0, t0, t2, t2) - t1;
+    Fq e = d - t0;
+    if (tm.t < 6) bus_st(b2 + t6 * 12, sel3(c1 ? 1 : 0, d, e, e));
+  }
+  sync(tm);
+  p0 = {bus_ld(b2), bus_ld(b2 + 12)};
+  p1 = {bus_ld(b2 + 24), bus_ld(b2 + 36)};
+  p2 = {bus_ld(b2 + 48), bus_ld(b2 + 60)};
 }
 
 // dbl-2009-l in three levels; the identity (Z = 0) maps to itself

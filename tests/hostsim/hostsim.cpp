@@ -101,7 +101,8 @@ static void run_group(Fn fn, int nreg = 8) {
   std::vector<std::thread> th;
   for (int t = 0; t < 6 * W; t++)
     th.emplace_back([&, t] {
-      l6::CtxT<W> c{t / W, sm.data(), &bar, t % W, sm.data() + l6::group_words(nreg, 4), 0};
+      l6::CtxT<W> c{t / W, sm.data(), &bar, t % W, sm.data() + l6::group_words(nreg, 4), 0,
+                    sm.data() + l6::group_words(nreg, 4) + l6::BUS_ZERO};
       fn(c);
     });
   for (auto& t : th) t.join();
@@ -167,7 +168,7 @@ static void l6_miller(const uint32_t* p, const uint32_t* q, const int* valid, in
       for (int j = 0; j < npairs; j++) {
         uint32_t* pb = pairs + j * l6::PAIR_WORDS;
         G1Aff P = ld<G1Aff>(p + 24 * j);
-        l6::st2(pb + l6::PB_P, Fq2{P.x, P.y});
+        l6::stage_pair_p(pb, P);
         l6::set_pair_q(pb, q + 48 * j);  // Q is read through its address (same words as a packed G2Aff)
         pb[l6::PB_VALID] = valid[j];
       }

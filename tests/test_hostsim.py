@@ -162,7 +162,7 @@ def test_l6_six_lane_fq12(hostsim, eng):
 
 def test_l18_lazy_sums(hostsim):
     """l6.cuh's address-driven lazy sums behind the eighteen-lane Granger-Scott squaring: the single-quotient reduction
-    of a 13-limb value below 32p (exhaustive over the 10 bits the estimate reads, both ends of every bucket), and the
+    of a 13-limb value below 2^386 (exhaustive over the 10 bits the estimate reads, both ends of every bucket), and the
     squaring against the six-lane body on inputs that drive every unreduced sum to its bound."""
     import numpy as np
 
@@ -171,16 +171,15 @@ def test_l18_lazy_sums(hostsim):
 
     radix = 1 << 384
     h = 0
-    while (h << 376) < 32 * E.P:
-        lo, hi = h << 376, min(((h + 1) << 376), 32 * E.P) - 1
+    while h < 1024:
+        lo, hi = h << 376, ((h + 1) << 376) - 1
         q_est = (h * 2520) >> 16
         for t in (lo, hi):
             assert 0 <= t // E.P - q_est <= 1
         h += 1
-    assert h <= 1024
-    cases = [0, 1, E.P - 1, E.P, E.P + 1, 2 * E.P - 1, 2 * E.P, 31 * E.P, 32 * E.P - 1]
-    cases += [k * E.P + d for k in range(1, 32) for d in (-1, 0, 1)]
-    cases += [rnd.randrange(32 * E.P) for _ in range(300)]
+    cases = [0, 1, E.P - 1, E.P, E.P + 1, 2 * E.P - 1, 2 * E.P, 31 * E.P, 32 * E.P - 1, (1 << 386) - 1]
+    cases += [k * E.P + d for k in range(1, 40) for d in (-1, 0, 1) if k * E.P + d < (1 << 386)]
+    cases += [rnd.randrange(1 << 386) for _ in range(300)]
     for t in cases:
         got = C._int(hostsim.call("hs_lz_reduce13", words13(t), out=12))
         assert got == t % E.P, hex(t)
