@@ -772,6 +772,77 @@ __global__ void __launch_bounds__(32 * XT_WARPS) k_fold4_xt(const FoldJobs jobs)
     if (i < job.n) ((Fr*)job.out)[i] = ((const Fr*)job.hi)[i] * job.s + ((const Fr*)job.lo)[i];
   }
 }
+// Part-parallel variant for the short vectors of the late rounds (n <= xp_max_n()): a CTA of four warps; warp w works
+// on endomorphism part w % m of the elements of group w / m (m = 4 parts for G2: one group of 3 elements per CTA; m = 2
+// for G1: two groups of 10), every team brings its part to affine form, and after the CTA barrier the part-0 warp adds
+// lo and the m parts.  Same group element as fold_xt_body (the sum is exact), half the dependent chain.
+constexpr int XP_WARPS = 4;
+template <class F>
+struct XpLayout {
+  typedef xt::TeamOf<F> TO;
+  static constexpr int AW = sizeof(Aff<F>) / 4;
+  static constexpr int TEAM_WORDS = 2 * TO::BUS_WORDS + AW;
+  static constexpr int PARTS_AT = XP_WARPS * TO::PER_WARP * TEAM_WORDS;
+  static constexpr int WORDS = PARTS_AT + XP_WARPS * TO::PER_WARP * AW;  // (group, element, part) slots: groups * m = XP_WARPS
+};
+template <class F>
+__device__ __forceinline__ void fold_xp_body(uint32_t* sm, const FoldJob& job, uint32_t block) {
+  typedef xt::TeamOf<F> TO;
+  typedef XpLayout<F> L;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int m = sizeof(F) == sizeof(Fq) ? 2 : 4;  // endo_digits' MAXD: the layout does not depend on the scalar
+  const int part = warp % m, grp = warp / m, groups = XP_WARPS / m;
+  const int vl = lane % (TO::LANES * TO::PER_WARP);
+  const int e = vl / TO::LANES;
+  size_t i = ((size_t)block * groups + grp) * TO::PER_WARP + e;
+  const bool live = i < job.n && lane == vl;
+  if (i >= job.n) i = job.n - 1;
+  uint32_t* scratch = sm + (warp * TO::PER_WARP + e) * L::TEAM_WORDS;
+  uint32_t* slots = sm + L::PARTS_AT + ((grp * TO::PER_WARP + e) * m) * L::AW;
+  xt::Team tm{vl % TO::LANES, scratch, 0, nullptr};
+  {
+    Jac<F> acc = xt::part_mul<F>(tm, ((const Aff<F>*)job.hi)[i], job.c, m, part, scratch + 2 * TO::BUS_WORDS);
+    Aff<F> pa = xt::to_affine<F>(tm, acc);
+    if (tm.t == 0 && lane == vl) xt::aff_st<F>(slots + part * L::AW, pa);
+  }
+  __syncthreads();
+  if (part == 0) {
+    Jac<F> s = Jac<F>::from_affine(((const Aff<F>*)job.lo)[i]);
+#pragma unroll 1
+    for (int t = 0; t < m; t++) s = xt::madd<F>(tm, s, xt::aff_ld<F>(slots + t * L::AW));
+    Aff<F> o = xt::to_affine<F>(tm, s);
+    if (live && tm.t == 0) ((Aff<F>*)job.out)[i] = o;
+  }
+}
+__global__ void __launch_bounds__(32 * XP_WARPS) k_fold4_xp(const FoldJobs jobs) {
+  constexpr int W1 = XpLayout<Fq>::WORDS, W2 = XpLayout<Fq2>::WORDS;
+  __shared__ __align__(16) uint32_t sm[W1 > W2 ? W1 : W2];
+  int k = 0;
+#pragma unroll
+  for (int t = 1; t < 4; t++)
+    if (jobs.j[t].type && blockIdx.x >= jobs.j[t].first_block) k = t;
+  const FoldJob& job = jobs.j[k];
+  const uint32_t block = blockIdx.x - job.first_block;
+  if (job.type == 1) {
+    fold_xp_body<Fq>(sm, job, block);
+  } else if (job.type == 2) {
+    fold_xp_body<Fq2>(sm, job, block);
+  } else if (job.type == 3) {
+    size_t i = (size_t)block * blockDim.x + threadIdx.x;
+    if (i < job.n) ((Fr*)job.out)[i] = ((const Fr*)job.hi)[i] * job.s + ((const Fr*)job.lo)[i];
+  }
+}
+// vectors up to this length fold part-parallel (RIPP_B200_XP_MAX overrides; 0 = never).  Measured on the 2^12 aggregation
+// (gpurun_out r2i): launch 1.25 ms against 1.45-1.6 ms for k_fold4_xt at n <= 128 (the G1 vectors' 128-bit parts are
+// the chain that remains), level at n = 256, slower above; whole aggregation 72.6 / 73.9 / 75.3 ms at 128 / 256 / 512.
+static size_t xp_max_n() {
+  static const long v = [] {
+    const char* e = getenv("RIPP_B200_XP_MAX");
+    return e ? atol(e) : 128L;
+  }();
+  return (size_t)v;
+}
+
 // types[t] in {0 none, 1 G1, 2 G2, 3 Fr}; out[t][i] = hi[t][i] * c[t] + lo[t][i].  Returns RIPP_OK and *fused = 1 when the
 // fused launch was used (all vectors short enough for lane teams), *fused = 0 when the caller should fold one by one.
 int ripp_fold4_internal(ripp_ctx* ctx, const int* types, const void* const* hi, const void* const* lo, const void* const* cs, size_t n,
@@ -783,6 +854,7 @@ int ripp_fold4_internal(ripp_ctx* ctx, const int* types, const void* const* hi, 
   memset(&jobs, 0, sizeof(jobs));
   uint32_t nblocks = 0;
   int nj = 0;
+  const bool xp = n <= xp_max_n();
   for (int t = 0; t < 4; t++) {
     if (!types[t] || !hi[t]) continue;
     FoldJob& j = jobs.j[nj++];
@@ -796,14 +868,15 @@ int ripp_fold4_internal(ripp_ctx* ctx, const int* types, const void* const* hi, 
     if (types[t] == 1) {
       j.c = endo_bits<Fq>(cs[t]);
       uint32_t warps = (uint32_t)((n + xt::TeamOf<Fq>::PER_WARP - 1) / xt::TeamOf<Fq>::PER_WARP);
-      blocks = (warps + XT_WARPS - 1) / XT_WARPS;
+      blocks = xp ? (warps * 2 + XP_WARPS - 1) / XP_WARPS : (warps + XT_WARPS - 1) / XT_WARPS;
     } else if (types[t] == 2) {
       j.c = endo_bits<Fq2>(cs[t]);
       uint32_t warps = (uint32_t)((n + xt::TeamOf<Fq2>::PER_WARP - 1) / xt::TeamOf<Fq2>::PER_WARP);
-      blocks = (warps + XT_WARPS - 1) / XT_WARPS;
+      blocks = xp ? (warps * 4 + XP_WARPS - 1) / XP_WARPS : (warps + XT_WARPS - 1) / XT_WARPS;
     } else {
       memcpy(j.s.v, cs[t], sizeof(Fr));
-      blocks = (uint32_t)((n + 32 * XT_WARPS - 1) / (32 * XT_WARPS));
+      const uint32_t bt = 32 * (xp ? XP_WARPS : XT_WARPS);
+      blocks = (uint32_t)((n + bt - 1) / bt);
     }
     nblocks += blocks;
   }
@@ -813,7 +886,10 @@ int ripp_fold4_internal(ripp_ctx* ctx, const int* types, const void* const* hi, 
   }
   // jobs are packed at the front of the array in launch order: unused slots keep type 0
   TimeScope ts_(ctx, RIPP_T_FOLD);
-  k_fold4_xt<<<nblocks, 32 * XT_WARPS, 0, ctx->stream>>>(jobs);
+  if (xp)
+    k_fold4_xp<<<nblocks, 32 * XP_WARPS, 0, ctx->stream>>>(jobs);
+  else
+    k_fold4_xt<<<nblocks, 32 * XT_WARPS, 0, ctx->stream>>>(jobs);
   LAUNCHED(ctx);
   *fused = 1;
   return RIPP_OK;

@@ -272,6 +272,24 @@ static void run_xt(Fn fn) {
   for (auto& t : th) t.join();
   pthread_barrier_destroy(&bar);
 }
+// the same fold as k_fold4_xp computes it: one team per endomorphism part (here one after the other), parts brought to
+// affine form, then lo + the parts on one team
+template <class F, int M>
+static void xp_fold(const uint32_t* p, const uint32_t* lo, const EndoBits& c, uint32_t* out) {
+  std::vector<Aff<F>> parts(M);
+  for (int part = 0; part < M; part++)
+    run_xt<F>([&](const xt::Team& tm) {
+      Jac<F> acc = xt::part_mul<F>(tm, ld<Aff<F>>(p), c, M, part, tm.bus + 2 * xt::TeamOf<F>::BUS_WORDS);
+      Aff<F> pa = xt::to_affine<F>(tm, acc);
+      if (tm.t == 0) parts[part] = pa;
+    });
+  run_xt<F>([&](const xt::Team& tm) {
+    Jac<F> s = Jac<F>::from_affine(ld<Aff<F>>(lo));
+    for (int t = 0; t < M; t++) s = xt::madd<F>(tm, s, parts[t]);
+    Aff<F> o = xt::to_affine<F>(tm, s);
+    if (tm.t == 0) st(out, o);
+  });
+}
 extern "C" {
 // out = k * p + lo exactly as k_fold_xt computes it (k = 8 canonical words; group 1 = G1, 2 = G2)
 void hs_xt_endo_fold(int group, const uint32_t* p, const uint32_t* lo, const uint32_t* k, uint32_t* out) {
@@ -291,6 +309,16 @@ void hs_xt_endo_fold(int group, const uint32_t* p, const uint32_t* lo, const uin
       G2Aff o = xt::to_affine<Fq2>(tm, acc);
       if (tm.t == 0) st(out, o);
     });
+  }
+}
+void hs_xp_endo_fold(int group, const uint32_t* p, const uint32_t* lo, const uint32_t* k, uint32_t* out) {
+  EndoBits c;
+  if (group == 1) {
+    endo_decompose<1>(k, c);
+    xp_fold<Fq, 2>(p, lo, c, out);
+  } else {
+    endo_decompose<2>(k, c);
+    xp_fold<Fq2, 4>(p, lo, c, out);
   }
 }
 }

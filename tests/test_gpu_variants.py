@@ -3,7 +3,8 @@ re-run in a subprocess with the non-default kernels selected -- thread-per-pair 
 (RIPP_B200_PAIRING=thread), the one-thread-per-element fold kernels with and without the endomorphisms
 (RIPP_B200_FOLD=endo / plain), three-warp teams (RIPP_B200_FOLD=w3), one thread per element for the scalings, and the
 six-lane shape everywhere (RIPP_B200_L18_WARPS=0), several pairs per
-eighteen-lane warp (RIPP_B200_L18_KP=4)."""
+eighteen-lane warp (RIPP_B200_L18_KP=4), and the fused folds of a round without / always with one team per
+endomorphism part (RIPP_B200_XP_MAX=0 / 100000)."""
 import os
 import subprocess
 import sys
@@ -23,6 +24,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     {"RIPP_B200_SCALE_PARTS_MAX": "0", "RIPP_B200_SCALE_XT_MAX": "100000"},
     {"RIPP_B200_L18_WARPS": "0"},
     {"RIPP_B200_L18_KP": "4"},
+    {"RIPP_B200_XP_MAX": "0"},
+    {"RIPP_B200_XP_MAX": "100000"},
 ], ids=lambda e: ",".join("%s=%s" % kv for kv in e.items()))
 def test_variant_paths(env):
     sel = ["tests/test_gpu_msm.py::test_folds", "tests/test_gpu_msm.py::test_scalings_match_oracle",

@@ -300,6 +300,15 @@ def test_xt_lane_team_folds(hostsim):
 
     _check_efold(efold, p1, l1, p2, l2)
 
+    # part-parallel shape (k_fold4_xp): one team per endomorphism part, the parts added afterwards
+    def pfold(group, p, lo, k):
+        enc, dec, w = (C.g1_enc, C.g1_dec, 24) if group == 1 else (C.g2_enc, C.g2_dec, 48)
+        return dec(hostsim.call("hs_xp_endo_fold", group, enc(p), enc(lo), C.scalar_words(k), out=w))
+
+    _check_efold(pfold, p1, l1, p2, l2)
+    for k in (E.X_ABS, E.X_ABS**2 - 1, E.X_ABS**3 + 5, 2):  # scalars that leave some parts empty
+        assert pfold(1, p1, l1, k) == E.g1_add(E.g1_mul(p1, k), l1) and pfold(2, p2, l2, k) == E.g2_add(E.g2_mul(p2, k), l2)
+
 
 def test_endomorphisms(hostsim):
     """phi = [x^2 - 1] on G1 and -psi = [|x|] on G2 (curve.cuh endo_map, constants from tools/gen_constants.py)."""
