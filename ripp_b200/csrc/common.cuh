@@ -50,6 +50,12 @@ struct ripp_ctx {
   // multi-GPU (comm.cu): one process per GPU, an NCCL communicator owned by the top-level context
   void* comm;  // ncclComm_t
   int rank, world;
+  // set (on the parent) by a GIPA recursion once its vectors are short and the GPU mostly idle: side products that are
+  // not on the critical path wait for it instead of competing with the long early rounds (gipa.cu, aggregate)
+  int rounds_short;
+  // work nothing waits for (the aggregation's side products): the pairing engine packs it into the fewest CTAs so that
+  // the lone warps of the critical path keep sub-partitions to themselves
+  int background;
 };
 #define RIPP_PINNED_BYTES 16384
 

@@ -338,6 +338,7 @@ static int gipa_prove(ripp_ctx* ctx, const GipaSpec& sp, const void* a_in, const
     std::vector<Val> com(6);
     double t_r0 = now_ms();
     OK(eval_products(ctx, 6, xs, ys, split, com.data()));
+    if (split <= 32 && ctx->parent) __atomic_store_n(&ctx->parent->rounds_short, 1, __ATOMIC_RELEASE);
     if (trace_on()) fprintf(stderr, "[trace] gipa(a=%d,b=%d) n'=%zu products+prev folds %.2f ms\n", sp.a, sp.b, split, now_ms() - t_r0);
     // gipa.rs:235-258 -- Fiat-Shamir challenge
     Fr c, c_inv;
@@ -717,7 +718,11 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
   if (trace_on()) fprintf(stderr, "[trace] aggregate prologue (3 commitments, r, scalings queued) %.2f ms\n", now_ms() - t_a0);
   Bytes proof_ab, proof_c;
   {
+    __atomic_store_n(&ctx->rounds_short, 0, __ATOMIC_RELEASE);
+    ik->background = 1;
     std::thread tip([&] {
+      // 2 n pairs that nothing waits for: started once the pairing recursion has left its long (throughput-bound) rounds
+      while (!__atomic_load_n(&ctx->rounds_short, __ATOMIC_ACQUIRE)) std::this_thread::sleep_for(std::chrono::microseconds(20));
       Slice xs[2] = {Slice{VT_G1, W + o_ar}, Slice{VT_G1, W + o_ar}};
       Slice ys[2] = {Slice{VT_G2, (const char*)b_dev}, Slice{VT_G2, W + o_ck1r}};
       st_ip = eval_products(ik, 2, xs, ys, n, ipv);
@@ -728,6 +733,7 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
       if (st_c != RIPP_OK) err_c = ripp_err_slot();
     });
     st_a = tipa_prove(ka, RIPP_GIPA_PAIRING, srs_g1_dev, srs_g2_dev, W + o_ar, b_dev, W + o_ck1r, ck2, n, r, &proof_ab);
+    __atomic_store_n(&ctx->rounds_short, 1, __ATOMIC_RELEASE);  // n < 2 or a failed recursion never reaches the short rounds
     tc.join();
     tip.join();
   }

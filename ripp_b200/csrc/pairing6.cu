@@ -471,6 +471,7 @@ int ripp_pairing_batch_l6(ripp_ctx* ctx, int nseg, const void* const* g1, const 
       return e ? atoi(e) : 0;
     }();
     if (force >= 1 && force <= 4) kp = force;
+    if (ctx->background) kp = 4;
   }
   const uint32_t R = 8;
   size_t nwarps = 0;
