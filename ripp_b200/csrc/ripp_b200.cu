@@ -236,6 +236,8 @@ __global__ void __launch_bounds__(64, 4) k_scale(const Aff<F>* __restrict__ pts,
 // multiplications with 128-bit (G1, m = 2) / 64-bit (G2, m = 4) scalars: m times the parallelism at 1/m of the chain,
 // then one thread per element adds the m parts and normalises.  Lane teams (k_scale_xt below, kept for A/B runs) were
 // measured SLOWER here (8.8 ms): at 1366 warps the redundant glue of nine lanes per element is throughput, not latency.
+// So were three-WARP teams per 32 (element, part) chains (x3.cuh, G2: 4.96 ms against 4.06 ms, gpurun_out r2j): the CTA
+// barriers of ~1150 exchanges and 2.4 KB of spills cost more than the shorter chain returns.
 template <class F, bool GEN>
 __global__ void __launch_bounds__(64, 4) k_scale_parts(const Aff<F>* __restrict__ pts, const Fr* __restrict__ sc, size_t n, int m,
                                                     Jac<F>* __restrict__ parts, Aff<F> gen) {

@@ -41,6 +41,14 @@ int lane_r();                                             // provided by the hos
 void gather3(const Fq& mine, Fq& t0, Fq& t1, Fq& t2);
 #endif
 
+// The exchanges are CTA barriers (bar.sync, warp-aligned): a warp whose lanes left a per-lane branch -- the patch of an
+// exceptional lane -- must be whole again before it reaches the next one, or its parts arrive separately and the
+// barrier releases early (seen as wrong sums once every lane had its own digits, k_scale_parts_w3).
+RIPP_HD void reconverge() {
+#if defined(__CUDA_ARCH__)
+  __syncwarp();
+#endif
+}
 RIPP_HD Fq fqmul(const Fq& a, const Fq& b) { return Fq::mul_fn(a, b); }
 RIPP_HD Fq sel3(int r, const Fq& a, const Fq& b, const Fq& c) {
   Fq o;
@@ -122,7 +130,8 @@ static RIPP_FN Jac<Fq> g1_madd(Jac<Fq> p, Aff<Fq> q) {
   r.z = ZH2 - Z1Z1 - HH;
   mul3(rr, V - r.x, p.y, J, p.y, J, M, YJ, d0);
   r.y = M - YJ.dbl();
-  if (q.is_inf() || p.is_inf() || H.is_zero()) return p.add_mixed_body(q);
+  if (q.is_inf() || p.is_inf() || H.is_zero()) r = p.add_mixed_body(q);
+  reconverge();
   return r;
 }
 
@@ -152,7 +161,8 @@ RIPP_HD Jac<Fq2x3> g2_madd(const Jac<Fq2x3>& p, const Aff<Fq2x3>& q) {
   r.x = rr.sqr() - J - V.dbl();
   r.y = rr * (V - r.x) - (p.y * J).dbl();
   r.z = (p.z + H).sqr() - Z1Z1 - HH;
-  if (q.is_inf() || p.is_inf() || H.is_zero()) return coop(plain(p).add_mixed_body(plain(q)));
+  if (q.is_inf() || p.is_inf() || H.is_zero()) r = coop(plain(p).add_mixed_body(plain(q)));
+  reconverge();
   return r;
 }
 
