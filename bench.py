@@ -55,7 +55,7 @@ LOG_GIPA = 18
 CLASS_KERNEL = {
     "msm_sort": ("k_msm_endo_expand / prepare / scan / scatter / size sort", "msm_sort"),
     "msm_reduce": ("k_msm_bucket_reduce + k_msm_window_sum + k_msm_horner_xt (bucket reduction and Horner tail)", "msm_reduce"),
-    "fold": ("k_fold4_xt (the four folds of a round in one launch: A' = A_R c + A_L, ..., gipa.rs:261-291) / k_fold_endo", "fold"),
+    "fold": ("k_fold4_xp / k_fold4_xt (the four folds of a round in one launch: A' = A_R c + A_L, ..., gipa.rs:261-291) / k_fold_endo", "fold"),
     # the class's most frequent launch in the 2^12 aggregation is k_miller18<1> (18 of 26): its capture gives `traffic`;
     # the throughput kernel k_miller6<4,4> at 2^16 pairs has its own capture under roofline["miller_2^16"]
     "miller": ("k_miller18 / k_miller6 + Fq12 product tree (cfg_multi_pairing, inner_products/src/lib.rs:77-116)", "miller18"),

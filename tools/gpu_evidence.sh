@@ -17,7 +17,7 @@ cap() {  # name, kernel regex, skip, count, command...
 }
 cap miller6 k_miller6 0 1 python tools/time_pairing.py 16
 cap msm_acc k_msm_accumulate 0 1 python tools/time_msm.py 18
-cap fold k_fold4_xt 14 2 python tools/time_tipp.py 12 1
+cap fold k_fold4_xp 6 2 python tools/time_tipp.py 12 1
 cap fexp k_final_exp18 10 1 python tools/time_tipp.py 12 1
 cap miller18 k_miller18 10 1 python tools/time_tipp.py 12 1
 cap scale k_scale_parts 0 2 python tools/time_tipp.py 12 1
