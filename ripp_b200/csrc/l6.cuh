@@ -132,6 +132,21 @@ RIPP_HD void add_unreduced(uint32_t* s, const Fq& a, const Fq& b) {
   for (int i = 1; i < 11; i++) addc_cc(s[i], a.v[i], b.v[i]);
   addc(s[11], a.v[11], b.v[11]);
 }
+// acc (12 limbs) += x;  the caller's bound keeps the sum below 2^384
+RIPP_HD void lz_add12(uint32_t* acc, const Fq& x) {
+  using namespace limb;
+  add_cc(acc[0], acc[0], x.v[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) addc_cc(acc[i], acc[i], x.v[i]);
+  addc(acc[11], acc[11], x.v[11]);
+}
+RIPP_HD void lz_sub12(uint32_t* acc, const Fq& x) {
+  using namespace limb;
+  sub_cc(acc[0], acc[0], x.v[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) subc_cc(acc[i], acc[i], x.v[i]);
+  subc(acc[11], acc[11], x.v[11]);
+}
 // One out-of-line copy of the Fq2 product on the device (operands by value, in registers) instead of an inlined
 // copy per use: the Miller loop body drops from 24 k to 18 k instructions (2^16 pairs: 21.4 -> 21.1 ms, small
 // batches 3.0 -> 2.7 ms: fewer instruction-cache misses for the lone warps of the late GIPA rounds).
@@ -209,6 +224,60 @@ RIPP_HD void f2_mac(const C& c, Acc1& A, const Fq2& a, const Fq2& b) {
   detail::wide_mul<FqParams>(t, u, v);
   detail::wide_add<24>(A.s, t);
 }
+// W = 3, operands by ADDRESS (canonical Fq2 values a, b in shared memory): the role's operand pair is formed as an
+// unreduced sum of slots instead of loading both components, reducing xi b and selecting --
+//   u = a0 | a1 | a0 + a1;   v = b0 | b1 | b0 + b1;   with `wrap` (the term carries xi):  v = b0 - b1 + p | b0 + b1 | 2 b0
+// (the three are the Karatsuba operands of xi b = (b0 - b1, b0 + b1) modulo p).  u, v < 2p: six products stay below
+// 24 p^2, the bound f2_finish already reduces from.
+template <class C>
+RIPP_HD void f2_mac_addr(const C& c, Acc1& A, const uint32_t* a, const uint32_t* b, bool wrap) {
+  using namespace limb;
+  const int r = c.role;
+  const uint32_t* Z = c.zero;
+  Fq u = ld1(r == 1 ? a + 12 : a);
+  lz_add12(u.v, ld1(r == 2 ? a + 12 : Z));
+  Fq v = ld1((!wrap && r == 1) ? b + 12 : b);
+  lz_add12(v.v, ld1(wrap ? (r == 0 ? Z : (r == 1 ? b + 12 : b)) : (r == 2 ? b + 12 : Z)));
+  const bool neg = wrap && r == 0;
+  const uint32_t m = neg ? 0xffffffffu : 0u;
+  add_cc(v.v[0], v.v[0], FqParams::p(0) & m);
+#pragma unroll
+  for (int i = 1; i < 11; i++) addc_cc(v.v[i], v.v[i], FqParams::p(i) & m);
+  addc(v.v[11], v.v[11], FqParams::p(11) & m);
+  lz_sub12(v.v, ld1(neg ? b + 12 : Z));
+  uint32_t t[24];
+  detail::wide_mul<FqParams>(t, u.v, v.v);
+  detail::wide_add<24>(A.s, t);
+}
+// The squaring's term  [2] [xi] a_i a_j  the same way: `on` = false adds nothing (coefficients with three terms), `twice`
+// doubles v (cross terms).  u < 2p, v < 4p: four terms stay below 32 p^2, reduced by f2_finish(c, acc, 4).
+template <class C>
+RIPP_HD void f2_mac_addr_sq(const C& c, Acc1& A, const uint32_t* a, const uint32_t* b, bool wrap, bool twice, bool on) {
+  using namespace limb;
+  const int r = c.role;
+  const uint32_t* Z = c.zero;
+  Fq u = ld1(!on ? Z : (r == 1 ? a + 12 : a));
+  lz_add12(u.v, ld1((on && r == 2) ? a + 12 : Z));
+  Fq v = ld1((!wrap && r == 1) ? b + 12 : b);
+  lz_add12(v.v, ld1(wrap ? (r == 0 ? Z : (r == 1 ? b + 12 : b)) : (r == 2 ? b + 12 : Z)));
+  const bool neg = wrap && r == 0;
+  const uint32_t m = neg ? 0xffffffffu : 0u;
+  add_cc(v.v[0], v.v[0], FqParams::p(0) & m);
+#pragma unroll
+  for (int i = 1; i < 11; i++) addc_cc(v.v[i], v.v[i], FqParams::p(i) & m);
+  addc(v.v[11], v.v[11], FqParams::p(11) & m);
+  lz_sub12(v.v, ld1(neg ? b + 12 : Z));
+  {
+    const uint32_t m2 = twice ? 0xffffffffu : 0u;
+    Fq w;
+#pragma unroll
+    for (int i = 0; i < 12; i++) w.v[i] = v.v[i] & m2;
+    lz_add12(v.v, w);
+  }
+  uint32_t t[24];
+  detail::wide_mul<FqParams>(t, u.v, v.v);
+  detail::wide_add<24>(A.s, t);
+}
 template <class C>
 RIPP_HD Fq2 f2_finish(const C&, Acc3& A) {
   using namespace limb;
@@ -226,9 +295,9 @@ RIPP_HD Fq2 f2_finish(const C&, Acc3& A) {
   return {c0, c1};
 }
 template <class C>
-RIPP_HD Fq2 f2_finish(const C& c, Acc1& A) {
+RIPP_HD Fq2 f2_finish(const C& c, Acc1& A, int subs = 3) {
   Fq r, t0, t1, t2;
-  detail::redc_wide<FqParams>(r.v, A.s, 3);  // role 2: < 24 p^2 / R + p < 3.5 p
+  detail::redc_wide<FqParams>(r.v, A.s, subs);  // role 2: < 24 p^2 / R + p < 3.5 p  (squaring by address: 32 p^2, 4.3 p, subs = 4)
   gather3(c, r, t0, t1, t2);
   return {t0 - t1, t2 - t0 - t1};
 }
@@ -303,8 +372,12 @@ RIPP_HD void mul_p_body(const C& c, uint32_t* D, const uint32_t* A, const uint32
     int j = c.k - i;
     bool wrap = j < 0;
     j += wrap ? 6 : 0;
-    Fq2 b = ld2(B + j * FQ2W);
-    f2_mac(c, acc, ld2(A + i * FQ2W), f2sel(wrap, f2xi(b), b));  // xi applied to the operand: stays linear
+    if constexpr (C::W == 3) {
+      f2_mac_addr(c, acc, A + i * FQ2W, B + j * FQ2W, wrap);
+    } else {
+      Fq2 b = ld2(B + j * FQ2W);
+      f2_mac(c, acc, ld2(A + i * FQ2W), f2sel(wrap, f2xi(b), b));  // xi applied to the operand: stays linear
+    }
   }
   Fq2 out = f2_finish(c, acc);
   sync(c);
@@ -349,13 +422,18 @@ RIPP_HD void sqr_body(const C& c, int dst, int a) {
       wrap = take ? w : wrap;
       found = found || take;
     }
-    Fq2 x = ld2(A + ii * FQ2W), y = ld2(A + jj * FQ2W);
-    y = f2sel(ii != jj, f2dbl(y), y);
-    y = f2sel(wrap, f2xi(y), y);
-    x = f2sel(found, x, Fq2::zero());  // coefficients with only three terms add 0 in the fourth slot
-    f2_mac(c, acc, x, y);
+    if constexpr (C::W == 3) {
+      f2_mac_addr_sq(c, acc, A + ii * FQ2W, A + jj * FQ2W, wrap, ii != jj, found);
+    } else {
+      Fq2 x = ld2(A + ii * FQ2W), y = ld2(A + jj * FQ2W);
+      y = f2sel(ii != jj, f2dbl(y), y);
+      y = f2sel(wrap, f2xi(y), y);
+      x = f2sel(found, x, Fq2::zero());  // coefficients with only three terms add 0 in the fourth slot
+      f2_mac(c, acc, x, y);
+    }
   }
-  Fq2 out = f2_finish(c, acc);
+  Fq2 out;
+  if constexpr (C::W == 3) out = f2_finish(c, acc, 4); else out = f2_finish(c, acc);
   sync(c);
   st2(freg(c, dst) + c.k * FQ2W, out);
   sync(c);
@@ -372,11 +450,17 @@ RIPP_HD void mul_line_body(const C& c, int dst, int a) {
   k3 += w3 ? 6 : 0;
   typename AccOf<C>::type acc;
   acc_zero(acc);
-  f2_mac(c, acc, ld2(A + k * FQ2W), ld2(L));
-  Fq2 d = ld2(L + FQ2W);
-  f2_mac(c, acc, ld2(A + k2 * FQ2W), f2sel(w2, f2xi(d), d));
-  d = ld2(L + 2 * FQ2W);
-  f2_mac(c, acc, ld2(A + k3 * FQ2W), f2sel(w3, f2xi(d), d));
+  if constexpr (C::W == 3) {
+    f2_mac_addr(c, acc, A + k * FQ2W, L, false);
+    f2_mac_addr(c, acc, A + k2 * FQ2W, L + FQ2W, w2);
+    f2_mac_addr(c, acc, A + k3 * FQ2W, L + 2 * FQ2W, w3);
+  } else {
+    f2_mac(c, acc, ld2(A + k * FQ2W), ld2(L));
+    Fq2 d = ld2(L + FQ2W);
+    f2_mac(c, acc, ld2(A + k2 * FQ2W), f2sel(w2, f2xi(d), d));
+    d = ld2(L + 2 * FQ2W);
+    f2_mac(c, acc, ld2(A + k3 * FQ2W), f2sel(w3, f2xi(d), d));
+  }
   Fq2 out = f2_finish(c, acc);
   sync(c);
   st2(freg(c, dst) + k * FQ2W, out);
@@ -457,21 +541,6 @@ template <int K>
 RIPP_HD uint32_t fq_kp(int i) {
   static_assert(K >= 1 && K <= 5, "tabulated multiples of p");
   return K == 1 ? FqParams::p(i) : (K == 2 ? FQ_2P(i) : (K == 3 ? FQ_3P(i) : (K == 4 ? FQ_4P(i) : FQ_5P(i))));
-}
-// acc (12 limbs) += x;  the caller's bound keeps the sum below 2^384
-RIPP_HD void lz_add12(uint32_t* acc, const Fq& x) {
-  using namespace limb;
-  add_cc(acc[0], acc[0], x.v[0]);
-#pragma unroll
-  for (int i = 1; i < 11; i++) addc_cc(acc[i], acc[i], x.v[i]);
-  addc(acc[11], acc[11], x.v[11]);
-}
-RIPP_HD void lz_sub12(uint32_t* acc, const Fq& x) {
-  using namespace limb;
-  sub_cc(acc[0], acc[0], x.v[0]);
-#pragma unroll
-  for (int i = 1; i < 11; i++) subc_cc(acc[i], acc[i], x.v[i]);
-  subc(acc[11], acc[11], x.v[11]);
 }
 template <int K>
 RIPP_HD void lz_addk12(uint32_t* acc) {  // acc += K p

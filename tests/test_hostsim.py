@@ -193,6 +193,16 @@ def test_l18_lazy_sums(hostsim):
         new = hostsim.call("hs_l18_op", 8, ea, ea, out=144)
         ref = hostsim.call("hs_l6_op", 8, ea, ea, out=144)
         assert (new == ref).all()
+    # the eighteen-lane Fq12 product and sparse line product (operands formed by address, xi applied as an unreduced
+    # role operand) against the six-lane bodies on the same patterns
+    for a in pats[:5]:
+        for b in (pats[0], pats[3], pats[4]):
+            ea, eb = C.gt_enc(a), C.gt_enc(b)
+            assert (hostsim.call("hs_l18_op", 0, ea, eb, out=144) == hostsim.call("hs_l6_op", 0, ea, eb, out=144)).all()
+        assert (hostsim.call("hs_l18_op", 1, C.gt_enc(a), C.gt_enc(a), out=144) == hostsim.call("hs_l6_op", 1, C.gt_enc(a), C.gt_enc(a), out=144)).all()
+        d = [C.fq2_enc(x) for x in (pats[0][0], pats[3][1], pats[4][2])]
+        ea = C.gt_enc(a)
+        assert (hostsim.call("hs_l18_mul_line", ea, d[0], d[1], d[2], out=144) == hostsim.call("hs_l6_mul_line", ea, d[0], d[1], d[2], out=144)).all()
 
 
 @pytest.mark.parametrize("eng", ["l6", "l18"])
