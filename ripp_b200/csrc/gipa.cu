@@ -720,6 +720,7 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
   {
     __atomic_store_n(&ctx->rounds_short, 0, __ATOMIC_RELEASE);
     ik->background = 1;
+    kc->background = getenv("RIPP_B200_SSM_FOREGROUND") ? 0 : 1;  // the SSM recursion has slack: its long rounds yield CTAs to the pairing recursion
     std::thread tip([&] {
       // 2 n pairs that nothing waits for: started once the pairing recursion has left its long (throughput-bound) rounds
       while (!__atomic_load_n(&ctx->rounds_short, __ATOMIC_ACQUIRE)) std::this_thread::sleep_for(std::chrono::microseconds(20));
