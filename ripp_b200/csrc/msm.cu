@@ -711,12 +711,14 @@ __global__ void __launch_bounds__(32 * XT_WARPS) k_fold_xt(const Aff<F>* __restr
   Aff<F> o = xt::to_affine<F>(tm, acc);
   if (live && tm.t == 0) out[i] = o;
 }
-// vectors up to this length run on lane teams (RIPP_B200_XT_MAX overrides): 2048 G2 elements are 683 warps, about one
-// per sub-partition
+// vectors up to this length run on lane teams (RIPP_B200_XT_MAX overrides).  Re-measured at the end of round 2 on the 2^12
+// aggregation (profiles/r2zi_last_call_xt_max.json): 67.2 ms at 2048, 64.8 at 1024, 65.8 at 512, 65.2 at 256 -- the four
+// 2048-element folds of the first round (1776 warps of teams in one launch, 3.7 ms) are served better by one thread per
+// element on four streams; from 1024 elements down the teams win.
 static size_t xt_max_n() {
   static const long v = [] {
     const char* e = getenv("RIPP_B200_XT_MAX");
-    return e ? atol(e) : 2048L;
+    return e ? atol(e) : 1024L;
   }();
   return (size_t)v;
 }
