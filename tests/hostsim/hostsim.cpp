@@ -67,8 +67,18 @@ void hs_fq_dot_redc(const uint32_t* a, const uint32_t* b, int k, int subs, uint3
   }
   detail::redc_wide<FqParams>(r, acc, subs);
 }
-// l6.cuh's lazy sums: T (13 limbs, < 32 p) -> T mod p
+// l6.cuh's lazy sums: T (13 limbs, < 2^386) -> T mod p
 void hs_lz_reduce13(const uint32_t* T, uint32_t* r) { st(r, l6::lz_reduce13(T)); }
+// one lane's share of a pass: slots = 8 canonical Fq values (12 words each): P = slots 0.., M = slots 4..;
+// shape 0: <4, 3, 1, HALF> (pass B), 1: <3, 3, 1> (pass F), 2: <2, 1, 12> (pass E)
+void hs_lz_pass(int shape, int half, const uint32_t* slots, uint32_t* r) {
+  const int P[4] = {0, 12, 24, 36}, M[3] = {48, 60, 72};
+  Fq o;
+  if (shape == 0) o = l6::lz_pass<4, 3, 1, true>(slots, P, M, half != 0);
+  else if (shape == 1) o = l6::lz_pass<3, 3, 1, false>(slots, P, M, false);
+  else o = l6::lz_pass<2, 1, 12, false>(slots, P, M, false);
+  st(r, o);
+}
 uint64_t hs_mul_count(int which) { return detail::mul_count_[which]; }
 void hs_mul_count_reset() { detail::mul_count_[0] = detail::mul_count_[1] = 0; }
 // k * P through the GLV / GLS decomposition (endo.cuh); k = 8 canonical words

@@ -183,6 +183,22 @@ def test_l18_lazy_sums(hostsim):
     for t in cases:
         got = C._int(hostsim.call("hs_lz_reduce13", words13(t), out=12))
         assert got == t % E.P, hex(t)
+    # one lane's share of the doubling step's passes: (sum of P slots - sum of M slots) [/ 2] [* 12] mod p on the word
+    # patterns that drive the unreduced sum to its bounds (every slot p - 1, or the added ones p - 1 and the subtracted 0, ...)
+    def fq_words(x):
+        return np.array([(x >> (32 * i)) & 0xFFFFFFFF for i in range(12)], dtype=np.uint32)
+
+    inv2 = pow(2, -1, E.P)
+    hi = E.P - 1
+    slot_sets = [[hi] * 7, [hi] * 4 + [0] * 3, [0] * 4 + [hi] * 3, [0] * 7, [1, 0, 0, 0, 0, 0, 0], [hi, hi, 0, 0, hi, 0, 0]]
+    slot_sets += [[rnd.randrange(E.P) for _ in range(7)] for _ in range(40)]
+    for sl in slot_sets:
+        words = np.concatenate([fq_words(x) for x in sl] + [fq_words(0)])
+        p4, p3, p2, m3, m1 = sum(sl[:4]), sum(sl[:3]), sum(sl[:2]), sum(sl[4:7]), sl[4]
+        assert C._int(hostsim.call("hs_lz_pass", 0, 0, words, out=12)) == (p4 - m3) % E.P
+        assert C._int(hostsim.call("hs_lz_pass", 0, 1, words, out=12)) == (p4 - m3) * inv2 % E.P
+        assert C._int(hostsim.call("hs_lz_pass", 1, 0, words, out=12)) == (p3 - m3) % E.P
+        assert C._int(hostsim.call("hs_lz_pass", 2, 0, words, out=12)) == 12 * (p2 - m1) % E.P
     # the squaring as a polynomial map (any Fq12 input, not only cyclotomic ones): extreme coefficient patterns
     big, mont = E.P - 1, lambda x: x * pow(radix, -1, E.P) % E.P  # mont(x): the value whose Montgomery form is the word pattern x
     pats = [tuple((mont(big), mont(big)) for _ in range(6)), tuple((0, 0) for _ in range(6)),
