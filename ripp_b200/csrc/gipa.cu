@@ -737,6 +737,7 @@ extern "C" int ripp_tipp_aggregate_dev(ripp_ctx* ctx, const void* srs_g1_dev, co
     __atomic_store_n(&ctx->rounds_short, 1, __ATOMIC_RELEASE);  // n < 2 or a failed recursion never reaches the short rounds
     tc.join();
     tip.join();
+    ik->background = kc->background = 0;  // the children are cached on the context: other entry points get them unhinted
   }
   if (st_a != RIPP_OK) return st_a;
   if (st_c != RIPP_OK) return fail(st_c, err_c);
