@@ -210,20 +210,6 @@ RIPP_HD void f2_mac(const C&, Acc3& A, const Fq2& a, const Fq2& b) {
   detail::wide_mul<FqParams>(t, sa, sb);
   detail::wide_add<24>(A.k, t);
 }
-template <class C>
-RIPP_HD void f2_mac(const C& c, Acc1& A, const Fq2& a, const Fq2& b) {
-  uint32_t sa[12], sb[12], u[12], v[12], t[24];
-  add_unreduced(sa, a.c0, a.c1);
-  add_unreduced(sb, b.c0, b.c1);
-  const int r = c.role;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    u[i] = r == 0 ? a.c0.v[i] : (r == 1 ? a.c1.v[i] : sa[i]);
-    v[i] = r == 0 ? b.c0.v[i] : (r == 1 ? b.c1.v[i] : sb[i]);
-  }
-  detail::wide_mul<FqParams>(t, u, v);
-  detail::wide_add<24>(A.s, t);
-}
 // W = 3, operands by ADDRESS (canonical Fq2 values a, b in shared memory): the role's operand pair is formed as an
 // unreduced sum of slots instead of loading both components, reducing xi b and selecting --
 //   u = a0 | a1 | a0 + a1;   v = b0 | b1 | b0 + b1;   with `wrap` (the term carries xi):  v = b0 - b1 + p | b0 + b1 | 2 b0
