@@ -353,3 +353,29 @@ def test_endo_scalar_multiplication(hostsim):
         kw = C.scalar_words(k)
         assert C.g1_dec(hostsim.call("hs_g1_endo_mul", C.g1_enc(p), kw, out=24)) == E.g1_mul(p, k), k
         assert C.g2_dec(hostsim.call("hs_g2_endo_mul", C.g2_enc(q), kw, out=48)) == E.g2_mul(q, k), k
+
+
+@pytest.mark.parametrize("flags", [["-DRIPP_FP_UNSATURATED"], ["-DRIPP_L6_CYC_EAGER"]], ids=lambda f: f[0][2:])
+def test_compile_time_variants(flags):
+    """The retained compile-time A/B arms stay bit-exact: the carry-free (28-bit limb) Montgomery product -- which now also
+    receives the unreduced operands of the lazy sums -- and the eighteen-lane squaring on the generic body."""
+    from conftest import _build_hostsim
+
+    hs = _build_hostsim(flags)
+    a, b = rf(), rf()
+    rinv = pow(1 << 384, -1, E.P)
+    import numpy as np
+
+    w = lambda v: np.array([(v >> (32 * i)) & 0xFFFFFFFF for i in range(12)], dtype=np.uint32)
+    assert C._int(hs.call("hs_fq_mul", w(a), w(b), out=12)) == a * b * rinv % E.P
+    x = rf12()
+    c = E.f12_mul(E.f12_conj(x), E.f12_inv(x))
+    c = E.f12_mul(E.f12_frob(c, 2), c)
+    ec = C.gt_enc(c)
+    for eng in ("l6", "l18"):
+        assert C.gt_dec(hs.call("hs_%s_op" % eng, 8, ec, ec, out=144)) == E.f12_sqr(c)
+        assert C.gt_dec(hs.call("hs_%s_op" % eng, 0, ec, C.gt_enc(x), out=144)) == E.f12_mul(c, x)
+    p, q = E.g1_mul(E.G1_GEN, 321), E.g2_mul(E.G2_GEN, 654)
+    one = np.array([1], dtype=np.int32)
+    got = hs.call("hs_l18_miller", C.g1_enc(p), C.g2_enc(q), one.view(np.uint32), 1, 1, out=144)
+    assert C.gt_dec(got) == E.pairing(p, q)
