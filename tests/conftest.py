@@ -39,7 +39,10 @@ class HostSim:
 
 def _build_hostsim(flags):
     src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
-    so = os.path.join(ROOT, "tests", "hostsim", "_hostsim%s.so" % ("_" + str(abs(hash(tuple(flags))) % 10**6) if flags else ""))
+    import hashlib
+
+    tag = "_" + hashlib.md5(" ".join(flags).encode()).hexdigest()[:8] if flags else ""  # stable across processes
+    so = os.path.join(ROOT, "tests", "hostsim", "_hostsim%s.so" % tag)
     csrc = os.path.join(ROOT, "ripp_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
