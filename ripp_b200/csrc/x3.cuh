@@ -42,8 +42,9 @@ void gather3(const Fq& mine, Fq& t0, Fq& t1, Fq& t2);
 #endif
 
 // The exchanges are CTA barriers (bar.sync, warp-aligned): a warp whose lanes left a per-lane branch -- the patch of an
-// exceptional lane -- must be whole again before it reaches the next one, or its parts arrive separately and the
-// barrier releases early (seen as wrong sums once every lane had its own digits, k_scale_parts_w3).
+// exceptional lane -- must be whole again before it reaches the next one, or its parts may arrive separately and the
+// barrier release early.  With a shared scalar the patch is rare (identity inputs); an experiment with per-lane digits
+// (element-wise scalings on these teams) takes it in most iterations.
 RIPP_HD void reconverge() {
 #if defined(__CUDA_ARCH__)
   __syncwarp();
