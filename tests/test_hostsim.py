@@ -238,6 +238,12 @@ def test_l6_miller_and_final_exp(hostsim, eng):
     valid = np.array([1, 0, 1], dtype=np.int32)
     got = hostsim.call("hs_%s_miller" % eng, C.g1_vec_enc(ps), C.g2_vec_enc(qs), valid.view(np.uint32), 3, 1, out=144)
     assert C.gt_dec(got) == E.multi_pairing([ps[0], ps[2]], [qs[0], qs[2]])
+    # four pairs with full-size random scalars, the third masked
+    ps = [E.g1_mul(E.G1_GEN, rnd.randrange(E.R)) for _ in range(4)]
+    qs = [E.g2_mul(E.G2_GEN, rnd.randrange(E.R)) for _ in range(4)]
+    valid = np.array([1, 1, 0, 1], dtype=np.int32)
+    got = hostsim.call("hs_%s_miller" % eng, C.g1_vec_enc(ps), C.g2_vec_enc(qs), valid.view(np.uint32), 4, 1, out=144)
+    assert C.gt_dec(got) == E.multi_pairing([ps[0], ps[1], ps[3]], [qs[0], qs[1], qs[3]])
 
 
 def test_lazy_sum_of_products(hostsim):
